@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py - TRPL forward simulations per second (nx=128, FP64), BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--sets S]
+
+Workload (config.workload): BASELINE configs[1] - 4096 random parameter sets (log-uniform in the
+prior box of the reference's Inputs/mcmc0.txt, as Dense_Sample/dense_sampling.py:17-35 draws them)
+x the 6 TRPL curves of the staub_MAPI_threepower_twothick example (nx=128, 119 measurement times
+each), 'std' model, PER GPU (weak scaling: every rank evaluates its own 4096 sets).  One "step" is
+one pass of the hot path over that batch: 24576 forward simulations + likelihoods.
+
+value   device-timed throughput, inputs resident in HBM (CUDA events on the library's stream)
+e2e     the same through the public API with HOST numpy buffers (H2D + kernel + D2H inside)
+The JSON line also carries the FP64 roofline of the trajectory kernel and a CPU baseline (the
+oracle port of the reference's numba+SciPy LSODA path, all host cores) timed in the same run.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NAMES = "n0 p0 mu_n mu_p ks Cn Cp Sf Sb tauN tauP eps Tm m".split()
+UNITS = np.array([1e-21, 1e-21, 1e5, 1e5, 1e12, 1e33, 1e33, 0.01, 0.01, 1, 1, 1, 1, 1.0])
+GUESS = np.array([1e8, 3e15, 20, 20, 4.8e-11, 4.4e-29, 4.4e-29, 10, 10, 511, 871, 10, 300, 1.0])
+LO = np.array([1e8, 1e14, 1, 1, 1e-11, 1e-29, 1e-29, 1e-4, 1e-4, 1, 1, 10, 300, 1.0])
+HI = np.array([1e8, 1e16, 100, 100, 1e-9, 1e-27, 1e-27, 1e4, 1e4, 1500, 3000, 10, 300, 1.0])
+IDX = {n: i for i, n in enumerate(NAMES)}
+LENGTHS = [311.0, 2000.0, 311.0, 2000.0, 311.0, 2000.0]
+NX = 128
+SIGMA = 1.0
+RTOL = 1e-7   # the reference's default RTOL (forward_solver.py:18)
+
+# Algorithmic FP64 flops of one integrator step per space node, 'std' model, 4 nodes per lane
+# (FMA = 2, division = 1); the breakdown is derived in DESIGN.md section 5.
+FLOPS_PER_NODE_STEP = 6 * 34 + 72 + 184 + 6 * 50 + 146 + 8   # = 914
+
+
+def workload_inputs():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "staub6.npz"))
+    return g["ini"], g["t"]
+
+
+def draw_states(n_sets, seed):
+    rng = np.random.default_rng(seed)
+    return 10 ** rng.uniform(np.log10(LO), np.log10(HI), size=(n_sets, len(NAMES)))
+
+
+def make_shared_fields(ini, t, vals, uncs):
+    sim = {"num_meas": 6, "lengths": LENGTHS, "nx": [NX] * 6, "meas_types": ["TRPL"] * 6}
+    return {"_sim_info": sim, "_init_params": ini, "_times": [t] * 6, "_vals": vals, "_uncs": uncs,
+            "_param_indexes": IDX, "units": UNITS, "model": "std", "ini_mode": "density", "hmax": 4,
+            "rtol": RTOL, "atol": None, "solver": ("solveivp",)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference path (numba RHS + SciPy LSODA + likelihood)
+# ---------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(ini, t, vals, uncs):
+    # one worker process per core, one thread each: LSODA's dense LU must not spawn BLAS threads
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        _W["tp"] = threadpool_limits(1)
+    except Exception:
+        pass
+    from oracle import trpl_oracle as orc
+    _W.update(orc=orc, ini=ini, t=t, vals=vals, uncs=uncs)
+    sim = {"num_meas": 1, "lengths": [311.0], "nx": [16], "meas_types": ["TRPL"]}
+    tt = np.linspace(0, 1, 3)
+    orc.state_loglik(GUESS, sim, [1e15 * np.ones(16)], [tt], [np.ones(3)], [np.ones(3)], IDX, UNITS,
+                     {"TRPL": 1.0})   # numba JIT warm-up, untimed
+
+
+def _cpu_one(state):
+    orc = _W["orc"]
+    sim = {"num_meas": 6, "lengths": LENGTHS, "nx": [NX] * 6, "meas_types": ["TRPL"] * 6}
+    t = _W["t"]
+    ll, _ = orc.state_loglik(state, sim, _W["ini"], [t] * 6, _W["vals"], _W["uncs"], IDX, UNITS,
+                             {"TRPL": SIGMA}, rtol=None, atol=None)
+    return ll
+
+
+def cpu_throughput(states, ini, t, vals, uncs, cores, pool=None):
+    """sims/s of the CPU path over `states` (6 curves each) with `cores` worker processes."""
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(ini, t, vals, uncs))
+        pool.map(_noop, range(cores * 2))
+    t0 = time.perf_counter()
+    pool.map(_cpu_one, list(states), chunksize=1)
+    dt = time.perf_counter() - t0
+    if own:
+        pool.close()
+    return 6 * len(states) / dt, dt
+
+
+def _noop(i):
+    time.sleep(0.05)
+    return i
+
+
+# ---------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+def allreduce_max(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    tns = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+    return float(tns.item())
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(local)
+
+
+def synth_measurement(ctx_eval, ini, t, rng):
+    """Measurement = simulated curves of the initial guess, log10, renoised (like staub's renoised file)."""
+    sf = make_shared_fields(ini, t, [np.zeros(len(t))] * 6, [np.ones(len(t))] * 6)
+    res = ctx_eval(GUESS[None, :], np.ones(1), {"TRPL": SIGMA}, sf, want_curves=True)
+    cur = res.curves.reshape(6, len(t))
+    vals = [np.log10(cur[m]) + 0.02 * rng.standard_normal(len(t)) for m in range(6)]
+    uncs = [np.full(len(t), 0.02) for _ in range(6)]
+    return vals, uncs
+
+
+def run_ours(args):
+    from metrotrpl_b200 import _capi
+    from metrotrpl_b200 import trial_move_evaluation as tme
+    from metrotrpl_b200.forward_solver import get_context
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    ini, t = workload_inputs()
+    ctx = get_context(local)
+    info = ctx.device_info()
+    rng = np.random.default_rng(1234)
+    vals, uncs = synth_measurement(lambda *a, **k: tme.eval_trial_moves(*a, cache=None, **k), ini, t, rng)
+    sf = make_shared_fields(ini, t, vals, uncs)
+    cache = tme.PathCache(sf, device=local)
+    states = draw_states(args.sets, seed=20261018 + rank)        # every rank its own shard
+    temps = np.ones((args.sets, 3))
+    params, aux = cache.pack(states, {"TRPL": SIGMA}, temps)
+    opts = cache.opts()
+    n_traj = args.sets * 6
+
+    peak_tf, _ = ctx.fp64_peak_probe(40000)
+    launches0 = ctx.launch_count()
+
+    # ---- device-resident throughput -------------------------------------------------------
+    ctx.upload(params, aux)
+    for _ in range(args.warmup):
+        ctx.flush_l2()
+        ctx.run_resident(opts)
+    ctx.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(dist, local)
+    kernel_ms = []
+    l_before = ctx.launch_count()
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ctx.run_resident(opts)
+        kernel_ms.append(ctx.last_kernel_ms())
+    total_ms = ctx.timer_end()
+    gpu_launches = ctx.launch_count() - l_before
+    barrier(dist, local)
+    clocks = sampler.stop() if rank == 0 else None
+    ll, status, nsteps, _ = ctx.download()
+    step_ms = allreduce_max(dist, local, total_ms / args.steps)
+    value = world * n_traj / (step_ms * 1e-3)
+
+    # ---- end to end through the public API (host numpy in, host numpy out) ----------------
+    for _ in range(max(1, args.warmup // 2)):
+        tme.eval_trial_moves(states, temps, {"TRPL": SIGMA}, sf, cache=cache)
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = tme.eval_trial_moves(states, temps, {"TRPL": SIGMA}, sf, cache=cache)
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    e2e_s = allreduce_max(dist, local, e2e_s)
+    e2e_value = world * n_traj / e2e_s
+    h2d = params.nbytes + aux.nbytes
+    d2h = res.per_meas.nbytes + res.status.nbytes + res.nsteps.nbytes
+
+    # ---- roofline of the trajectory kernel (FP64 pipe; HBM traffic is negligible) ----------
+    steps_total = float(nsteps.sum())                               # accepted + rejected
+    flops = steps_total * NX * FLOPS_PER_NODE_STEP
+    k_ms = float(np.mean(kernel_ms))
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    alg_bytes = h2d + d2h + ini.nbytes + 3 * 6 * len(t) * 8
+    roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved / peak_tf, "traffic": None,
+            "peak_source": "in-run DFMA probe (trpl_fp64_peak_probe); B200 nominal FP64 = 37 TFLOP/s; "
+                           "MEASURED_PEAKS.json has no FP64 entry",
+            "kernel": "trpl_forward_kernel<4,std>", "kernel_ms": k_ms,
+            "flops_per_launch": flops, "flops_per_node_step": FLOPS_PER_NODE_STEP,
+            "integrator_steps_per_launch": steps_total,
+            "hbm_algorithmic_bytes_per_launch": alg_bytes,
+            "hbm_gbs_if_all_traffic_were_dram": alg_bytes / (k_ms * 1e-3) / 1e9}
+
+    if rank != 0:
+        return
+    # ---- CPU baseline on the host cores (rank 0, N=1 semantics: a bounded sample) ----------
+    cores = os.cpu_count() or 1
+    n_cpu_sets = max(cores, min(args.cpu_sets, 6 * cores))
+    cpu_states = states[:n_cpu_sets]
+    cpu_val, cpu_dt = cpu_throughput(cpu_states, ini, t, vals, uncs, cores)
+    out = {
+        "metric": "TRPL forward sims/sec (nx=128, FP64)", "value": value, "unit": "sims/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 4096 random parameter sets x 6 TRPL curves "
+                               "(staub_MAPI threepower_twothick), nx=128, std model, per GPU",
+                   "sets_per_gpu": args.sets, "curves_per_set": 6, "times_per_curve": int(len(t)),
+                   "rtol": RTOL, "hmax": "error-controlled (reference hmax not imposed)",
+                   "l2": "flushed between steps (256 MiB memset); inputs are 0.5 MB and L2-resident by design",
+                   "parallelism": f"independent parameter-set shards x{world}, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": {"value": cpu_val, "unit": "sims/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_cpu_sets} of the same parameter sets x 6 curves "
+                                   f"({cpu_dt:.1f} s wall), oracle port of numba RHS + SciPy LSODA + likelihood"},
+        "device": info,
+        "stats": {"mean_steps_per_sim": float(nsteps[..., 0].mean()), "max_steps": int(nsteps[..., 0].max()),
+                  "mean_rejected": float(nsteps[..., 1].mean()),
+                  "frac_floored": float(np.mean((status & 8) != 0)),
+                  "frac_failed": float(np.mean((status & 7) != 0)),
+                  "kernel_ms_each": [float(x) for x in kernel_ms]},
+    }
+    print(json.dumps(out))
+
+
+def run_reference(args):
+    """The reference's CPU path (oracle port: the reference is Python and cannot travel) on all
+    host cores; each step is a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import trpl_oracle as orc
+    ini, t = workload_inputs()
+    rng = np.random.default_rng(1234)
+    sim = {"num_meas": 6, "lengths": LENGTHS, "nx": [NX] * 6, "meas_types": ["TRPL"] * 6}
+    cur = [orc.simulate(ini[m], orc.Grid(LENGTHS[m], NX, t, 4), GUESS, IDX, units=UNITS) for m in range(6)]
+    vals = [np.log10(cur[m]) + 0.02 * rng.standard_normal(len(t)) for m in range(6)]
+    uncs = [np.full(len(t), 0.02) for _ in range(6)]
+    cores = os.cpu_count() or 1
+    per_step = cores * args.ref_sets_per_core
+    states = draw_states(per_step * (args.steps + args.warmup), seed=20261018)
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(ini, t, vals, uncs))
+    pool.map(_noop, range(cores * 2))
+    k = 0
+    for _ in range(args.warmup):
+        cpu_throughput(states[k:k + per_step], ini, t, vals, uncs, cores, pool=pool)
+        k += per_step
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_throughput(states[k:k + per_step], ini, t, vals, uncs, cores, pool=pool)
+        k += per_step
+    dt = time.perf_counter() - t0
+    pool.close()
+    value = 6 * per_step * args.steps / dt
+    out = {"impl": "reference", "metric": "TRPL forward sims/sec (nx=128, FP64)", "value": value,
+           "unit": "sims/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "configs[1] sample: random parameter sets x 6 TRPL curves, nx=128, std model",
+                      "sets_per_step": per_step, "rtol": 1e-7, "atol": 1e-10, "hmax": 4},
+           "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port",
+                            "sample": f"{per_step} parameter sets x 6 curves per step"},
+           "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sets", type=int, default=4096, help="parameter sets per GPU")
+    ap.add_argument("--cpu-sets", type=int, default=48, help="parameter sets in the CPU baseline sample")
+    ap.add_argument("--ref-sets-per-core", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

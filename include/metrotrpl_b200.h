@@ -1,0 +1,133 @@
+/* metrotrpl_b200.h - C ABI of the B200 forward-simulation + likelihood library.
+ *
+ * This is the drop-in boundary for MetroTRPL's data-parallel hot path.  The reference is pure
+ * Python; the binding a maintainer adds is a ctypes stub (shown in INTEGRATION.md) that replaces
+ *
+ *   forward_solver.py:41-203        solve(iniPar, g, state, indexes, meas, units, solver, model,
+ *                                         ini_mode, RTOL, ATOL)          -> trpl_solve_batch
+ *   trial_move_evaluation.py:9-28   eval_trial_move(state, unique_fields, shared_fields, logger)
+ *   trial_move_evaluation.py:30-166 one_sim_likelihood(...)             -> trpl_loglik_batch
+ *   Dense_Sample/dense_sampling.py:42-196 simulate(...) inner loops      -> trpl_loglik_batch
+ *
+ * with whole batches of parameter sets per call instead of one state at a time.
+ * Plain pointers and sizes only; all arrays are C-contiguous float64 / int32 HOST arrays unless a
+ * function name says "resident".  Every function returns 0 on success, non-zero on failure;
+ * trpl_last_error() returns a description.  There is no CPU fallback: without a CUDA device
+ * trpl_create fails.
+ */
+#ifndef METROTRPL_B200_H
+#define METROTRPL_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRPL_ABI_VERSION 1
+#define TRPL_NPARAM 16  /* doubles per parameter set, model units (nm, ns, V) */
+#define TRPL_NAUX 6     /* doubles per trajectory, see below */
+#define TRPL_NTEMP 3    /* likelihoods are returned for three temperatures per trajectory */
+
+/* parameter slots (forward_solver.py:128-138 order; state[indexes[name]] * units) */
+enum trpl_param_slot {
+  TRPL_P_N0 = 0, TRPL_P_P0, TRPL_P_MUN, TRPL_P_MUP, TRPL_P_KS, TRPL_P_CN, TRPL_P_CP, TRPL_P_SF,
+  TRPL_P_SB, TRPL_P_TAUN, TRPL_P_TAUP, TRPL_P_EPS, TRPL_P_TM, TRPL_P_KC, TRPL_P_NT, TRPL_P_TAUE
+};
+/* aux slots, one row per (parameter set, measurement) trajectory */
+enum trpl_aux_slot {
+  TRPL_A_SCALE_SHIFT = 0, /* log10(_s#), trial_move_evaluation.py:52-60 */
+  TRPL_A_S2T0, TRPL_A_S2T1, TRPL_A_S2T2, /* model_uncertainty[meas_type]^2 * T, :150-156 */
+  TRPL_A_FLUENCE_MULT, /* _f# factor, :38-44 */
+  TRPL_A_ABSORB_MULT   /* _a# factor, :45-51 */
+};
+
+enum trpl_model { TRPL_MODEL_STD = 0, TRPL_MODEL_TRAPS = 1 };       /* forward_solver.py:420-423 */
+enum trpl_meas_type { TRPL_MEAS_TRPL = 0, TRPL_MEAS_TRTS = 1 };      /* forward_solver.py:186-203 */
+enum trpl_ini_mode { TRPL_INI_DENSITY = 0, TRPL_INI_FLUENCE = 1 };   /* forward_solver.py:100-117 */
+
+/* status bits per trajectory */
+enum trpl_status {
+  TRPL_ST_OK = 0, TRPL_ST_MAX_STEPS = 1, TRPL_ST_H_UNDERFLOW = 2, TRPL_ST_NONFINITE = 4,
+  TRPL_ST_FLOORED = 8, TRPL_ST_NEG_FRAC = 16, TRPL_ST_NAN_LL = 32
+};
+enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2 };
+
+/* one measurement (sim_info["lengths"/"nx"/"meas_types"][i] + its slice of the data arrays) */
+typedef struct trpl_meas_desc {
+  double thickness;   /* nm */
+  double ini_a;       /* fluence mode: fluence [cm^-2] */
+  double ini_b;       /* fluence mode: absorption coefficient [cm^-1] */
+  int32_t nx;         /* space nodes, 2..256 */
+  int32_t meas_type;  /* trpl_meas_type */
+  int32_t ini_mode;   /* trpl_ini_mode */
+  int32_t ini_dir;    /* fluence mode: <0 reverses the profile */
+  int32_t n_t;        /* measurement times of this curve; times[t_off] must be 0 */
+  int32_t t_off;      /* offset into times / vals / uncs / per-set curves */
+  int32_t prof_off;   /* density mode: offset into profiles (cm^-3, nx values) */
+  int32_t pad_;
+} trpl_meas_desc;
+
+typedef struct trpl_solver_opts {
+  double rtol;        /* relative local tolerance of the Rosenbrock controller (reference RTOL) */
+  double atol;        /* absolute floor [nm^-3]; see DESIGN.md "tolerances" */
+  double hmax;        /* > 0: cap on the step size [ns] (reference "hmax"); <= 0: error control only */
+  int32_t max_steps;  /* accepted + rejected step budget per trajectory */
+  int32_t flags;      /* trpl_opt_flags */
+} trpl_solver_opts;
+
+typedef struct trpl_handle trpl_handle;
+
+const char* trpl_last_error(void);
+int trpl_abi_version(void);
+
+/* Create / destroy a context bound to one CUDA device (one process per GPU). */
+int trpl_create(int device, trpl_handle** out);
+void trpl_destroy(trpl_handle* h);
+int trpl_device_info(trpl_handle* h, int32_t* sm_count, int32_t* sm_clock_khz, char* name, int32_t name_len);
+
+/* Upload the measurement set shared by every parameter set of later calls
+ * (shared_fields["_sim_info"], "_times", "_vals", "_uncs", "_init_params").  vals/uncs may be NULL
+ * when only curves are wanted; profiles may be NULL in fluence mode. */
+int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_meas_desc* meas,
+                     int32_t n_times_total, const double* times, const double* vals,
+                     const double* uncs, int32_t n_profile_total, const double* profiles);
+
+/* Whole-batch likelihood: n_sets parameter sets x n_meas measurements.
+ *   params  [n_sets][TRPL_NPARAM]
+ *   aux     [n_sets][n_meas][TRPL_NAUX]
+ *   logll   [n_sets][n_meas][TRPL_NTEMP]  per-curve log-likelihood (sum over n_meas = eval_trial_move)
+ *   status  [n_sets][n_meas]              trpl_status bits
+ *   nsteps  [n_sets][n_meas][2]           accepted, rejected steps (may be NULL)
+ *   curves  [n_sets][n_times_total]       simulated signals in measurement units (may be NULL)
+ * Host buffers in, host buffers out; H2D and D2H copies happen inside the call. */
+int trpl_loglik_batch(trpl_handle* h, int32_t n_sets, const double* params, const double* aux,
+                      const trpl_solver_opts* opts, double* logll, int32_t* status, int32_t* nsteps,
+                      double* curves);
+
+/* forward_solver.solve() for a batch: curves only (flags |= TRPL_OPT_NO_LIKELIHOOD). */
+int trpl_solve_batch(trpl_handle* h, int32_t n_sets, const double* params, const double* aux,
+                     const trpl_solver_opts* opts, double* curves, int32_t* status, int32_t* nsteps);
+
+/* Split form used for device-resident timing: inputs stay in HBM between runs. */
+int trpl_upload_batch(trpl_handle* h, int32_t n_sets, const double* params, const double* aux);
+int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want_curves);
+int trpl_download_results(trpl_handle* h, double* logll, int32_t* status, int32_t* nsteps, double* curves);
+/* Duration of the last trajectory-kernel launch, CUDA events on the library's stream [ms]. */
+int trpl_last_kernel_ms(trpl_handle* h, float* ms);
+/* Number of kernel launches this context has issued (bench.py's gpu_launches claim). */
+int64_t trpl_launch_count(trpl_handle* h);
+int trpl_synchronize(trpl_handle* h);
+
+/* Bracket a timed region with CUDA events on the library's stream (bench.py: K steps). */
+int trpl_timer_begin(trpl_handle* h);
+int trpl_timer_end(trpl_handle* h, float* ms);
+/* Write a 256 MiB scratch buffer on the library's stream (evicts the 126 MB L2 between steps). */
+int trpl_flush_l2(trpl_handle* h);
+
+/* Dependent-free DFMA stream on every SM: measured FP64 peak for the roofline denominator. */
+int trpl_fp64_peak_probe(trpl_handle* h, int32_t iters, double* tflops, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METROTRPL_B200_H */

@@ -1,0 +1,291 @@
+// model.h - drift-diffusion-recombination right-hand side and its exact block-tridiagonal Jacobian.
+//
+// Physics: the reference's semi-discrete carrier model, forward_solver.py:332-372 (dydt_numba, 'std')
+// and :374-418 (dydt_numba_traps).  The reference integrates [N, P, E] with dE/dt = -Lambda (Jn+Jp).
+// Because Jn+Jp vanishes on both contacts, E stays equal to Gauss's law (E_field(),
+// forward_solver.py:26-38) for all time, so the same trajectory is described by
+//
+//     u_i = ( N_i , Q_{i+1} ),   Q_k = sum_{j<k} (P_j - N_j [- Ntrap_j] - (p0 - n0))   (running net charge)
+//     E_k = Lambda * dx * Q_k ,  P_i = N_i [+ Ntrap_i] + (p0 - n0) + Q_{i+1} - Q_i
+//
+// In these variables every equation touches only nodes i-1, i, i+1: the Jacobian is block
+// tridiagonal with 2x2 blocks, which is what the in-warp solver (blocktri.h) factorises.
+//
+// Node ownership: lane l owns the NPL consecutive nodes i = l*NPL + j, j = 0..NPL-1.  Nodes with
+// i >= L are padding (frozen, decoupled).
+#pragma once
+#include "simt.h"
+
+namespace trpl {
+using namespace simt;
+
+// Parameter vector layout (model units: nm, ns, V), one per parameter set.  The host mirror fills
+// it from `state * units` exactly as forward_solver.py:119-138 does.
+enum ParamSlot {
+  P_N0 = 0, P_P0, P_MUN, P_MUP, P_KS, P_CN, P_CP, P_SF, P_SB, P_TAUN, P_TAUP, P_EPS, P_TM,
+  P_KC, P_NT, P_TAUE, NPARAM = 16
+};
+
+constexpr double KB_EV = 8.61773e-5;                 // forward_solver.py:24
+constexpr double EPS0_NM = 8.854 * 1e-12 * 1e-9;     // forward_solver.py:21
+constexpr double Q_COULOMB = 1.602e-19;              // forward_solver.py:23
+
+enum Model { MODEL_STD = 0, MODEL_TRAPS = 1 };
+enum MeasType { MEAS_TRPL = 0, MEAS_TRTS = 1 };
+
+// warp-uniform coefficients derived once per trajectory
+struct Coef {
+  double n0, p0, d0;          // d0 = p0 - n0
+  double an, ap;              // mu/2
+  double dn, dp;              // mu * kB*T / dx
+  double ld;                  // Lambda * dx  (E_k = ld * Q_k)
+  double ix;                  // 1/dx
+  double ks, cn, cp, taun, taup, sf, sb, n0p0;
+  double kc, nt, itaue;       // traps
+  double mun, mup;            // for the TRTS readout
+  double dx;
+  int L;                      // real node count
+};
+
+TRPL_FN Coef make_coef(const double* p, double thickness, int L) {
+  Coef c;
+  c.L = L;
+  c.dx = thickness / L;                                   // sim_utils.py:268
+  c.ix = 1.0 / c.dx;
+  c.n0 = p[P_N0]; c.p0 = p[P_P0]; c.d0 = c.p0 - c.n0; c.n0p0 = c.n0 * c.p0;
+  const double kT = KB_EV * p[P_TM];
+  c.mun = p[P_MUN]; c.mup = p[P_MUP];
+  c.an = 0.5 * p[P_MUN]; c.ap = 0.5 * p[P_MUP];
+  c.dn = p[P_MUN] * kT * c.ix; c.dp = p[P_MUP] * kT * c.ix;
+  c.ld = (Q_COULOMB / (p[P_EPS] * EPS0_NM)) * c.dx;       // forward_solver.py:131
+  c.ks = p[P_KS]; c.cn = p[P_CN]; c.cp = p[P_CP];
+  c.taun = p[P_TAUN]; c.taup = p[P_TAUP]; c.sf = p[P_SF]; c.sb = p[P_SB];
+  c.kc = p[P_KC]; c.nt = p[P_NT]; c.itaue = 1.0 / p[P_TAUE];
+  return c;
+}
+
+// Per-lane node classification (constant for a trajectory).
+template <int NPL>
+struct NodeMask {
+  mask real_node[NPL];   // i <  L
+  mask last_node[NPL];   // i == L-1
+  mask inner_face[NPL];  // right face of node i is an interior face (i < L-1)
+  mask first_lane;       // lane 0 (owns node 0)
+};
+
+template <int NPL>
+TRPL_FN NodeMask<NPL> make_mask(int L) {
+  NodeMask<NPL> m;
+  const ivec base = imul(lane_id(), NPL);
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const ivec i = iadd(base, j);
+    m.real_node[j] = i < L;
+    m.last_node[j] = i == (L - 1);
+    m.inner_face[j] = i < (L - 1);
+  }
+  m.first_lane = lane_id() == 0;
+  return m;
+}
+
+// One per-lane state slice.  NT is only used by the traps model.
+template <int NPL, int MODEL>
+struct Vec {
+  real n[NPL];
+  real q[NPL];
+  real t[MODEL == MODEL_TRAPS ? NPL : 1];
+};
+
+// Everything the RHS computes that later stages want to reuse.
+template <int NPL>
+struct RhsAux {
+  real p[NPL];     // hole density
+};
+
+// Right-hand side f(u).  Also returns P for the readout / error scale.
+template <int NPL, int MODEL>
+TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u,
+                 Vec<NPL, MODEL>& f, RhsAux<NPL>& aux) {
+  // left running charge of my first node comes from my left neighbour
+  real ql0 = shfl_up(u.q[NPL - 1], 1);
+  ql0 = sel(m.first_lane, 0.0, ql0);
+  real P[NPL];
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const real ql = (j == 0) ? ql0 : u.q[j - 1];
+    P[j] = u.n[j] + c.d0 + (u.q[j] - ql);
+    if (MODEL == MODEL_TRAPS) P[j] = P[j] + u.t[j];
+    aux.p[j] = P[j];
+  }
+  const real n_next = shfl_down(u.n[0], 1);
+  const real p_next = shfl_down(P[0], 1);
+
+  // node-local recombination, and the surface term of whichever contact this lane owns
+  real np_ex[NPL], loss[NPL];
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    np_ex[j] = fmadd(u.n[j], P[j], -c.n0p0);
+    const real inv = rcp(fmadd(c.taun, P[j], c.taup * u.n[j]));
+    const real rate = fmadd(c.cn, u.n[j], fmadd(c.cp, P[j], c.ks)) + inv;
+    loss[j] = rate * np_ex[j];
+  }
+  // one division serves both contacts: lane 0 evaluates the front (node 0), the lane holding node
+  // L-1 the back.  NPL is chosen minimal by the host so these are different lanes.
+  real bn = u.n[0], bp = P[0], bx = np_ex[0];
+  mask has_last = mconst(false);
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    bn = sel(m.last_node[j], u.n[j], bn);
+    bp = sel(m.last_node[j], P[j], bp);
+    bx = sel(m.last_node[j], np_ex[j], bx);
+    has_last = mor(has_last, m.last_node[j]);
+  }
+  const real svel = sel(has_last, c.sb, c.sf);
+  const real surf = svel * bx * rcp(bn + bp);       // forward_solver.py:346-347
+
+  // right-face currents of my nodes
+  real jn[NPL], jsum[NPL];
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const real nn = (j == NPL - 1) ? n_next : u.n[j + 1];
+    const real pn = (j == NPL - 1) ? p_next : P[j + 1];
+    const real e = c.ld * u.q[j];
+    real a = fmadd(c.an * (u.n[j] + nn), e, c.dn * (nn - u.n[j]));      // forward_solver.py:356-357
+    real b = fmadd(c.ap * (P[j] + pn), e, -(c.dp * (pn - P[j])));       // forward_solver.py:358-359
+    // back contact: Jn = -S, Jp = +S (sum exactly zero); padding: no current
+    a = sel(m.inner_face[j], a, sel(m.last_node[j], -surf, 0.0));
+    jn[j] = a;
+    jsum[j] = sel(m.inner_face[j], a + b, 0.0);
+  }
+  if (MODEL != MODEL_TRAPS) f.t[0] = splat(0.0);
+  real jl0 = shfl_up(jn[NPL - 1], 1);
+  jl0 = sel(m.first_lane, surf, jl0);                                   // forward_solver.py:349
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const real jl = (j == 0) ? jl0 : jn[j - 1];
+    real fn = fmadd(c.ix, jn[j] - jl, -loss[j]);                        // forward_solver.py:369
+    real fq = -(c.ix * jsum[j]);                                        // forward_solver.py:363 (/ (Lambda dx))
+    if (MODEL == MODEL_TRAPS) {
+      const real capture = c.kc * u.n[j] * (c.nt - u.t[j]);             // forward_solver.py:410
+      const real release = u.t[j] * c.itaue;                            // forward_solver.py:411
+      fn = fn + (release - capture);
+      f.t[j] = sel(m.real_node[j], capture - release, 0.0);
+    }
+    f.n[j] = sel(m.real_node[j], fn, 0.0);
+    f.q[j] = fq;
+  }
+}
+
+// 2x2 block, row-major {a00, a01, a10, a11}
+struct Blk { real a00, a01, a10, a11; };
+
+// Jacobian blocks of f with respect to u (traps: the Ntrap unknown is condensed out by the caller,
+// see trajectory.h; here we return the extra couplings it needs).
+template <int NPL>
+struct JacTraps {
+  real fn_t[NPL];   // d fN / d Ntrap   (total, including through P)
+  real fq_t[NPL];   // d fQ_{i+1} / d Ntrap_i
+  real fq_tn[NPL];  // d fQ_{i+1} / d Ntrap_{i+1}
+  real ft_n[NPL];   // d fT / d N
+  real ft_t[NPL];   // d fT / d Ntrap
+};
+
+template <int NPL, int MODEL>
+TRPL_FN void jacobian(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u,
+                      const RhsAux<NPL>& aux, Blk (&A)[NPL], Blk (&B)[NPL], Blk (&C)[NPL],
+                      JacTraps<NPL>& jt) {
+  const real* P = aux.p;
+  real ql0 = shfl_up(u.q[NPL - 1], 1);
+  ql0 = sel(m.first_lane, 0.0, ql0);
+  const real n_prev = shfl_up(u.n[NPL - 1], 1);
+  const real n_next = shfl_down(u.n[0], 1);
+  const real p_next = shfl_down(P[0], 1);
+
+  // contact term partials (one lane each, same trick as in rhs)
+  real bn = u.n[0], bp = P[0];
+  mask has_last = mconst(false);
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    bn = sel(m.last_node[j], u.n[j], bn);
+    bp = sel(m.last_node[j], P[j], bp);
+    has_last = mor(has_last, m.last_node[j]);
+  }
+  const real svel = sel(has_last, c.sb, c.sf);
+  const real isum = rcp(bn + bp);
+  const real bx = fmadd(bn, bp, -c.n0p0);
+  const real common = bx * isum * isum;
+  const real s_n = svel * (bp * isum - common);   // dS/dN at fixed P
+  const real s_p = svel * (bn * isum - common);   // dS/dP at fixed N
+
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const real nj = u.n[j], pj = P[j];
+    const real ql = (j == 0) ? ql0 : u.q[j - 1];
+    const real nm = (j == 0) ? n_prev : u.n[j - 1];
+    const real nn = (j == NPL - 1) ? n_next : u.n[j + 1];
+    const real pn = (j == NPL - 1) ? p_next : P[j + 1];
+    // recombination partials
+    const real npx = fmadd(nj, pj, -c.n0p0);
+    const real inv = rcp(fmadd(c.taun, pj, c.taup * nj));
+    const real rate = fmadd(c.cn, nj, fmadd(c.cp, pj, c.ks)) + inv;
+    const real inv2 = inv * inv;
+    const real r_n = fmadd(c.cn - c.taup * inv2, npx, rate * pj);
+    const real r_p = fmadd(c.cp - c.taun * inv2, npx, rate * nj);
+    // right face (between i and i+1), interior form
+    const real er = c.ld * u.q[j];
+    real jr_ni = fmadd(c.an, er, -c.dn);            // d jnR / d N_i
+    real jr_nn = fmadd(c.an, er, c.dn);             // d jnR / d N_{i+1}
+    real jr_q = c.an * (nj + nn) * c.ld;            // d jnR / d Q_{i+1}
+    real jr_pi = splat(0.0);                        // d jnR / d P_i (only through the back contact)
+    real jp_pi = fmadd(c.ap, er, c.dp);             // d jpR / d P_i
+    real jp_pn = fmadd(c.ap, er, -c.dp);            // d jpR / d P_{i+1}
+    real jp_q = c.ap * (pj + pn) * c.ld;            // d jpR / d Q_{i+1} (explicit field)
+    // back contact replaces the right face of node L-1: jnR = -S(N_i, P_i)
+    jr_ni = sel(m.inner_face[j], jr_ni, sel(m.last_node[j], -s_n, 0.0));
+    jr_pi = sel(m.last_node[j], -s_p, jr_pi);
+    jr_nn = sel(m.inner_face[j], jr_nn, 0.0);
+    jr_q = sel(m.inner_face[j], jr_q, 0.0);
+    // left face (between i-1 and i)
+    const real el = c.ld * ql;
+    real jl_nm = fmadd(c.an, el, -c.dn);            // d jnL / d N_{i-1}
+    real jl_ni = fmadd(c.an, el, c.dn);             // d jnL / d N_i
+    real jl_q = c.an * (nm + nj) * c.ld;            // d jnL / d Q_i
+    real jl_pi = splat(0.0);
+    if (j == 0) {                                   // front contact: jnL = +S(N_0, P_0)
+      jl_nm = sel(m.first_lane, 0.0, jl_nm);
+      jl_q = sel(m.first_lane, 0.0, jl_q);
+      jl_ni = sel(m.first_lane, s_n, jl_ni);
+      jl_pi = sel(m.first_lane, s_p, jl_pi);
+    }
+    // chain coefficient of P_i in fN_i
+    const real c_p = fmadd(c.ix, jr_pi - jl_pi, -r_p);
+    real b00 = fmadd(c.ix, jr_ni - jl_ni, -r_n) + c_p;
+    real b01 = fmadd(c.ix, jr_q, c_p);
+    real a00 = -(c.ix * jl_nm);
+    real a01 = -fmadd(c.ix, jl_q, c_p);
+    real c00 = c.ix * jr_nn;
+    // fQ_{i+1} = -ix (jnR + jpR) on interior faces, identically zero otherwise
+    real b10 = -(c.ix * (jr_ni + jp_pi));
+    real b11 = -(c.ix * (jr_q + jp_pi - jp_pn + jp_q));
+    real a11 = c.ix * jp_pi;
+    real c10 = -(c.ix * (jr_nn + jp_pn));
+    real c11 = -(c.ix * jp_pn);
+    b10 = sel(m.inner_face[j], b10, 0.0);
+    b11 = sel(m.inner_face[j], b11, 0.0);
+    a11 = sel(m.inner_face[j], a11, 0.0);
+    c10 = sel(m.inner_face[j], c10, 0.0);
+    c11 = sel(m.inner_face[j], c11, 0.0);
+    if (MODEL == MODEL_TRAPS) {
+      const real cap_n = c.kc * (c.nt - u.t[j]);    // d capture / d N
+      const real cap_t = -(c.kc * nj);              // d capture / d Ntrap
+      b00 = b00 - cap_n;
+      // Ntrap enters fN directly (release - capture) and through P_i (+1)
+      jt.fn_t[j] = sel(m.real_node[j], (c.itaue - cap_t) + c_p, 0.0);
+      jt.fq_t[j] = sel(m.inner_face[j], -(c.ix * jp_pi), 0.0);
+      jt.fq_tn[j] = sel(m.inner_face[j], -(c.ix * jp_pn), 0.0);
+      jt.ft_n[j] = sel(m.real_node[j], cap_n, 0.0);
+      jt.ft_t[j] = sel(m.real_node[j], cap_t - c.itaue, 0.0);
+    }
+    // padding nodes are frozen
+    A[j].a00 = sel(m.real_node[j], a00, 0.0); A[j].a01 = sel(m.real_node[j], a01, 0.0);
+    A[j].a10 = splat(0.0);                     A[j].a11 = a11;
+    B[j].a00 = sel(m.real_node[j], b00, 0.0); B[j].a01 = sel(m.real_node[j], b01, 0.0);
+    B[j].a10 = b10;                            B[j].a11 = b11;
+    C[j].a00 = sel(m.real_node[j], c00, 0.0); C[j].a01 = splat(0.0);
+    C[j].a10 = c10;                            C[j].a11 = c11;
+  }
+}
+
+}  // namespace trpl

@@ -1,0 +1,187 @@
+// simt.h - the one-warp SIMT vocabulary the trajectory integrator is written in.
+//
+// The integrator (trajectory.h and the headers it includes) is written once against this
+// vocabulary: `real` is "one double per lane", `mask` is "one predicate per lane", control flow
+// is warp-uniform, and all cross-lane traffic goes through shfl_* / warp_* / ballot.
+//
+//   * Device build (nvcc, sm_100a): real == double, every function is a forced-inline wrapper
+//     around the warp intrinsic it names.  This is the product.
+//   * Host lock-step build (-DTRPL_HOST_EMU, g++): real is a 32-wide array with overloaded
+//     arithmetic, shuffles are permutations.  It exists so tests/ can run the very same
+//     integrator source on a CPU-only box; it is compiled only by tests/emu and is never
+//     reachable from the metrotrpl_b200 package.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(TRPL_HOST_EMU)
+// ------------------------------------------------------------------------------------------
+// device
+// ------------------------------------------------------------------------------------------
+#define TRPL_FN __device__ __forceinline__
+#define TRPL_UNROLL _Pragma("unroll")
+
+namespace simt {
+typedef double real;
+typedef bool mask;
+typedef int ivec;
+constexpr unsigned FULL = 0xffffffffu;
+
+TRPL_FN ivec lane_id() { return (int)(threadIdx.x & 31u); }
+TRPL_FN real splat(double x) { return x; }
+TRPL_FN double uni(real x) { return x; }                 // x is known to be warp-uniform
+TRPL_FN double lane0(real x) { return __shfl_sync(FULL, x, 0); }
+TRPL_FN real shfl_up(real x, int d) { return __shfl_up_sync(FULL, x, d); }     // from lane-d (own if out of range)
+TRPL_FN real shfl_down(real x, int d) { return __shfl_down_sync(FULL, x, d); } // from lane+d (own if out of range)
+TRPL_FN real shfl_idx(real x, int src) { return __shfl_sync(FULL, x, src); }
+TRPL_FN real sel(mask m, real a, real b) { return m ? a : b; }
+TRPL_FN ivec seli(mask m, ivec a, ivec b) { return m ? a : b; }
+TRPL_FN mask mand(mask a, mask b) { return a && b; }
+TRPL_FN mask mor(mask a, mask b) { return a || b; }
+TRPL_FN mask mnot(mask a) { return !a; }
+TRPL_FN mask mconst(bool b) { return b; }
+TRPL_FN bool warp_any(mask m) { return __any_sync(FULL, m) != 0; }
+TRPL_FN unsigned warp_ballot(mask m) { return __ballot_sync(FULL, m); }
+TRPL_FN mask lane_lt(ivec l, int k) { return l < k; }
+TRPL_FN real fmadd(real a, real b, real c) { return fma(a, b, c); }
+TRPL_FN real rcp(real x) { return 1.0 / x; }
+TRPL_FN real vabs(real x) { return fabs(x); }
+TRPL_FN real vmax(real a, real b) { return fmax(a, b); }
+TRPL_FN real vmin(real a, real b) { return fmin(a, b); }
+TRPL_FN real vexp(real x) { return exp(x); }
+TRPL_FN real vlog(real x) { return log(x); }
+TRPL_FN real vlog10(real x) { return log10(x); }
+TRPL_FN real vsqrt(real x) { return sqrt(x); }
+TRPL_FN mask is_nan(real x) { return x != x; }
+TRPL_FN real warp_sum(real x) {
+  TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+  return x;  // bit-identical on every lane (fp add is commutative)
+}
+TRPL_FN real warp_max(real x) {
+  TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
+  return x;
+}
+// inclusive prefix sum over lanes (Gauss's law: E-field from the running net charge)
+TRPL_FN real warp_scan_incl(real x) {
+  const int l = lane_id();
+  TRPL_UNROLL for (int o = 1; o < 32; o <<= 1) {
+    real y = __shfl_up_sync(FULL, x, o);
+    if (l >= o) x += y;
+  }
+  return x;
+}
+TRPL_FN real gather(const double* p, ivec idx, mask m, double other) { return m ? p[idx] : other; }
+TRPL_FN void scatter(double* p, ivec idx, mask m, real v) { if (m) p[idx] = v; }
+TRPL_FN ivec iadd(ivec a, int b) { return a + b; }
+TRPL_FN ivec imul(ivec a, int b) { return a * b; }
+TRPL_FN ivec irsub(int a, ivec b) { return a - b; }
+TRPL_FN real to_real(ivec a) { return (double)a; }
+
+// per-warp scratch in shared memory, slot-major: slot s of lane l lives at base[s*32 + l]
+struct LaneMem {
+  double* base;
+  TRPL_FN real ld(int slot) const { return base[slot * 32 + (threadIdx.x & 31u)]; }
+  TRPL_FN void st(int slot, real v) const { base[slot * 32 + (threadIdx.x & 31u)] = v; }
+};
+TRPL_FN void warp_sync() { __syncwarp(); }
+}  // namespace simt
+
+#else
+// ------------------------------------------------------------------------------------------
+// host lock-step emulation (tests only)
+// ------------------------------------------------------------------------------------------
+#include <vector>
+#include <algorithm>
+#define TRPL_FN inline
+#define TRPL_UNROLL
+
+namespace simt {
+struct real {
+  double v[32];
+  real() {}
+  real(double x) { for (int i = 0; i < 32; ++i) v[i] = x; }
+};
+struct mask { bool v[32]; };
+struct ivec { int v[32]; };
+
+#define TRPL_BIN(op)                                                                          \
+  inline real operator op(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b.v[i]; return r; } \
+  inline real operator op(const real& a, double b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b; return r; }           \
+  inline real operator op(double a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a op b.v[i]; return r; }
+TRPL_BIN(+) TRPL_BIN(-) TRPL_BIN(*) TRPL_BIN(/)
+#undef TRPL_BIN
+inline real operator-(const real& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = -a.v[i]; return r; }
+inline real& operator+=(real& a, const real& b) { for (int i = 0; i < 32; ++i) a.v[i] += b.v[i]; return a; }
+inline real& operator-=(real& a, const real& b) { for (int i = 0; i < 32; ++i) a.v[i] -= b.v[i]; return a; }
+inline real& operator*=(real& a, const real& b) { for (int i = 0; i < 32; ++i) a.v[i] *= b.v[i]; return a; }
+#define TRPL_CMP(op)                                                                          \
+  inline mask operator op(const real& a, const real& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b.v[i]; return r; } \
+  inline mask operator op(const real& a, double b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b; return r; }
+TRPL_CMP(<) TRPL_CMP(<=) TRPL_CMP(>) TRPL_CMP(>=) TRPL_CMP(!=) TRPL_CMP(==)
+#undef TRPL_CMP
+#define TRPL_ICMP(op)                                                                         \
+  inline mask operator op(const ivec& a, int b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b; return r; } \
+  inline mask operator op(const ivec& a, const ivec& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b.v[i]; return r; }
+TRPL_ICMP(<) TRPL_ICMP(<=) TRPL_ICMP(>) TRPL_ICMP(>=) TRPL_ICMP(==) TRPL_ICMP(!=)
+#undef TRPL_ICMP
+
+inline ivec lane_id() { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i; return r; }
+inline real splat(double x) { return real(x); }
+inline double uni(const real& x) { return x.v[0]; }
+inline double lane0(const real& x) { return x.v[0]; }
+inline real shfl_up(const real& x, int d) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (i - d >= 0) ? x.v[i - d] : x.v[i]; return r; }
+inline real shfl_down(const real& x, int d) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (i + d < 32) ? x.v[i + d] : x.v[i]; return r; }
+inline real shfl_idx(const real& x, int s) { return real(x.v[s]); }
+inline real sel3(const mask& m, const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
+template <class A, class B> inline real sel(const mask& m, const A& a, const B& b) { return sel3(m, real(a), real(b)); }
+inline ivec seli(const mask& m, const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
+inline mask mand(const mask& a, const mask& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] && b.v[i]; return r; }
+inline mask mor(const mask& a, const mask& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] || b.v[i]; return r; }
+inline mask mnot(const mask& a) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = !a.v[i]; return r; }
+inline mask mconst(bool b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = b; return r; }
+inline bool warp_any(const mask& m) { for (int i = 0; i < 32; ++i) if (m.v[i]) return true; return false; }
+inline unsigned warp_ballot(const mask& m) { unsigned b = 0; for (int i = 0; i < 32; ++i) if (m.v[i]) b |= (1u << i); return b; }
+inline mask lane_lt(const ivec& l, int k) { return l < k; }
+inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
+template <class A, class B, class C> inline real fmadd(const A& a, const B& b, const C& c) { return fmadd3(real(a), real(b), real(c)); }
+inline real rcp(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
+#define TRPL_UN(name, expr) inline real name(const real& x) { real r; for (int i = 0; i < 32; ++i) { double a = x.v[i]; r.v[i] = (expr); } return r; }
+TRPL_UN(vabs, fabs(a)) TRPL_UN(vexp, exp(a)) TRPL_UN(vlog, log(a)) TRPL_UN(vlog10, log10(a)) TRPL_UN(vsqrt, sqrt(a))
+#undef TRPL_UN
+inline real vmax2(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fmax(a.v[i], b.v[i]); return r; }
+inline real vmin2(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fmin(a.v[i], b.v[i]); return r; }
+template <class A, class B> inline real vmax(const A& a, const B& b) { return vmax2(real(a), real(b)); }
+template <class A, class B> inline real vmin(const A& a, const B& b) { return vmin2(real(a), real(b)); }
+inline mask is_nan(const real& x) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = (x.v[i] != x.v[i]); return r; }
+inline real warp_sum(real x) {
+  for (int o = 16; o > 0; o >>= 1) { real y; for (int i = 0; i < 32; ++i) y.v[i] = x.v[i] + x.v[i ^ o]; x = y; }
+  return x;
+}
+inline real warp_max(real x) {
+  for (int o = 16; o > 0; o >>= 1) { real y; for (int i = 0; i < 32; ++i) y.v[i] = fmax(x.v[i], x.v[i ^ o]); x = y; }
+  return x;
+}
+inline real warp_scan_incl(real x) {
+  for (int o = 1; o < 32; o <<= 1) { real y = x; for (int i = o; i < 32; ++i) y.v[i] = x.v[i] + x.v[i - o]; x = y; }
+  return x;
+}
+inline real gather(const double* p, const ivec& idx, const mask& m, double other) {
+  real r; for (int i = 0; i < 32; ++i) r.v[i] = m.v[i] ? p[idx.v[i]] : other; return r;
+}
+inline void scatter(double* p, const ivec& idx, const mask& m, const real& v) {
+  for (int i = 0; i < 32; ++i) if (m.v[i]) p[idx.v[i]] = v.v[i];
+}
+inline ivec iadd(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] + b; return r; }
+inline ivec imul(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] * b; return r; }
+inline ivec irsub(int a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a - b.v[i]; return r; }
+inline real to_real(const ivec& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (double)a.v[i]; return r; }
+
+struct LaneMem {
+  std::vector<real> slots;
+  explicit LaneMem(int n) : slots(n) {}
+  real ld(int slot) const { return slots[slot]; }
+  void st(int slot, const real& v) { slots[slot] = v; }
+};
+inline void warp_sync() {}
+}  // namespace simt
+#endif

@@ -1,0 +1,546 @@
+// trajectory.h - one (parameter set, measurement) trajectory, start to finish, inside one warp:
+// initial condition -> adaptive RODAS4 time integration -> PL/TRTS readout at the measurement
+// times -> log-likelihood against the measurement.  Replaces, for one trajectory,
+//   forward_solver.py:41-203   solve()            (init, LSODA integration, PL readout, min_y floor)
+//   trial_move_evaluation.py:96-166 one_sim_likelihood() (abs/negative test, log10 residual, sum)
+//
+// Integrator: RODAS4 (Hairer & Wanner, Solving ODEs II, sec. IV.7/IV.10; 6 stages, order 4(3),
+// stiffly accurate, L-stable, gamma = 1/4), exact Jacobian every step, error = 6th stage.
+// The coefficient set is verified against the order conditions in tools/proto/check_rodas_coeffs.py.
+// Step control: Gustafsson predictive controller, all norms reduced with warp shuffles.
+// Output: quintic Hermite interpolation of ln(signal) through the last three step points
+// (value + time derivative, both by warp reductions), evaluated by the lanes in parallel.
+#pragma once
+#include <float.h>
+#include "simt.h"
+#include "model.h"
+#include "blocktri.h"
+
+namespace trpl {
+using namespace simt;
+
+#if defined(TRPL_FN) && defined(__CUDACC__) && !defined(TRPL_HOST_EMU)
+#define TRPL_CONST __constant__ const
+#else
+#define TRPL_CONST static const
+#endif
+
+// RODAS4 in the Hairer-Wanner "transformed" form:
+//   (1/(gamma h) I - J) K_i = f(u + sum_j a_ij K_j) + sum_j (c_ij / h) K_j ,  u_new = u + sum m_i K_i
+TRPL_CONST double RODAS4_A[6][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.1544000000000000e+01, 0, 0, 0, 0, 0},
+    {0.9466785280815826e+00, 0.2557011698983284e+00, 0, 0, 0, 0},
+    {0.3314825187068521e+01, 0.2896124015972201e+01, 0.9986419139977817e+00, 0, 0, 0},
+    {0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 0, 0},
+    {0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 1.0, 0}};
+TRPL_CONST double RODAS4_C[6][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {-0.5668800000000000e+01, 0, 0, 0, 0, 0},
+    {-0.2430093356833875e+01, -0.2063599157091915e+00, 0, 0, 0, 0},
+    {-0.1073529058151375e+00, -0.9594562251023355e+01, -0.2047028614809616e+02, 0, 0, 0},
+    {0.7496443313967647e+01, -0.1024680431464352e+02, -0.3399990352819905e+02, 0.1170890893206160e+02, 0, 0},
+    {0.8083246795921522e+01, -0.7981132988064893e+01, -0.3152159432874371e+02, 0.1631930543123136e+02,
+     -0.6058818238834054e+01, 0}};
+constexpr double RODAS4_GAMMA = 0.25;
+
+enum StatusBits {
+  ST_OK = 0,
+  ST_MAX_STEPS = 1,     // step budget exhausted before the last measurement time
+  ST_H_UNDERFLOW = 2,   // step size collapsed
+  ST_NONFINITE = 4,     // NaN/Inf state
+  ST_FLOORED = 8,       // signal fell below DBL_MIN and was floored (forward_solver.py:190-192)
+  ST_NEG_FRAC = 16,     // too many negative values (trial_move_evaluation.py:117-123) -> -inf
+  ST_NAN_LL = 32        // likelihood was NaN -> -inf (trial_move_evaluation.py:159-165)
+};
+
+enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2 };
+
+struct SolverOpts {
+  double rtol, atol;
+  double hmax;          // <= 0: steps limited by the error controller only
+  int max_steps;
+  int flags;
+};
+
+// one measurement (shared by every parameter set)
+struct MeasDesc {
+  double thickness;
+  double ini_a, ini_b;   // fluence mode: fluence [cm^-2], absorption [cm^-1]
+  int nx;
+  int meas_type;         // MeasType
+  int ini_mode;          // 0 density profile, 1 fluence/absorption/direction
+  int ini_dir;           // fluence mode: <0 reverses the profile
+  int n_t;               // number of measurement times (times[0] == 0)
+  int t_off;             // offset of this measurement in times/vals/uncs
+  int prof_off;          // offset of this measurement's profile (density mode)
+  int pad_;
+};
+
+struct TrajIn {
+  const double* par;     // TRPL_NPARAM model-unit parameters
+  const MeasDesc* md;
+  const double* times;   // [n_t]
+  const double* vals;    // [n_t] log10 measurement (may be null with OPT_NO_LIKELIHOOD)
+  const double* uncs;    // [n_t]
+  const double* profile; // [nx] cm^-3 (density mode)
+  double scale_shift;    // log10 of the curve's scale factor
+  double s2T[3];         // model_uncertainty^2 * T for up to three temperatures
+  double fl_mult, al_mult;
+  double* curve;         // optional [n_t] simulated signal in measurement units
+};
+
+struct TrajOut {
+  double logll[3];
+  int status, n_acc, n_rej;
+};
+
+// shared-memory slot budget of one warp
+template <int NPL, int MODEL>
+struct Slots {
+  static constexpr int NC = (MODEL == MODEL_TRAPS) ? 3 : 2;   // unknowns per node
+  static constexpr int KSTRIDE = NC * NPL;
+  static constexpr int KBASE = 0;
+  static constexpr int NKS = 5;                                // stages kept (the 6th is consumed in registers)
+  static constexpr int FAC = KBASE + NKS * KSTRIDE;
+  static constexpr int TRAP = FAC + FacSlots<NPL>::COUNT;      // traps: 5 condensation coefficients per node
+  static constexpr int COUNT = TRAP + ((MODEL == MODEL_TRAPS) ? 5 * NPL : 0);
+  static constexpr int BYTES = COUNT * 32 * 8;
+};
+
+// ---- readout: signal and its time derivative, reduced over the warp --------------------------
+template <int NPL, int MODEL>
+TRPL_FN void readout(const Coef& c, const NodeMask<NPL>& m, int meas_type, const Vec<NPL, MODEL>& u,
+                     const Vec<NPL, MODEL>& f, const RhsAux<NPL>& aux, double& val, double& dval) {
+  real fql0 = shfl_up(f.q[NPL - 1], 1);
+  fql0 = sel(m.first_lane, 0.0, fql0);
+  real acc = splat(0.0), dacc = splat(0.0);
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const real fql = (j == 0) ? fql0 : f.q[j - 1];
+    real fp = f.n[j] + (f.q[j] - fql);
+    if (MODEL == MODEL_TRAPS) fp = fp + f.t[j];
+    real a, d;
+    if (meas_type == MEAS_TRPL) {                       // forward_solver.py:228-236,267-269
+      a = fmadd(u.n[j], aux.p[j], -c.n0p0);
+      d = fmadd(f.n[j], aux.p[j], u.n[j] * fp);
+    } else {                                            // forward_solver.py:239-247,272-274
+      a = fmadd(c.mun, u.n[j] - c.n0, c.mup * (aux.p[j] - c.p0));
+      d = fmadd(c.mun, f.n[j], c.mup * fp);
+    }
+    acc = acc + sel(m.real_node[j], a, 0.0);
+    dacc = dacc + sel(m.real_node[j], d, 0.0);
+  }
+  const double scale = (meas_type == MEAS_TRPL) ? c.ks * c.dx * 1e23 : Q_COULOMB * c.dx * 1e9;
+  val = uni(warp_sum(acc)) * scale;
+  dval = uni(warp_sum(dacc)) * scale;
+}
+
+// ---- Hermite history (warp-uniform scalars) -------------------------------------------------
+struct History {
+  double t[3], v[3], d[3];   // index 2 = newest
+  int n;
+};
+
+struct HermiteCoef {
+  double t1, t2, t0;
+  double c0, c1, c2, c3, c4, c5;
+  bool in_log;
+};
+
+// Newton form on the doubled nodes [t1,t1,t2,t2,t0,t0] (t1,t2 = last step; t0 = the step before)
+TRPL_FN HermiteCoef hermite_setup(const History& H) {
+  HermiteCoef k;
+  const bool three = H.n >= 3;
+  k.in_log = H.v[1] > 0.0 && H.v[2] > 0.0 && (!three || H.v[0] > 0.0);
+  double v0, v1, v2, d0, d1, d2;
+  if (k.in_log) {
+    v1 = log(H.v[1]); v2 = log(H.v[2]); d1 = H.d[1] / H.v[1]; d2 = H.d[2] / H.v[2];
+    v0 = three ? log(H.v[0]) : 0.0; d0 = three ? H.d[0] / H.v[0] : 0.0;
+  } else {
+    v1 = H.v[1]; v2 = H.v[2]; d1 = H.d[1]; d2 = H.d[2]; v0 = H.v[0]; d0 = H.d[0];
+  }
+  k.t1 = H.t[1]; k.t2 = H.t[2]; k.t0 = H.t[0];
+  const double i21 = 1.0 / (k.t2 - k.t1);
+  const double f12 = (v2 - v1) * i21;
+  const double f112 = (f12 - d1) * i21;
+  const double f122 = (d2 - f12) * i21;
+  const double f1122 = (f122 - f112) * i21;
+  k.c0 = v1; k.c1 = d1; k.c2 = f112; k.c3 = f1122; k.c4 = 0.0; k.c5 = 0.0;
+  if (three) {
+    const double i01 = 1.0 / (k.t0 - k.t1), i02 = 1.0 / (k.t0 - k.t2);
+    const double f20 = (v0 - v2) * i02;
+    const double f220 = (f20 - d2) * i02;
+    const double f200 = (d0 - f20) * i02;
+    const double f1220 = (f220 - f122) * i01;
+    const double f2200 = (f200 - f220) * i02;
+    const double f11220 = (f1220 - f1122) * i01;
+    const double f12200 = (f2200 - f1220) * i01;
+    k.c4 = f11220;
+    k.c5 = (f12200 - f11220) * i01;
+  }
+  return k;
+}
+
+TRPL_FN real hermite_eval(const HermiteCoef& k, real tq) {
+  const real a = tq - k.t1, b = tq - k.t2, e = tq - k.t0;
+  const real a2 = a * a, b2 = b * b;
+  real p = fmadd(e, k.c5, k.c4);          // c4 + c5 (t-t0)
+  p = fmadd(p, b2, fmadd(b, k.c3, k.c2)); // c2 + c3 (t-t2) + (t-t2)^2 (...)
+  p = fmadd(p, a2, fmadd(a, k.c1, k.c0)); // c0 + c1 (t-t1) + (t-t1)^2 (...)
+  return k.in_log ? vexp(p) : p;
+}
+
+// ---- the trajectory -------------------------------------------------------------------------
+template <int NPL, int MODEL>
+TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm, TrajOut& out) {
+  typedef Slots<NPL, MODEL> SL;
+  typedef Vec<NPL, MODEL> V;
+  const MeasDesc& md = *in.md;
+  const int L = md.nx;
+  const Coef c = make_coef(in.par, md.thickness, L);
+  const NodeMask<NPL> m = make_mask<NPL>(L);
+  const ivec lane = lane_id();
+  const ivec node0 = imul(lane, NPL);
+  const int n_t = md.n_t;
+  const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
+
+  // ---- initial condition (forward_solver.py:100-122) ----
+  V u;
+  {
+    real rho_run = splat(0.0);
+    real qloc[NPL];
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+      const ivec i = iadd(node0, j);
+      real dn;
+      if (md.ini_mode == 0) {
+        const ivec src = i;
+        dn = gather(in.profile, src, m.real_node[j], 0.0) * 1e-21;
+      } else {
+        const double fluence = md.ini_a * in.fl_mult * 1e-14;
+        const double alpha = md.ini_b * in.al_mult * 1e-7;
+        const double x0 = 0.5 * c.dx;
+        const double step = (L > 1) ? (md.thickness - c.dx) / (L - 1) : 0.0;   // np.linspace, sim_utils.py:269
+        const real idx = to_real((md.ini_dir < 0) ? irsub(L - 1, i) : i);
+        const real x = fmadd(idx, step, x0);
+        dn = (fluence * alpha) * vexp(-(alpha * x));
+      }
+      const real n = dn + c.n0, p = dn + c.p0;
+      const real rho = (p - c.p0) - (n - c.n0);                  // forward_solver.py:28-29
+      rho_run = rho_run + sel(m.real_node[j], rho, 0.0);
+      qloc[j] = rho_run;
+      u.n[j] = sel(m.real_node[j], n, 1.0);
+      if (MODEL == MODEL_TRAPS) u.t[j] = splat(0.0);
+    }
+    if (MODEL != MODEL_TRAPS) u.t[0] = splat(0.0);
+    // Gauss's law: running net charge = in-lane running sum + exclusive warp scan of lane totals
+    const real incl = warp_scan_incl(rho_run);
+    const real excl = incl - rho_run;
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) u.q[j] = sel(m.real_node[j], qloc[j] + excl, 0.0);
+  }
+
+  // ---- bookkeeping ----
+  double t = 0.0;
+  const double tend = in.times[n_t - 1];
+  int io = 0;                       // next measurement index to emit
+  int status = ST_OK, n_acc = 0, n_rej = 0;
+  bool floored = false;
+  real ll0 = splat(0.0), ll1 = splat(0.0), ll2 = splat(0.0);
+  real nneg = splat(0.0);
+  History H; H.n = 0;
+  TRPL_UNROLL for (int k = 0; k < 3; ++k) { H.t[k] = 0; H.v[k] = 0; H.d[k] = 0; }
+
+  V f0; RhsAux<NPL> aux0;
+  rhs<NPL, MODEL>(c, m, u, f0, aux0);
+  double val, dval;
+  readout<NPL, MODEL>(c, m, md.meas_type, u, f0, aux0, val, dval);
+
+  // emit every measurement time in (t_prev, t]; lanes work on consecutive indices
+  auto emit = [&](double t_now, bool fill_floor) {
+    HermiteCoef hc;
+    bool have_hc = false;
+    while (io < n_t) {
+      const ivec k = iadd(lane, io);
+      const mask in_range = k < n_t;
+      const real tq = gather(in.times, k, in_range, DBL_MAX);
+      const mask due = fill_floor ? in_range : mand(in_range, tq <= t_now);
+      const unsigned bits = warp_ballot(due);
+      if (bits == 0u) break;
+      int cnt = 0;
+      { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }   // contiguous from lane 0 (times ascend)
+      real y;
+      if (fill_floor) {
+        y = splat(DBL_MIN);
+      } else if (H.n < 2) {
+        y = splat(H.v[2]);                                         // t == 0
+      } else {
+        if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
+        y = hermite_eval(hc, tq);
+        y = sel(tq >= H.t[2], H.v[2], y);                          // exact on the step end
+      }
+      // forward_solver.py:190-192: from the first value below DBL_MIN on, the curve is DBL_MIN
+      const mask take = lane < cnt;
+      if (!floored) {
+        const unsigned low = warp_ballot(mand(take, y < DBL_MIN));
+        if (low != 0u) {
+          int first = 0; { unsigned b = low; while (!(b & 1u)) { ++first; b >>= 1; } }
+          y = sel(lane >= first, DBL_MIN, y);
+          floored = true; status |= ST_FLOORED;
+        }
+      } else {
+        y = splat(DBL_MIN);
+      }
+      if (in.curve) scatter(in.curve, k, take, y);
+      if (want_ll) {
+        // trial_move_evaluation.py:117-130 and :147-156
+        const mask neg = mand(take, y < 0.0);
+        nneg = nneg + sel(neg, 1.0, 0.0);
+        const real ya = vabs(y);
+        const real vk = gather(in.vals, k, take, 0.0);
+        const real uk = gather(in.uncs, k, take, 1.0);
+        const real r = (vlog10(ya) + in.scale_shift) - vk;
+        const real r2 = r * r;
+        const real u2 = 2.0 * (uk * uk);
+        ll0 = ll0 + sel(take, r2 / (in.s2T[0] + u2), 0.0);
+        ll1 = ll1 + sel(take, r2 / (in.s2T[1] + u2), 0.0);
+        ll2 = ll2 + sel(take, r2 / (in.s2T[2] + u2), 0.0);
+      }
+      io += cnt;
+      if (cnt < 32) break;
+    }
+  };
+
+  H.t[2] = 0.0; H.v[2] = val; H.d[2] = dval; H.n = 1;
+  emit(0.0, false);
+
+  // ---- initial step (Hairer's d0/d1 rule on the scaled norms) ----
+  double h;
+  {
+    real s0 = splat(0.0), s1 = splat(0.0);
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+      const real scn = fmadd(opt.rtol, vabs(u.n[j]), opt.atol);
+      const real scq = fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(aux0.p[j])), opt.atol);
+      const real a = u.n[j] / scn, b = f0.n[j] / scn, q = u.q[j] / scq, g = f0.q[j] / scq;
+      s0 = s0 + sel(m.real_node[j], fmadd(a, a, q * q), 0.0);
+      s1 = s1 + sel(m.real_node[j], fmadd(b, b, g * g), 0.0);
+    }
+    const double d0 = sqrt(uni(warp_sum(s0))), d1 = sqrt(uni(warp_sum(s1)));
+    h = (d1 > 0.0 && d0 > 0.0) ? 0.01 * d0 / d1 : 1e-6;
+    h = fmin(h, 1e-3 * fmax(tend, 1e-300));
+    if (!(h > 0.0)) h = 1e-6;
+  }
+  double err_old = 1e-4, h_acc = h;
+  bool first = true, last_rejected = false;
+  const double inv_n = 1.0 / (2.0 * L + ((MODEL == MODEL_TRAPS) ? L : 0));
+  const double h_min = 1e-14 * fmax(tend, 1e-300);
+
+  while (io < n_t) {
+    if (n_acc + n_rej >= opt.max_steps) { status |= ST_MAX_STEPS; break; }
+    if (opt.hmax > 0.0) h = fmin(h, opt.hmax);
+    bool final_step = false;
+    if (t + 1.01 * h >= tend) { h = tend - t; final_step = true; }
+    if (h < h_min) { status |= ST_H_UNDERFLOW; break; }
+
+    // ---- W = 1/(gamma h) I - J, factorised ----
+    const double gi = 1.0 / (RODAS4_GAMMA * h);
+    const double ih = 1.0 / h;
+    PcrFac pf;
+    {
+      Blk A[NPL], B[NPL], C[NPL];
+      JacTraps<NPL> jt;
+      jacobian<NPL, MODEL>(c, m, u, aux0, A, B, C, jt);
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+        A[j] = blk_neg(A[j]); C[j] = blk_neg(C[j]);
+        B[j].a00 = gi - B[j].a00; B[j].a01 = -B[j].a01; B[j].a10 = -B[j].a10; B[j].a11 = gi - B[j].a11;
+      }
+      // the front contact has no left neighbour (Q_0 is the fixed corner field)
+      A[0] = blk_sel(m.first_lane, blk_zero(), A[0]);
+      if (MODEL == MODEL_TRAPS) {
+        // condense the node-local trap occupancy out of the block rows
+        real idt[NPL], g_n[NPL];
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          idt[j] = rcp(gi - jt.ft_t[j]);
+          g_n[j] = jt.ft_n[j] * idt[j];           // K_T = idt * r_T + g_n * K_N
+        }
+        const real gn_next = shfl_down(g_n[0], 1);
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          const real gnn = (j == NPL - 1) ? gn_next : g_n[j + 1];
+          B[j].a00 = B[j].a00 - jt.fn_t[j] * g_n[j];
+          B[j].a10 = B[j].a10 - jt.fq_t[j] * g_n[j];
+          C[j].a10 = C[j].a10 - jt.fq_tn[j] * gnn;
+          sm.st(SL::TRAP + 5 * j + 0, idt[j]);
+          sm.st(SL::TRAP + 5 * j + 1, g_n[j]);
+          sm.st(SL::TRAP + 5 * j + 2, jt.fn_t[j]);
+          sm.st(SL::TRAP + 5 * j + 3, jt.fq_t[j]);
+          sm.st(SL::TRAP + 5 * j + 4, jt.fq_tn[j]);
+        }
+      }
+      bt_factor<NPL>(A, B, C, sm, SL::FAC, pf);
+    }
+
+    // ---- six stages ----
+    V us = u;                 // stage argument, ends up as the embedded solution, then u_new
+    V kk;                     // current stage increment
+    if (MODEL != MODEL_TRAPS) kk.t[0] = splat(0.0);
+    for (int s = 0; s < 6; ++s) {
+      V r;
+      if (s == 0) {
+        r = f0;
+      } else {
+        V cs;
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          us.n[j] = u.n[j]; us.q[j] = u.q[j]; cs.n[j] = splat(0.0); cs.q[j] = splat(0.0);
+          if (MODEL == MODEL_TRAPS) { us.t[j] = u.t[j]; cs.t[j] = splat(0.0); }
+        }
+        for (int p = 0; p < s; ++p) {
+          const double a = RODAS4_A[s][p], cc = RODAS4_C[s][p] * ih;
+          const int kb = SL::KBASE + p * SL::KSTRIDE;
+          TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+            const real kn = sm.ld(kb + SL::NC * j), kq = sm.ld(kb + SL::NC * j + 1);
+            us.n[j] = fmadd(a, kn, us.n[j]); us.q[j] = fmadd(a, kq, us.q[j]);
+            cs.n[j] = fmadd(cc, kn, cs.n[j]); cs.q[j] = fmadd(cc, kq, cs.q[j]);
+            if (MODEL == MODEL_TRAPS) {
+              const real kt = sm.ld(kb + SL::NC * j + 2);
+              us.t[j] = fmadd(a, kt, us.t[j]); cs.t[j] = fmadd(cc, kt, cs.t[j]);
+            }
+          }
+        }
+        RhsAux<NPL> auxs;
+        rhs<NPL, MODEL>(c, m, us, r, auxs);
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          r.n[j] = r.n[j] + cs.n[j]; r.q[j] = r.q[j] + cs.q[j];
+          if (MODEL == MODEL_TRAPS) r.t[j] = r.t[j] + cs.t[j];
+        }
+      }
+      V2 b[NPL];
+      if (MODEL == MODEL_TRAPS) {
+        real w[NPL];
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) w[j] = sm.ld(SL::TRAP + 5 * j + 0) * r.t[j];   // idt * r_T
+        const real w_next = shfl_down(w[0], 1);
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          const real wn = (j == NPL - 1) ? w_next : w[j + 1];
+          b[j].x = fmadd(sm.ld(SL::TRAP + 5 * j + 2), w[j], r.n[j]);
+          b[j].y = fmadd(sm.ld(SL::TRAP + 5 * j + 3), w[j], fmadd(sm.ld(SL::TRAP + 5 * j + 4), wn, r.q[j]));
+        }
+        bt_solve<NPL>(b, sm, SL::FAC, pf);
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) kk.t[j] = fmadd(sm.ld(SL::TRAP + 5 * j + 1), b[j].x, w[j]);
+      } else {
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) { b[j].x = r.n[j]; b[j].y = r.q[j]; }
+        bt_solve<NPL>(b, sm, SL::FAC, pf);
+      }
+      const int kb = SL::KBASE + s * SL::KSTRIDE;
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+        kk.n[j] = b[j].x; kk.q[j] = b[j].y;
+        if (s < SL::NKS) {
+          sm.st(kb + SL::NC * j, kk.n[j]); sm.st(kb + SL::NC * j + 1, kk.q[j]);
+          if (MODEL == MODEL_TRAPS) sm.st(kb + SL::NC * j + 2, kk.t[j]);
+        }
+      }
+    }
+    // us = u + sum_{j<5} a_5j K_j is the embedded (3rd-order) solution's argument; u_new = us + K_6
+    real esum = splat(0.0);
+    mask bad = mconst(false);
+    V un;
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+      un.n[j] = us.n[j] + kk.n[j]; un.q[j] = us.q[j] + kk.q[j];
+      const real scn = fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(un.n[j])), opt.atol);
+      const real scq = fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(aux0.p[j])), opt.atol);
+      const real en = kk.n[j] / scn, eq = kk.q[j] / scq;
+      real e2 = fmadd(en, en, eq * eq);
+      if (MODEL == MODEL_TRAPS) {
+        un.t[j] = us.t[j] + kk.t[j];
+        const real sct = fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(un.t[j]), vabs(u.n[j]))), opt.atol);
+        const real et = kk.t[j] / sct;
+        e2 = fmadd(et, et, e2);
+      }
+      esum = esum + sel(m.real_node[j], e2, 0.0);
+      bad = mor(bad, mand(m.real_node[j], mor(is_nan(un.n[j]), is_nan(un.q[j]))));
+    }
+    const double err2 = uni(warp_sum(esum)) * inv_n;
+    const bool nonfinite = warp_any(bad) || !(err2 == err2) || err2 > 1e300;
+    const double err = nonfinite ? 1e10 : sqrt(err2);
+
+    // ---- controller (Hairer's RODAS: standard + Gustafsson predictive) ----
+    double fac = fmax(0.2, fmin(6.0, pow(err, 0.25) / 0.9));
+    double h_new = h / fac;
+    if (err <= 1.0) {
+      ++n_acc;
+      if (!first) {
+        double fg = (h_acc / h) * pow(err * err / err_old, 0.25) / 0.9;
+        fg = fmax(0.2, fmin(6.0, fg));
+        fac = fmax(fac, fg);
+        h_new = h / fac;
+      }
+      first = false; h_acc = h; err_old = fmax(1e-2, err);
+      if (last_rejected) h_new = fmin(h_new, h);
+      last_rejected = false;
+      t = final_step ? tend : t + h;
+      u = un;
+      rhs<NPL, MODEL>(c, m, u, f0, aux0);
+      readout<NPL, MODEL>(c, m, md.meas_type, u, f0, aux0, val, dval);
+      H.t[0] = H.t[1]; H.v[0] = H.v[1]; H.d[0] = H.d[1];
+      H.t[1] = H.t[2]; H.v[1] = H.v[2]; H.d[1] = H.d[2];
+      H.t[2] = t; H.v[2] = val; H.d[2] = dval;
+      if (H.n < 3) ++H.n;
+      emit(t, false);
+      if (floored) break;       // the rest of the curve is DBL_MIN by definition
+      h = h_new;
+    } else {
+      ++n_rej;
+      last_rejected = true;
+      if (nonfinite) { h *= 0.1; } else { h = h_new; }
+    }
+  }
+  // anything not emitted (failure, or floor reached): forward_solver.py:168 + :190-192 -> DBL_MIN
+  if (io < n_t) {
+    if (!floored && (status & (ST_MAX_STEPS | ST_H_UNDERFLOW))) { floored = true; }
+    emit(tend, true);
+  }
+
+  // ---- likelihood (trial_move_evaluation.py:117-166) ----
+  out.status = status; out.n_acc = n_acc; out.n_rej = n_rej;
+  if (want_ll && (opt.flags & OPT_FORCE_MIN_Y) && in.curve) {
+    // utils.py:16-32 set_min_y: raise |sol| to 10**min(vals - shift) from the index np.searchsorted
+    // finds on -|sol| (a plain bisection, reproduced step for step), then redo the sum.
+    warp_sync();
+    real mn = splat(DBL_MAX);
+    for (int k0 = 0; k0 < n_t; k0 += 32) {
+      const ivec k = iadd(lane, k0);
+      mn = vmin(mn, gather(in.vals, k, k < n_t, DBL_MAX) - in.scale_shift);
+    }
+    const double floor_y = pow(10.0, -uni(warp_max(-mn)));
+    int lo = 0, hi = n_t;
+    while (lo < hi) {
+      const int mid = lo + ((hi - lo) >> 1);
+      if (-fabs(in.curve[mid]) < -floor_y) lo = mid + 1; else hi = mid;
+    }
+    ll0 = splat(0.0); ll1 = splat(0.0); ll2 = splat(0.0);
+    for (int k0 = 0; k0 < n_t; k0 += 32) {
+      const ivec k = iadd(lane, k0);
+      const mask take = k < n_t;
+      real ya = vabs(gather(in.curve, k, take, 1.0));
+      ya = sel(k >= lo, floor_y, ya);
+      const real vk = gather(in.vals, k, take, 0.0);
+      const real uk = gather(in.uncs, k, take, 1.0);
+      const real r = (vlog10(ya) + in.scale_shift) - vk;
+      const real r2 = r * r;
+      const real u2 = 2.0 * (uk * uk);
+      ll0 = ll0 + sel(take, r2 / (in.s2T[0] + u2), 0.0);
+      ll1 = ll1 + sel(take, r2 / (in.s2T[1] + u2), 0.0);
+      ll2 = ll2 + sel(take, r2 / (in.s2T[2] + u2), 0.0);
+    }
+  }
+  if (want_ll) {
+    const double n_neg = uni(warp_sum(nneg));
+    double l0 = -uni(warp_sum(ll0)), l1 = -uni(warp_sum(ll1)), l2 = -uni(warp_sum(ll2));
+    const double ninf = -HUGE_VAL;
+    if (!(n_neg < 0.2 * n_t)) { out.status |= ST_NEG_FRAC; l0 = l1 = l2 = ninf; }
+    if (l0 != l0) { out.status |= ST_NAN_LL; l0 = ninf; }
+    if (l1 != l1) l1 = ninf;
+    if (l2 != l2) l2 = ninf;
+    out.logll[0] = l0; out.logll[1] = l1; out.logll[2] = l2;
+  } else {
+    out.logll[0] = out.logll[1] = out.logll[2] = 0.0;
+  }
+}
+
+}  // namespace trpl

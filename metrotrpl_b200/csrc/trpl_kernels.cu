@@ -1,0 +1,422 @@
+// trpl_kernels.cu - sm_100a kernels and the C ABI (include/metrotrpl_b200.h).
+//
+// Execution model: persistent warps.  The grid is (SM count x 2) CTAs of 4 warps; every warp
+// repeatedly claims the next (parameter set, measurement) trajectory from a global counter and
+// integrates it start to finish (trajectory.h) using only its registers and its private slice of
+// shared memory.  There is no __syncthreads anywhere on the path, no inter-warp communication,
+// and the only global traffic per trajectory is its 16 parameters, the measurement arrays
+// (L2-resident, shared by all trajectories) and a handful of result scalars.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/metrotrpl_b200.h"
+#include "trajectory.h"
+
+namespace {
+
+using namespace trpl;
+
+static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch");
+static_assert(sizeof(trpl_solver_opts) == sizeof(SolverOpts), "ABI struct mismatch");
+static_assert(TRPL_NPARAM == trpl::NPARAM, "ABI constant mismatch");
+
+constexpr int WARPS_PER_CTA = 4;
+
+struct KernelArgs {
+  const double* params;      // [n_sets][16]
+  const double* aux;         // [n_sets][n_meas][6]
+  const MeasDesc* meas;      // [n_meas]
+  const double* times;
+  const double* vals;
+  const double* uncs;
+  const double* profiles;
+  double* logll;             // [n_traj][3]
+  int* status;               // [n_traj]
+  int* nsteps;               // [n_traj][2]
+  double* curves;            // [n_sets][n_times_total] or null
+  int* counter;              // work queue head
+  int n_traj, n_meas, n_times_total;
+  SolverOpts opt;
+};
+
+template <int NPL, int MODEL>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(const KernelArgs a) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  LaneMem sm{smem + warp * (Slots<NPL, MODEL>::COUNT * 32)};
+  for (;;) {
+    int traj = 0;
+    if (lane == 0) traj = atomicAdd(a.counter, 1);
+    traj = __shfl_sync(0xffffffffu, traj, 0);
+    if (traj >= a.n_traj) break;
+    const int set = traj / a.n_meas;
+    const int mi = traj - set * a.n_meas;
+    const MeasDesc* md = a.meas + mi;
+    TrajIn in;
+    in.par = a.params + (size_t)set * TRPL_NPARAM;
+    in.md = md;
+    in.times = a.times + md->t_off;
+    in.vals = a.vals ? a.vals + md->t_off : nullptr;
+    in.uncs = a.uncs ? a.uncs + md->t_off : nullptr;
+    in.profile = a.profiles ? a.profiles + md->prof_off : nullptr;
+    const double* ax = a.aux + (size_t)traj * TRPL_NAUX;
+    in.scale_shift = ax[TRPL_A_SCALE_SHIFT];
+    in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
+    in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
+    in.curve = a.curves ? a.curves + (size_t)set * a.n_times_total + md->t_off : nullptr;
+    TrajOut out;
+    run_trajectory<NPL, MODEL>(in, a.opt, sm, out);
+    if (lane == 0) {
+      a.logll[3 * (size_t)traj + 0] = out.logll[0];
+      a.logll[3 * (size_t)traj + 1] = out.logll[1];
+      a.logll[3 * (size_t)traj + 2] = out.logll[2];
+      a.status[traj] = out.status;
+      a.nsteps[2 * (size_t)traj + 0] = out.n_acc;
+      a.nsteps[2 * (size_t)traj + 1] = out.n_rej;
+    }
+    __syncwarp();
+  }
+}
+
+// FP64 peak probe: 8 independent FMA chains per thread, no memory traffic.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed) {
+  double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
+         a6 = seed + 6, a7 = seed + 7;
+  const double m = 0.999999, c = 1e-9 * threadIdx.x;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; defeats DCE
+}
+
+thread_local std::string g_err;
+int fail(const std::string& msg) { g_err = msg; return 1; }
+#define CU(call)                                                                             \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+struct trpl_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
+  DevBuf<char> d_flush;
+  cudaDeviceProp prop;
+  int model = 0, n_meas = 0, n_times_total = 0, max_nx = 0;
+  bool have_vals = false, have_profiles = false;
+  DevBuf<MeasDesc> d_meas;
+  DevBuf<double> d_times, d_vals, d_uncs, d_profiles;
+  DevBuf<double> d_params, d_aux, d_logll, d_curves;
+  DevBuf<int> d_status, d_nsteps, d_counter;
+  int n_sets = 0;
+  bool curves_valid = false;
+  float last_ms = 0.f;
+  int64_t launches = 0;
+};
+
+namespace {
+
+template <int NPL, int MODEL>
+int launch(trpl_handle* h, const KernelArgs& a) {
+  const size_t smem = (size_t)WARPS_PER_CTA * Slots<NPL, MODEL>::BYTES;
+  auto kern = trpl_forward_kernel<NPL, MODEL>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS_PER_CTA, smem));
+  if (per_sm < 1) return fail("trajectory kernel does not fit on an SM");
+  const int warps_needed = a.n_traj;
+  int grid = h->prop.multiProcessorCount * per_sm;
+  const int ctas_needed = (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  if (grid > ctas_needed) grid = ctas_needed;
+  if (grid < 1) grid = 1;
+  CU(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
+  CU(cudaEventRecord(h->ev0, h->stream));
+  kern<<<grid, 32 * WARPS_PER_CTA, smem, h->stream>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  return 0;
+}
+
+template <int MODEL>
+int launch_npl(trpl_handle* h, const KernelArgs& a) {
+  const int nx = h->max_nx;
+  if (nx <= 32) return launch<1, MODEL>(h, a);
+  if (nx <= 64) return launch<2, MODEL>(h, a);
+  if (nx <= 128) return launch<4, MODEL>(h, a);
+  if (nx <= 256) return launch<8, MODEL>(h, a);
+  return fail("nx > 256 is not supported by this build");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* trpl_last_error(void) { return g_err.c_str(); }
+int trpl_abi_version(void) { return TRPL_ABI_VERSION; }
+
+int trpl_create(int device, trpl_handle** out) {
+  if (!out) return fail("trpl_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0)
+    return fail(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                "); metrotrpl_b200 has no CPU fallback");
+  if (device < 0 || device >= n) return fail("trpl_create: bad device index");
+  CU(cudaSetDevice(device));
+  trpl_handle* h = new trpl_handle();
+  h->device = device;
+  CU(cudaGetDeviceProperties(&h->prop, device));
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  CU(cudaEventCreate(&h->tm0));
+  CU(cudaEventCreate(&h->tm1));
+  CU(h->d_counter.reserve(1));
+  *out = h;
+  return 0;
+}
+
+void trpl_destroy(trpl_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaEventDestroy(h->ev0);
+  cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->tm0);
+  cudaEventDestroy(h->tm1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int trpl_device_info(trpl_handle* h, int32_t* sm_count, int32_t* sm_clock_khz, char* name, int32_t name_len) {
+  if (!h) return fail("null handle");
+  if (sm_count) *sm_count = h->prop.multiProcessorCount;
+  if (sm_clock_khz) {
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    *sm_clock_khz = khz;
+  }
+  if (name && name_len > 0) { strncpy(name, h->prop.name, name_len - 1); name[name_len - 1] = 0; }
+  return 0;
+}
+
+int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_meas_desc* meas,
+                     int32_t n_times_total, const double* times, const double* vals,
+                     const double* uncs, int32_t n_profile_total, const double* profiles) {
+  if (!h) return fail("null handle");
+  if (model != TRPL_MODEL_STD && model != TRPL_MODEL_TRAPS) return fail("Invalid model");
+  if (n_meas < 1 || !meas || !times || n_times_total < 1) return fail("trpl_set_problem: empty problem");
+  int max_nx = 0;
+  for (int i = 0; i < n_meas; ++i) {
+    const trpl_meas_desc& m = meas[i];
+    if (m.nx < 2 || m.nx > 256) return fail("nx must be in 2..256");
+    if (m.n_t < 1 || m.t_off < 0 || m.t_off + m.n_t > n_times_total) return fail("bad time slice");
+    if (times[m.t_off] != 0.0) return fail("Grid error - times must start at t=0");   // sim_utils.py:271-272
+    for (int k = 1; k < m.n_t; ++k)
+      if (!(times[m.t_off + k] > times[m.t_off + k - 1])) return fail("measurement times must be strictly ascending");
+    if (m.meas_type != TRPL_MEAS_TRPL && m.meas_type != TRPL_MEAS_TRTS) return fail("TRTS or TRPL only");
+    if (m.ini_mode == TRPL_INI_DENSITY) {
+      if (!profiles || m.prof_off < 0 || m.prof_off + m.nx > n_profile_total)
+        return fail("density mode needs nx initial densities per measurement");
+    } else if (m.ini_mode != TRPL_INI_FLUENCE) {
+      return fail("Invalid ini_mode - must be 'density' or 'fluence'");
+    }
+    if (!(m.thickness > 0)) return fail("thickness must be positive");
+    if (m.nx > max_nx) max_nx = m.nx;
+  }
+  // all measurements of one launch share the nodes-per-lane template: nx must fit 32*NPL and
+  // exceed NPL so that the two contacts sit on different lanes
+  const int npl = max_nx <= 32 ? 1 : max_nx <= 64 ? 2 : max_nx <= 128 ? 4 : 8;
+  for (int i = 0; i < n_meas; ++i)
+    if (meas[i].nx <= npl) return fail("mixed nx: smallest nx must exceed max_nx/32 rounded up to a power of two");
+  CU(cudaSetDevice(h->device));
+  CU(h->d_meas.reserve(n_meas));
+  CU(h->d_times.reserve(n_times_total));
+  CU(cudaMemcpyAsync(h->d_meas.p, meas, sizeof(MeasDesc) * n_meas, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_times.p, times, sizeof(double) * n_times_total, cudaMemcpyHostToDevice, h->stream));
+  h->have_vals = vals && uncs;
+  if (h->have_vals) {
+    CU(h->d_vals.reserve(n_times_total));
+    CU(h->d_uncs.reserve(n_times_total));
+    CU(cudaMemcpyAsync(h->d_vals.p, vals, sizeof(double) * n_times_total, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_uncs.p, uncs, sizeof(double) * n_times_total, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->have_profiles = profiles && n_profile_total > 0;
+  if (h->have_profiles) {
+    CU(h->d_profiles.reserve(n_profile_total));
+    CU(cudaMemcpyAsync(h->d_profiles.p, profiles, sizeof(double) * n_profile_total, cudaMemcpyHostToDevice, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  h->model = model; h->n_meas = n_meas; h->n_times_total = n_times_total; h->max_nx = max_nx;
+  return 0;
+}
+
+int trpl_upload_batch(trpl_handle* h, int32_t n_sets, const double* params, const double* aux) {
+  if (!h) return fail("null handle");
+  if (h->n_meas < 1) return fail("trpl_set_problem has not been called");
+  if (n_sets < 1 || !params || !aux) return fail("empty batch");
+  CU(cudaSetDevice(h->device));
+  const size_t n_traj = (size_t)n_sets * h->n_meas;
+  CU(h->d_params.reserve((size_t)n_sets * TRPL_NPARAM));
+  CU(h->d_aux.reserve(n_traj * TRPL_NAUX));
+  CU(h->d_logll.reserve(n_traj * 3));
+  CU(h->d_status.reserve(n_traj));
+  CU(h->d_nsteps.reserve(n_traj * 2));
+  CU(cudaMemcpyAsync(h->d_params.p, params, sizeof(double) * n_sets * TRPL_NPARAM, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_aux.p, aux, sizeof(double) * n_traj * TRPL_NAUX, cudaMemcpyHostToDevice, h->stream));
+  h->n_sets = n_sets;
+  return 0;
+}
+
+int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want_curves) {
+  if (!h || !opts) return fail("null argument");
+  if (h->n_sets < 1) return fail("no batch uploaded");
+  if (!(opts->rtol > 0) || !(opts->atol >= 0) || opts->max_steps < 1) return fail("bad solver options");
+  const bool want_ll = !(opts->flags & TRPL_OPT_NO_LIKELIHOOD);
+  if (want_ll && !h->have_vals) return fail("likelihood requested but no measurement values uploaded");
+  if (opts->flags & TRPL_OPT_FORCE_MIN_Y) want_curves = 1;   // the min_y pass re-reads the curve
+  CU(cudaSetDevice(h->device));
+  KernelArgs a;
+  a.params = h->d_params.p; a.aux = h->d_aux.p; a.meas = h->d_meas.p; a.times = h->d_times.p;
+  a.vals = h->have_vals ? h->d_vals.p : nullptr; a.uncs = h->have_vals ? h->d_uncs.p : nullptr;
+  a.profiles = h->have_profiles ? h->d_profiles.p : nullptr;
+  a.logll = h->d_logll.p; a.status = h->d_status.p; a.nsteps = h->d_nsteps.p;
+  a.curves = nullptr;
+  if (want_curves) {
+    CU(h->d_curves.reserve((size_t)h->n_sets * h->n_times_total));
+    a.curves = h->d_curves.p;
+  }
+  h->curves_valid = want_curves != 0;
+  a.counter = h->d_counter.p;
+  a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;
+  memcpy(&a.opt, opts, sizeof(SolverOpts));
+  if (h->model == TRPL_MODEL_STD) return launch_npl<MODEL_STD>(h, a);
+  return launch_npl<MODEL_TRAPS>(h, a);
+}
+
+int trpl_download_results(trpl_handle* h, double* logll, int32_t* status, int32_t* nsteps, double* curves) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  const size_t n_traj = (size_t)h->n_sets * h->n_meas;
+  if (logll) CU(cudaMemcpyAsync(logll, h->d_logll.p, sizeof(double) * n_traj * 3, cudaMemcpyDeviceToHost, h->stream));
+  if (status) CU(cudaMemcpyAsync(status, h->d_status.p, sizeof(int) * n_traj, cudaMemcpyDeviceToHost, h->stream));
+  if (nsteps) CU(cudaMemcpyAsync(nsteps, h->d_nsteps.p, sizeof(int) * n_traj * 2, cudaMemcpyDeviceToHost, h->stream));
+  if (curves) {
+    if (!h->curves_valid) return fail("curves were not produced by the last run");
+    CU(cudaMemcpyAsync(curves, h->d_curves.p, sizeof(double) * h->n_sets * h->n_times_total, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  return 0;
+}
+
+int trpl_loglik_batch(trpl_handle* h, int32_t n_sets, const double* params, const double* aux,
+                      const trpl_solver_opts* opts, double* logll, int32_t* status, int32_t* nsteps,
+                      double* curves) {
+  if (int r = trpl_upload_batch(h, n_sets, params, aux)) return r;
+  if (int r = trpl_run_resident(h, opts, curves != nullptr)) return r;
+  return trpl_download_results(h, logll, status, nsteps, curves);
+}
+
+int trpl_solve_batch(trpl_handle* h, int32_t n_sets, const double* params, const double* aux,
+                     const trpl_solver_opts* opts, double* curves, int32_t* status, int32_t* nsteps) {
+  if (!opts || !curves) return fail("null argument");
+  trpl_solver_opts o = *opts;
+  o.flags |= TRPL_OPT_NO_LIKELIHOOD;
+  if (int r = trpl_upload_batch(h, n_sets, params, aux)) return r;
+  if (int r = trpl_run_resident(h, &o, 1)) return r;
+  return trpl_download_results(h, nullptr, status, nsteps, curves);
+}
+
+int trpl_last_kernel_ms(trpl_handle* h, float* ms) {
+  if (!h || !ms) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  *ms = h->last_ms;
+  return 0;
+}
+
+int64_t trpl_launch_count(trpl_handle* h) { return h ? h->launches : 0; }
+
+int trpl_synchronize(trpl_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int trpl_timer_begin(trpl_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaEventRecord(h->tm0, h->stream));
+  return 0;
+}
+
+int trpl_timer_end(trpl_handle* h, float* ms) {
+  if (!h || !ms) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->tm1, h->stream));
+  CU(cudaEventSynchronize(h->tm1));
+  CU(cudaEventElapsedTime(ms, h->tm0, h->tm1));
+  return 0;
+}
+
+int trpl_flush_l2(trpl_handle* h) {
+  if (!h) return fail("null handle");
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = (size_t)256 << 20;
+  CU(h->d_flush.reserve(bytes));
+  CU(cudaMemsetAsync(h->d_flush.p, 1, bytes, h->stream));
+  return 0;
+}
+
+int trpl_fp64_peak_probe(trpl_handle* h, int32_t iters, double* tflops, float* ms_out) {
+  if (!h || !tflops) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  const int threads = 256, blocks = h->prop.multiProcessorCount * 8;
+  DevBuf<double> sink;
+  CU(sink.reserve((size_t)threads * blocks));
+  fp64_probe_kernel<<<blocks, threads, 0, h->stream>>>(sink.p, 1000, 1.0);   // warm-up
+  CU(cudaEventRecord(h->ev0, h->stream));
+  fp64_probe_kernel<<<blocks, threads, 0, h->stream>>>(sink.p, iters, 1.0);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->launches += 2;
+  const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+  *tflops = flops / (ms * 1e-3) / 1e12;
+  if (ms_out) *ms_out = ms;
+  return 0;
+}
+
+}  // extern "C"

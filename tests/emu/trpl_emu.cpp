@@ -1,0 +1,76 @@
+// trpl_emu.cpp - host lock-step build of the SAME integrator source the CUDA kernel compiles
+// (metrotrpl_b200/csrc/trajectory.h) with TRPL_HOST_EMU.  Test infrastructure only: it lets the
+// CPU-only test tier exercise the warp algorithm (partition + PCR solve, RODAS4 controller, Hermite
+// readout, likelihood) against the oracle.  It is built and loaded by tests/ only and is never
+// reachable from the metrotrpl_b200 package.
+#define TRPL_HOST_EMU 1
+#include <stdint.h>
+#include <string.h>
+#include "../../include/metrotrpl_b200.h"
+#include "../../metrotrpl_b200/csrc/trajectory.h"
+
+using namespace trpl;
+
+template <int NPL, int MODEL>
+static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const double* times,
+                    const double* vals, const double* uncs, const double* profiles, int n_sets,
+                    const double* params, const double* aux, const SolverOpts& opt, double* logll,
+                    int32_t* status, int32_t* nsteps, double* curves) {
+  const int n_traj = n_sets * n_meas;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int traj = 0; traj < n_traj; ++traj) {
+    const int set = traj / n_meas, mi = traj % n_meas;
+    const MeasDesc* md = meas + mi;
+    simt::LaneMem sm(Slots<NPL, MODEL>::COUNT);
+    TrajIn in;
+    in.par = params + (size_t)set * TRPL_NPARAM;
+    in.md = md;
+    in.times = times + md->t_off;
+    in.vals = vals ? vals + md->t_off : nullptr;
+    in.uncs = uncs ? uncs + md->t_off : nullptr;
+    in.profile = profiles ? profiles + md->prof_off : nullptr;
+    const double* ax = aux + (size_t)traj * TRPL_NAUX;
+    in.scale_shift = ax[TRPL_A_SCALE_SHIFT];
+    in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
+    in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
+    in.curve = curves ? curves + (size_t)set * n_times_total + md->t_off : nullptr;
+    TrajOut out;
+    run_trajectory<NPL, MODEL>(in, opt, sm, out);
+    for (int k = 0; k < 3; ++k) logll[3 * (size_t)traj + k] = out.logll[k];
+    status[traj] = out.status;
+    if (nsteps) { nsteps[2 * traj] = out.n_acc; nsteps[2 * traj + 1] = out.n_rej; }
+  }
+}
+
+template <int MODEL>
+static int dispatch(int max_nx, int n_meas, const MeasDesc* meas, int n_times_total,
+                    const double* times, const double* vals, const double* uncs,
+                    const double* profiles, int n_sets, const double* params, const double* aux,
+                    const SolverOpts& opt, double* logll, int32_t* status, int32_t* nsteps,
+                    double* curves) {
+#define GO(N) run_all<N, MODEL>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves)
+  if (max_nx <= 32) GO(1);
+  else if (max_nx <= 64) GO(2);
+  else if (max_nx <= 128) GO(4);
+  else if (max_nx <= 256) GO(8);
+  else return 1;
+#undef GO
+  return 0;
+}
+
+extern "C" int trpl_emu_loglik_batch(int32_t model, int32_t n_meas, const trpl_meas_desc* meas,
+                                     int32_t n_times_total, const double* times, const double* vals,
+                                     const double* uncs, const double* profiles, int32_t n_sets,
+                                     const double* params, const double* aux,
+                                     const trpl_solver_opts* opts, double* logll, int32_t* status,
+                                     int32_t* nsteps, double* curves) {
+  static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch");
+  SolverOpts opt;
+  memcpy(&opt, opts, sizeof(opt));
+  int max_nx = 0;
+  for (int i = 0; i < n_meas; ++i) if (meas[i].nx > max_nx) max_nx = meas[i].nx;
+  const MeasDesc* md = reinterpret_cast<const MeasDesc*>(meas);
+  if (model == TRPL_MODEL_STD)
+    return dispatch<MODEL_STD>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves);
+  return dispatch<MODEL_TRAPS>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves);
+}

@@ -1,0 +1,82 @@
+"""CPU tier: the shared library loads and exports every entry point include/metrotrpl_b200.h
+declares; the ctypes structs match the C structs; host-side packing rejects what the reference
+rejects.  No compute calls (no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from metrotrpl_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "metrotrpl_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(trpl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _capi.load_library()
+    names = declared_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.trpl_abi_version() == 1
+
+
+def test_struct_layouts():
+    assert C.sizeof(_capi.MeasDesc) == 56
+    assert C.sizeof(_capi.SolverOpts) == 32
+    assert _capi.MeasDesc.nx.offset == 24 and _capi.MeasDesc.prof_off.offset == 48
+
+
+def test_create_without_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(_capi.TrplError) as e:
+        _capi.Context(0)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_packing_mirrors_reference_errors():
+    sim = {"num_meas": 1, "lengths": [311], "nx": [128], "meas_types": ["TRPL"]}
+    t = np.linspace(0, 10, 11)
+    with pytest.raises(ValueError, match="Expected 128 initial densities"):
+        _capi.pack_problem(sim, [np.ones(100)], [t])                       # forward_solver.py:104
+    with pytest.raises(ValueError, match="times must start at t=0"):
+        _capi.pack_problem(sim, [np.ones(128)], [t + 1])                   # sim_utils.py:271
+    with pytest.raises(ValueError, match="Invalid ini_mode"):
+        _capi.pack_problem(sim, [np.ones(128)], [t], ini_mode="bogus")     # forward_solver.py:117
+    with pytest.raises(ValueError, match="Invalid model"):
+        _capi.pack_problem(sim, [np.ones(128)], [t], model="bogus")        # forward_solver.py:140
+    with pytest.raises(ValueError, match="Expected only fluence"):
+        _capi.pack_problem(sim, [np.ones(5)], [t], ini_mode="fluence")     # forward_solver.py:115
+    with pytest.raises(NotImplementedError):
+        _capi.pack_problem(dict(sim, meas_types=["XRD"]), [np.ones(128)], [t])
+    p = _capi.pack_problem(sim, [np.array([1e12, 6e4, -1])], [t], ini_mode="fluence")
+    assert p.meas[0].ini_dir == -1 and p.meas[0].ini_a == 1e12
+    p = _capi.pack_problem(sim, [np.array([1e12, 6e4])], [t], ini_mode="fluence")
+    assert p.meas[0].ini_dir == 1
+
+
+def test_param_packing_applies_units():
+    names = "n0 p0 mu_n mu_p ks Cn Cp Sf Sb tauN tauP eps Tm m".split()
+    idx = {n: i for i, n in enumerate(names)}
+    units = np.arange(1, 15, dtype=float)
+    st = np.ones((2, 14)) * 2
+    out = _capi.pack_params(st, idx, units)
+    assert out.shape == (2, 16)
+    for slot, n in enumerate(_capi.PARAM_SLOTS[:13]):
+        assert out[0, slot] == 2 * units[idx[n]]
+    assert out[0, 15] == 1.0       # tauE placeholder for the std model
+
+
+def test_tolerance_mapping():
+    assert _capi.effective_tolerances(None, None) == (1e-7, 1e-20)
+    assert _capi.effective_tolerances(1e-5, 1e-8) == (1e-5, 1e-20)
+    assert _capi.effective_tolerances(1e-5, 1e-25) == (1e-5, 1e-25)

@@ -1,0 +1,31 @@
+"""CPU tier: the kernel's own integrator source, compiled for the host in lock-step (tests/emu),
+against the oracle, the golden fixtures and closed forms.  This validates the warp algorithm
+(partition + PCR block-tridiagonal solve, RODAS4 controller, Hermite readout, in-kernel
+likelihood) without a GPU; the GPU tier (test_gpu_parity.py) repeats every case through the C ABI.
+"""
+import numpy as np
+import pytest
+
+from tests import parity_cases as pc
+from tests.emu import emu
+
+
+def backend(prob, params, aux, opts, want_curves):
+    return emu.loglik_batch(prob, params, aux, opts, want_curves)
+
+
+def test_staub_fixture_rtol_1e7():
+    rep = pc.check_staub(backend, rtol=1e-7)
+    print(rep)
+
+
+def test_known_answers_of_reference_tests():
+    print(pc.check_known_answers(backend))
+
+
+def test_closed_forms():
+    print(pc.check_analytic(backend))
+
+
+def test_ragged_and_fluence_inputs():
+    assert pc.check_edges(backend)

@@ -1,0 +1,102 @@
+"""GPU tier: every parity case through the CUDA library's C ABI (include/metrotrpl_b200.h).
+
+These tests fail loudly if the library is missing or no device is present - there is no fallback.
+"""
+import numpy as np
+import pytest
+
+from metrotrpl_b200 import _capi
+from tests import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _capi.Context(0)
+    yield c
+    c.close()
+
+
+def make_backend(ctx):
+    def backend(prob, params, aux, opts, want_curves):
+        ctx.set_problem(prob)
+        return ctx.loglik_batch(params, aux, opts, want_curves=want_curves)
+    return backend
+
+
+def test_device_is_blackwell(ctx):
+    info = ctx.device_info()
+    print(info)
+    assert info["sm_count"] > 0
+
+
+def test_staub_fixture_rtol_1e7(ctx):
+    rep = pc.check_staub(make_backend(ctx), rtol=1e-7)
+    print(rep)
+    assert ctx.launch_count() >= 1
+
+
+def test_staub_fixture_rtol_1e6(ctx):
+    print(pc.check_staub(make_backend(ctx), rtol=1e-6))
+
+
+def test_known_answers_of_reference_tests(ctx):
+    print(pc.check_known_answers(make_backend(ctx)))
+
+
+def test_closed_forms(ctx):
+    print(pc.check_analytic(make_backend(ctx)))
+
+
+def test_ragged_and_fluence_inputs(ctx):
+    assert pc.check_edges(make_backend(ctx))
+
+
+def test_gpu_matches_host_lockstep_build(ctx):
+    """Same source, two compilers: device results equal the host lock-step build to rounding."""
+    from tests.emu import emu
+    g, prob, params, aux = pc.staub_problem()
+    opts = _capi.make_opts(RTOL=1e-7)
+    ctx.set_problem(prob)
+    ll_g, st_g, ns_g, cur_g = ctx.loglik_batch(params[:4], aux[:4], opts, want_curves=True)
+    ll_e, st_e, ns_e, cur_e = emu.loglik_batch(prob, params[:4], aux[:4], opts, True)
+    ok = cur_e > 1e-200
+    np.testing.assert_allclose(cur_g[ok], cur_e[ok], rtol=1e-6)
+    assert np.abs(ns_g[..., 0] - ns_e[..., 0]).max() <= 3
+
+
+def test_full_size_batch_properties(ctx):
+    """BASELINE configs[1] size (4096 sets x 6 curves): size-independent properties.
+    (a) permutation invariance: shuffling the parameter sets permutes the results bit-exactly;
+    (b) replicated sets give bit-identical results wherever they land in the batch;
+    (c) monotonicity: PL of every non-floored curve is positive and finite."""
+    g, prob, params, aux = pc.staub_problem()
+    rng = np.random.default_rng(5)
+    n = 4096
+    pick = rng.integers(0, len(pc.CLEAN_STATES), n)
+    base = np.array(pc.CLEAN_STATES)[pick]
+    P = params[base].copy()
+    jitter = 10 ** rng.uniform(-0.05, 0.05, size=(n, 11))
+    P[:, 1:12] *= jitter          # perturb everything but n0 and the trap slots
+    P[:, _capi.PARAM_SLOTS.index("eps")] = params[0, _capi.PARAM_SLOTS.index("eps")]
+    P[-1] = P[0]                  # (b) replica
+    A = np.repeat(aux[:1], n, axis=0)
+    opts = _capi.make_opts(RTOL=1e-6)
+    ctx.set_problem(prob)
+    ll, st, ns, cur = ctx.loglik_batch(P, A, opts, want_curves=True)
+    assert np.all(np.isfinite(ll))
+    np.testing.assert_array_equal(ll[0], ll[-1])
+    np.testing.assert_array_equal(cur[0], cur[-1])
+    perm = rng.permutation(n)
+    ll2, st2, ns2, cur2 = ctx.loglik_batch(P[perm], A[perm], opts, want_curves=True)
+    np.testing.assert_array_equal(ll2, ll[perm])
+    np.testing.assert_array_equal(cur2, cur[perm])
+    assert np.all(cur > 0) and np.all(np.isfinite(cur))
+    assert np.all(st == 0)
+    print("steps: mean", ns[..., 0].mean(), "max", ns[..., 0].max(), "kernel ms", ctx.last_kernel_ms())
+
+
+def test_no_device_no_fallback():
+    with pytest.raises(_capi.TrplError):
+        _capi.Context(99)
