@@ -59,11 +59,14 @@ def test_gpu_matches_host_lockstep_build(ctx):
     g, prob, params, aux = pc.staub_problem()
     opts = _capi.make_opts(RTOL=1e-7)
     ctx.set_problem(prob)
-    ll_g, st_g, ns_g, cur_g = ctx.loglik_batch(params[:4], aux[:4], opts, want_curves=True)
-    ll_e, st_e, ns_e, cur_e = emu.loglik_batch(prob, params[:4], aux[:4], opts, True)
-    ok = cur_e > 1e-200
-    np.testing.assert_allclose(cur_g[ok], cur_e[ok], rtol=1e-6)
-    assert np.abs(ns_g[..., 0] - ns_e[..., 0]).max() <= 3
+    sel = pc.CLEAN_STATES[:4]
+    ll_g, st_g, ns_g, cur_g = ctx.loglik_batch(params[sel], aux[sel], opts, want_curves=True)
+    ll_e, st_e, ns_e, cur_e = emu.loglik_batch(prob, params[sel], aux[sel], opts, True)
+    # nvcc contracts a*b+c into FMAs, g++ is built with -ffp-contract=off: agreement is to
+    # integrator tolerance, not bitwise
+    np.testing.assert_allclose(cur_g, cur_e, rtol=5e-7)
+    np.testing.assert_allclose(ll_g, ll_e, rtol=1e-6)
+    assert np.abs(ns_g[..., 0] - ns_e[..., 0]).max() <= 5
 
 
 def test_full_size_batch_properties(ctx):
