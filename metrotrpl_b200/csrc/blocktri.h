@@ -65,18 +65,20 @@ TRPL_FN V2 add_mv(const V2& r, const Blk& m, const V2& v) {
   V2 o; o.x = fmadd(m.a01, v.y, fmadd(m.a00, v.x, r.x)); o.y = fmadd(m.a11, v.y, fmadd(m.a10, v.x, r.y)); return o;
 }
 
-// shared-memory slot map of one factorisation (per lane; every entry is one double slot)
+// shared-memory slot map of one factorisation (per lane; every entry is one double slot).
+// Structural zeros are not stored: super-diagonal blocks have a01 == 0 (dN_i/dt does not see
+// Q_{i+2}), sub-diagonal blocks have a10 == 0 (dQ_{i+1}/dt does not see N_{i-1}).
 template <int NPL>
 struct FacSlots {
   static constexpr int NI = NPL - 1;                 // interior rows per lane
-  static constexpr int DINV = 0;                     // NI blocks
-  static constexpr int LMUL = DINV + 4 * NI;         // NI blocks (index 0 unused)
-  static constexpr int CSUP = LMUL + 4 * NI;         // NI blocks: super-diagonal of interior rows (last one couples to z_l)
-  static constexpr int VSPK = CSUP + 4 * NI;         // NI blocks
-  static constexpr int WSPK = VSPK + 4 * NI;         // NI blocks
-  static constexpr int AZ = WSPK + 4 * NI;           // 1 block
-  static constexpr int CZ = AZ + 4;                  // 1 block
-  static constexpr int COUNT = CZ + 4;
+  static constexpr int DINV = 0;                     // NI full blocks
+  static constexpr int LMUL = DINV + 4 * NI;         // NI-1 full blocks (rows 1..NI-1)
+  static constexpr int CSUP = LMUL + 4 * (NI > 0 ? NI - 1 : 0);   // NI lower-triangular blocks (3 entries)
+  static constexpr int VSPK = CSUP + 3 * NI;         // NI full blocks
+  static constexpr int WSPK = VSPK + 4 * NI;         // NI full blocks
+  static constexpr int AZ = WSPK + 4 * NI;           // upper-triangular (3 entries)
+  static constexpr int CZ = AZ + 3;                  // lower-triangular (3 entries)
+  static constexpr int COUNT = CZ + 3;
 };
 
 TRPL_FN void st_blk(LaneMem& sm, int slot, const Blk& b) {
@@ -84,6 +86,18 @@ TRPL_FN void st_blk(LaneMem& sm, int slot, const Blk& b) {
 }
 TRPL_FN Blk ld_blk(const LaneMem& sm, int slot) {
   Blk b; b.a00 = sm.ld(slot); b.a01 = sm.ld(slot + 1); b.a10 = sm.ld(slot + 2); b.a11 = sm.ld(slot + 3); return b;
+}
+// triangular blocks: {a00, off-diagonal, a11}
+struct Tri { real a00, off, a11; };
+TRPL_FN void st_lower(LaneMem& sm, int slot, const Blk& b) { sm.st(slot, b.a00); sm.st(slot + 1, b.a10); sm.st(slot + 2, b.a11); }
+TRPL_FN void st_upper(LaneMem& sm, int slot, const Blk& b) { sm.st(slot, b.a00); sm.st(slot + 1, b.a01); sm.st(slot + 2, b.a11); }
+TRPL_FN Tri ld_tri(const LaneMem& sm, int slot) { Tri t; t.a00 = sm.ld(slot); t.off = sm.ld(slot + 1); t.a11 = sm.ld(slot + 2); return t; }
+// r - M v for M lower triangular (a01 == 0) / upper triangular (a10 == 0)
+TRPL_FN V2 sub_mv_lower(const V2& r, const Tri& m, const V2& v) {
+  V2 o; o.x = fmadd(-m.a00, v.x, r.x); o.y = fmadd(-m.a11, v.y, fmadd(-m.off, v.x, r.y)); return o;
+}
+TRPL_FN V2 sub_mv_upper(const V2& r, const Tri& m, const V2& v) {
+  V2 o; o.x = fmadd(-m.off, v.y, fmadd(-m.a00, v.x, r.x)); o.y = fmadd(-m.a11, v.y, r.y); return o;
 }
 
 // register-resident part of the factorisation (PCR multipliers of the reduced system)
@@ -120,13 +134,13 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
     }
     TRPL_UNROLL for (int j = 0; j < NI; ++j) {
       st_blk(sm, base + S::DINV + 4 * j, dinv[j]);
-      if (j > 0) st_blk(sm, base + S::LMUL + 4 * j, lm[j]);
-      st_blk(sm, base + S::CSUP + 4 * j, C[j]);
+      if (j > 0) st_blk(sm, base + S::LMUL + 4 * (j - 1), lm[j]);
+      st_lower(sm, base + S::CSUP + 3 * j, C[j]);
       st_blk(sm, base + S::VSPK + 4 * j, v[j]);
       st_blk(sm, base + S::WSPK + 4 * j, w[j]);
     }
-    st_blk(sm, base + S::AZ, A[NPL - 1]);
-    st_blk(sm, base + S::CZ, C[NPL - 1]);
+    st_upper(sm, base + S::AZ, A[NPL - 1]);
+    st_lower(sm, base + S::CZ, C[NPL - 1]);
     // reduced (interface) row of this lane
     const Blk v0n = blk_shfl_down(v[0], 1);
     const Blk w0n = blk_shfl_down(w[0], 1);
@@ -170,15 +184,15 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const LaneMem& sm, int base, const PcrFac& p
   if constexpr (NI > 0) {
     // interior forward / backward sweep
     g[0] = r[0];
-    TRPL_UNROLL for (int j = 1; j < NI; ++j) g[j] = sub_mv(r[j], ld_blk(sm, base + S::LMUL + 4 * j), g[j - 1]);
+    TRPL_UNROLL for (int j = 1; j < NI; ++j) g[j] = sub_mv(r[j], ld_blk(sm, base + S::LMUL + 4 * (j - 1)), g[j - 1]);
     g[NI - 1] = blk_mv(ld_blk(sm, base + S::DINV + 4 * (NI - 1)), g[NI - 1]);
     TRPL_UNROLL for (int j = NI - 2; j >= 0; --j) {
-      const V2 t = sub_mv(g[j], ld_blk(sm, base + S::CSUP + 4 * j), g[j + 1]);
+      const V2 t = sub_mv_lower(g[j], ld_tri(sm, base + S::CSUP + 3 * j), g[j + 1]);
       g[j] = blk_mv(ld_blk(sm, base + S::DINV + 4 * j), t);
     }
     V2 g0n; g0n.x = shfl_down(g[0].x, 1); g0n.y = shfl_down(g[0].y, 1);
-    rr = sub_mv(r[NPL - 1], ld_blk(sm, base + S::AZ), g[NI - 1]);
-    rr = sub_mv(rr, ld_blk(sm, base + S::CZ), g0n);      // CZ is zero on the last lane
+    rr = sub_mv_upper(r[NPL - 1], ld_tri(sm, base + S::AZ), g[NI - 1]);
+    rr = sub_mv_lower(rr, ld_tri(sm, base + S::CZ), g0n);      // CZ is zero on the last lane
   } else {
     rr = r[0];
   }

@@ -73,15 +73,28 @@ struct NodeMask {
   mask first_lane;       // lane 0 (owns node 0)
 };
 
-template <int NPL>
+// FULL: L == 32*NPL is known at compile time (no padding), so every mask but the two contact
+// lanes folds to a constant and the selects disappear from the unrolled node loops.
+template <int NPL, bool FULL>
 TRPL_FN NodeMask<NPL> make_mask(int L) {
   NodeMask<NPL> m;
   const ivec base = imul(lane_id(), NPL);
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    const ivec i = iadd(base, j);
-    m.real_node[j] = i < L;
-    m.last_node[j] = i == (L - 1);
-    m.inner_face[j] = i < (L - 1);
+    if (FULL) {
+      m.real_node[j] = mconst(true);
+      if (j == NPL - 1) {
+        m.last_node[j] = lane_id() == 31;
+        m.inner_face[j] = lane_id() < 31;
+      } else {
+        m.last_node[j] = mconst(false);
+        m.inner_face[j] = mconst(true);
+      }
+    } else {
+      const ivec i = iadd(base, j);
+      m.real_node[j] = i < L;
+      m.last_node[j] = i == (L - 1);
+      m.inner_face[j] = i < (L - 1);
+    }
   }
   m.first_lane = lane_id() == 0;
   return m;
@@ -100,6 +113,18 @@ template <int NPL>
 struct RhsAux {
   real p[NPL];     // hole density
 };
+
+// hole density from the state: P_i = N_i [+ Ntrap_i] + (p0 - n0) + Q_{i+1} - Q_i
+template <int NPL, int MODEL>
+TRPL_FN void holes(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u, real (&P)[NPL]) {
+  real ql0 = shfl_up(u.q[NPL - 1], 1);
+  ql0 = sel(m.first_lane, 0.0, ql0);
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const real ql = (j == 0) ? ql0 : u.q[j - 1];
+    P[j] = u.n[j] + c.d0 + (u.q[j] - ql);
+    if (MODEL == MODEL_TRAPS) P[j] = P[j] + u.t[j];
+  }
+}
 
 // Right-hand side f(u).  Also returns P for the readout / error scale.
 template <int NPL, int MODEL>
@@ -186,11 +211,15 @@ struct JacTraps {
 
 template <int NPL, int MODEL>
 TRPL_FN void jacobian(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u,
-                      const RhsAux<NPL>& aux, Blk (&A)[NPL], Blk (&B)[NPL], Blk (&C)[NPL],
-                      JacTraps<NPL>& jt) {
-  const real* P = aux.p;
+                      Blk (&A)[NPL], Blk (&B)[NPL], Blk (&C)[NPL], JacTraps<NPL>& jt) {
   real ql0 = shfl_up(u.q[NPL - 1], 1);
   ql0 = sel(m.first_lane, 0.0, ql0);
+  real P[NPL];
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    const real ql = (j == 0) ? ql0 : u.q[j - 1];
+    P[j] = u.n[j] + c.d0 + (u.q[j] - ql);
+    if (MODEL == MODEL_TRAPS) P[j] = P[j] + u.t[j];
+  }
   const real n_prev = shfl_up(u.n[NPL - 1], 1);
   const real n_next = shfl_down(u.n[0], 1);
   const real p_next = shfl_down(P[0], 1);

@@ -44,7 +44,18 @@ TRPL_FN bool warp_any(mask m) { return __any_sync(FULL, m) != 0; }
 TRPL_FN unsigned warp_ballot(mask m) { return __ballot_sync(FULL, m); }
 TRPL_FN mask lane_lt(ivec l, int k) { return l < k; }
 TRPL_FN real fmadd(real a, real b, real c) { return fma(a, b, c); }
-TRPL_FN real rcp(real x) { return 1.0 / x; }
+// Reciprocal: hardware seed (MUFU.RCP64H, ~2^-23) + two Newton steps, no special-case slow path.
+// Every argument on this path is a finite, normal, non-zero number (densities, determinants of
+// diagonally dominated blocks, error scales), so the IEEE corner cases of `1.0 / x` are not needed.
+TRPL_FN real rcp(real x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
 TRPL_FN real vabs(real x) { return fabs(x); }
 TRPL_FN real vmax(real a, real b) { return fmax(a, b); }
 TRPL_FN real vmin(real a, real b) { return fmin(a, b); }

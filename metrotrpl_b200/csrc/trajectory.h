@@ -102,7 +102,8 @@ struct Slots {
   static constexpr int KSTRIDE = NC * NPL;
   static constexpr int KBASE = 0;
   static constexpr int NKS = 5;                                // stages kept (the 6th is consumed in registers)
-  static constexpr int FAC = KBASE + NKS * KSTRIDE;
+  static constexpr int F0 = KBASE + NKS * KSTRIDE;             // f(u) of the current step (for retries)
+  static constexpr int FAC = F0 + KSTRIDE;
   static constexpr int TRAP = FAC + FacSlots<NPL>::COUNT;      // traps: 5 condensation coefficients per node
   static constexpr int COUNT = TRAP + ((MODEL == MODEL_TRAPS) ? 5 * NPL : 0);
   static constexpr int BYTES = COUNT * 32 * 8;
@@ -191,14 +192,22 @@ TRPL_FN real hermite_eval(const HermiteCoef& k, real tq) {
 }
 
 // ---- the trajectory -------------------------------------------------------------------------
-template <int NPL, int MODEL>
+// Control flow is a small state machine so that the right-hand side, the readout/emit block and the
+// linear solve each exist at exactly ONE code site (the kernel is instruction-cache sensitive):
+//   PH_ACCEPTED  evaluate f(u) at the newly accepted state, read the signal out, emit measurement
+//                times, then start a step (Jacobian + factorisation), stage 1 uses f(u)
+//   PH_STAGE     evaluate f(stage argument), add the c-combination, solve
+//   PH_RETRY     step rejected: same u, same f(u) (kept in shared memory), new h
+enum Phase { PH_ACCEPTED = 0, PH_STAGE = 1, PH_RETRY = 2 };
+
+template <int NPL, int MODEL, bool FULL>
 TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm, TrajOut& out) {
   typedef Slots<NPL, MODEL> SL;
   typedef Vec<NPL, MODEL> V;
   const MeasDesc& md = *in.md;
   const int L = md.nx;
   const Coef c = make_coef(in.par, md.thickness, L);
-  const NodeMask<NPL> m = make_mask<NPL>(L);
+  const NodeMask<NPL> m = make_mask<NPL, FULL>(L);
   const ivec lane = lane_id();
   const ivec node0 = imul(lane, NPL);
   const int n_t = md.n_t;
@@ -213,8 +222,7 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       const ivec i = iadd(node0, j);
       real dn;
       if (md.ini_mode == 0) {
-        const ivec src = i;
-        dn = gather(in.profile, src, m.real_node[j], 0.0) * 1e-21;
+        dn = gather(in.profile, i, m.real_node[j], 0.0) * 1e-21;
       } else {
         const double fluence = md.ini_a * in.fl_mult * 1e-14;
         const double alpha = md.ini_b * in.al_mult * 1e-7;
@@ -249,168 +257,167 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   History H; H.n = 0;
   TRPL_UNROLL for (int k = 0; k < 3; ++k) { H.t[k] = 0; H.v[k] = 0; H.d[k] = 0; }
 
-  V f0; RhsAux<NPL> aux0;
-  rhs<NPL, MODEL>(c, m, u, f0, aux0);
-  double val, dval;
-  readout<NPL, MODEL>(c, m, md.meas_type, u, f0, aux0, val, dval);
-
-  // emit every measurement time in (t_prev, t]; lanes work on consecutive indices
-  auto emit = [&](double t_now, bool fill_floor) {
-    HermiteCoef hc;
-    bool have_hc = false;
-    while (io < n_t) {
-      const ivec k = iadd(lane, io);
-      const mask in_range = k < n_t;
-      const real tq = gather(in.times, k, in_range, DBL_MAX);
-      const mask due = fill_floor ? in_range : mand(in_range, tq <= t_now);
-      const unsigned bits = warp_ballot(due);
-      if (bits == 0u) break;
-      int cnt = 0;
-      { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }   // contiguous from lane 0 (times ascend)
-      real y;
-      if (fill_floor) {
-        y = splat(DBL_MIN);
-      } else if (H.n < 2) {
-        y = splat(H.v[2]);                                         // t == 0
-      } else {
-        if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
-        y = hermite_eval(hc, tq);
-        y = sel(tq >= H.t[2], H.v[2], y);                          // exact on the step end
-      }
-      // forward_solver.py:190-192: from the first value below DBL_MIN on, the curve is DBL_MIN
-      const mask take = lane < cnt;
-      if (!floored) {
-        const unsigned low = warp_ballot(mand(take, y < DBL_MIN));
-        if (low != 0u) {
-          int first = 0; { unsigned b = low; while (!(b & 1u)) { ++first; b >>= 1; } }
-          y = sel(lane >= first, DBL_MIN, y);
-          floored = true; status |= ST_FLOORED;
-        }
-      } else {
-        y = splat(DBL_MIN);
-      }
-      if (in.curve) scatter(in.curve, k, take, y);
-      if (want_ll) {
-        // trial_move_evaluation.py:117-130 and :147-156
-        const mask neg = mand(take, y < 0.0);
-        nneg = nneg + sel(neg, 1.0, 0.0);
-        const real ya = vabs(y);
-        const real vk = gather(in.vals, k, take, 0.0);
-        const real uk = gather(in.uncs, k, take, 1.0);
-        const real r = (vlog10(ya) + in.scale_shift) - vk;
-        const real r2 = r * r;
-        const real u2 = 2.0 * (uk * uk);
-        ll0 = ll0 + sel(take, r2 / (in.s2T[0] + u2), 0.0);
-        ll1 = ll1 + sel(take, r2 / (in.s2T[1] + u2), 0.0);
-        ll2 = ll2 + sel(take, r2 / (in.s2T[2] + u2), 0.0);
-      }
-      io += cnt;
-      if (cnt < 32) break;
+  // likelihood contribution of a batch of emitted values (trial_move_evaluation.py:117-130, :147-156)
+  auto accumulate = [&](const ivec& k, const mask& take, const real& y) {
+    if (in.curve) scatter(in.curve, k, take, y);
+    if (want_ll) {
+      nneg = nneg + sel(mand(take, y < 0.0), 1.0, 0.0);
+      const real vk = gather(in.vals, k, take, 0.0);
+      const real uk = gather(in.uncs, k, take, 1.0);
+      const real r = (vlog10(vabs(y)) + in.scale_shift) - vk;
+      const real r2 = r * r;
+      const real u2 = 2.0 * (uk * uk);
+      ll0 = ll0 + sel(take, r2 * rcp(in.s2T[0] + u2), 0.0);
+      ll1 = ll1 + sel(take, r2 * rcp(in.s2T[1] + u2), 0.0);
+      ll2 = ll2 + sel(take, r2 * rcp(in.s2T[2] + u2), 0.0);
     }
   };
 
-  H.t[2] = 0.0; H.v[2] = val; H.d[2] = dval; H.n = 1;
-  emit(0.0, false);
-
-  // ---- initial step (Hairer's d0/d1 rule on the scaled norms) ----
-  double h;
-  {
-    real s0 = splat(0.0), s1 = splat(0.0);
-    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      const real scn = fmadd(opt.rtol, vabs(u.n[j]), opt.atol);
-      const real scq = fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(aux0.p[j])), opt.atol);
-      const real a = u.n[j] / scn, b = f0.n[j] / scn, q = u.q[j] / scq, g = f0.q[j] / scq;
-      s0 = s0 + sel(m.real_node[j], fmadd(a, a, q * q), 0.0);
-      s1 = s1 + sel(m.real_node[j], fmadd(b, b, g * g), 0.0);
-    }
-    const double d0 = sqrt(uni(warp_sum(s0))), d1 = sqrt(uni(warp_sum(s1)));
-    h = (d1 > 0.0 && d0 > 0.0) ? 0.01 * d0 / d1 : 1e-6;
-    h = fmin(h, 1e-3 * fmax(tend, 1e-300));
-    if (!(h > 0.0)) h = 1e-6;
-  }
-  double err_old = 1e-4, h_acc = h;
-  bool first = true, last_rejected = false;
+  double h = 0.0, h_new = 0.0, gi = 0.0, ih = 0.0;
+  double err_old = 1e-4, h_acc = 0.0;
+  bool first = true, last_rejected = false, final_step = false;
   const double inv_n = 1.0 / (2.0 * L + ((MODEL == MODEL_TRAPS) ? L : 0));
   const double h_min = 1e-14 * fmax(tend, 1e-300);
+  int phase = PH_ACCEPTED;
+  int s = 0;
+  V us = u;       // argument of the next right-hand-side evaluation
+  V cs;           // sum_j c_sj / h K_j of the current stage
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) { cs.n[j] = splat(0.0); cs.q[j] = splat(0.0); }
+  TRPL_UNROLL for (int j = 0; j < (MODEL == MODEL_TRAPS ? NPL : 1); ++j) cs.t[j] = splat(0.0);
+  PcrFac pf;
 
-  while (io < n_t) {
-    if (n_acc + n_rej >= opt.max_steps) { status |= ST_MAX_STEPS; break; }
-    if (opt.hmax > 0.0) h = fmin(h, opt.hmax);
-    bool final_step = false;
-    if (t + 1.01 * h >= tend) { h = tend - t; final_step = true; }
-    if (h < h_min) { status |= ST_H_UNDERFLOW; break; }
-
-    // ---- W = 1/(gamma h) I - J, factorised ----
-    const double gi = 1.0 / (RODAS4_GAMMA * h);
-    const double ih = 1.0 / h;
-    PcrFac pf;
-    {
-      Blk A[NPL], B[NPL], C[NPL];
-      JacTraps<NPL> jt;
-      jacobian<NPL, MODEL>(c, m, u, aux0, A, B, C, jt);
-      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-        A[j] = blk_neg(A[j]); C[j] = blk_neg(C[j]);
-        B[j].a00 = gi - B[j].a00; B[j].a01 = -B[j].a01; B[j].a10 = -B[j].a10; B[j].a11 = gi - B[j].a11;
-      }
-      // the front contact has no left neighbour (Q_0 is the fixed corner field)
-      A[0] = blk_sel(m.first_lane, blk_zero(), A[0]);
-      if (MODEL == MODEL_TRAPS) {
-        // condense the node-local trap occupancy out of the block rows
-        real idt[NPL], g_n[NPL];
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          idt[j] = rcp(gi - jt.ft_t[j]);
-          g_n[j] = jt.ft_n[j] * idt[j];           // K_T = idt * r_T + g_n * K_N
-        }
-        const real gn_next = shfl_down(g_n[0], 1);
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          const real gnn = (j == NPL - 1) ? gn_next : g_n[j + 1];
-          B[j].a00 = B[j].a00 - jt.fn_t[j] * g_n[j];
-          B[j].a10 = B[j].a10 - jt.fq_t[j] * g_n[j];
-          C[j].a10 = C[j].a10 - jt.fq_tn[j] * gnn;
-          sm.st(SL::TRAP + 5 * j + 0, idt[j]);
-          sm.st(SL::TRAP + 5 * j + 1, g_n[j]);
-          sm.st(SL::TRAP + 5 * j + 2, jt.fn_t[j]);
-          sm.st(SL::TRAP + 5 * j + 3, jt.fq_t[j]);
-          sm.st(SL::TRAP + 5 * j + 4, jt.fq_tn[j]);
-        }
-      }
-      bt_factor<NPL>(A, B, C, sm, SL::FAC, pf);
-    }
-
-    // ---- six stages ----
-    V us = u;                 // stage argument, ends up as the embedded solution, then u_new
-    V kk;                     // current stage increment
-    if (MODEL != MODEL_TRAPS) kk.t[0] = splat(0.0);
-    for (int s = 0; s < 6; ++s) {
-      V r;
-      if (s == 0) {
-        r = f0;
-      } else {
-        V cs;
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          us.n[j] = u.n[j]; us.q[j] = u.q[j]; cs.n[j] = splat(0.0); cs.q[j] = splat(0.0);
-          if (MODEL == MODEL_TRAPS) { us.t[j] = u.t[j]; cs.t[j] = splat(0.0); }
-        }
-        for (int p = 0; p < s; ++p) {
-          const double a = RODAS4_A[s][p], cc = RODAS4_C[s][p] * ih;
-          const int kb = SL::KBASE + p * SL::KSTRIDE;
-          TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-            const real kn = sm.ld(kb + SL::NC * j), kq = sm.ld(kb + SL::NC * j + 1);
-            us.n[j] = fmadd(a, kn, us.n[j]); us.q[j] = fmadd(a, kq, us.q[j]);
-            cs.n[j] = fmadd(cc, kn, cs.n[j]); cs.q[j] = fmadd(cc, kq, cs.q[j]);
-            if (MODEL == MODEL_TRAPS) {
-              const real kt = sm.ld(kb + SL::NC * j + 2);
-              us.t[j] = fmadd(a, kt, us.t[j]); cs.t[j] = fmadd(cc, kt, cs.t[j]);
+  for (;;) {
+    V r;
+    if (phase != PH_RETRY) {
+      RhsAux<NPL> aux;
+      rhs<NPL, MODEL>(c, m, us, r, aux);
+      if (phase == PH_ACCEPTED) {
+        // ---- newly accepted state (us == u): readout, history, measurement times ----
+        double val, dval;
+        readout<NPL, MODEL>(c, m, md.meas_type, u, r, aux, val, dval);
+        H.t[0] = H.t[1]; H.v[0] = H.v[1]; H.d[0] = H.d[1];
+        H.t[1] = H.t[2]; H.v[1] = H.v[2]; H.d[1] = H.d[2];
+        H.t[2] = t; H.v[2] = val; H.d[2] = dval;
+        if (H.n < 3) ++H.n;
+        {
+          HermiteCoef hc;
+          bool have_hc = false;
+          while (io < n_t) {
+            const ivec k = iadd(lane, io);
+            const mask in_range = k < n_t;
+            const real tq = gather(in.times, k, in_range, DBL_MAX);
+            const unsigned bits = warp_ballot(mand(in_range, tq <= t));
+            if (bits == 0u) break;
+            int cnt = 0;
+            { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }   // contiguous from lane 0 (times ascend)
+            real y;
+            if (H.n < 2) {
+              y = splat(val);                                            // t == 0
+            } else {
+              if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
+              y = hermite_eval(hc, tq);
+              y = sel(tq >= t, val, y);                                  // exact on the step end
             }
+            // forward_solver.py:190-192: from the first value below DBL_MIN on, the curve is DBL_MIN
+            const mask take = lane < cnt;
+            const unsigned low = warp_ballot(mand(take, y < DBL_MIN));
+            if (low != 0u) {
+              int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
+              y = sel(lane >= firstlow, DBL_MIN, y);
+              floored = true; status |= ST_FLOORED;
+            }
+            accumulate(k, take, y);
+            io += cnt;
+            if (cnt < 32 || floored) break;
           }
         }
-        RhsAux<NPL> auxs;
-        rhs<NPL, MODEL>(c, m, us, r, auxs);
+        if (io >= n_t || floored) break;     // done, or the rest of the curve is DBL_MIN by definition
+        if (n_acc == 0) {
+          // ---- initial step (Hairer's d0/d1 rule on the scaled norms) ----
+          real s0 = splat(0.0), s1 = splat(0.0);
+          TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+            const real iscn = rcp(fmadd(opt.rtol, vabs(u.n[j]), opt.atol));
+            const real iscq = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(aux.p[j])), opt.atol));
+            const real a = u.n[j] * iscn, b = r.n[j] * iscn, q = u.q[j] * iscq, g = r.q[j] * iscq;
+            s0 = s0 + sel(m.real_node[j], fmadd(a, a, q * q), 0.0);
+            s1 = s1 + sel(m.real_node[j], fmadd(b, b, g * g), 0.0);
+          }
+          const double d0 = sqrt(uni(warp_sum(s0))), d1 = sqrt(uni(warp_sum(s1)));
+          h = (d1 > 0.0 && d0 > 0.0) ? 0.01 * d0 / d1 : 1e-6;
+          h = fmin(h, 1e-3 * fmax(tend, 1e-300));
+          if (!(h > 0.0)) h = 1e-6;
+          h_acc = h;
+        } else {
+          h = h_new;
+        }
+        // keep f(u) for a possible retry
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          r.n[j] = r.n[j] + cs.n[j]; r.q[j] = r.q[j] + cs.q[j];
-          if (MODEL == MODEL_TRAPS) r.t[j] = r.t[j] + cs.t[j];
+          sm.st(SL::F0 + SL::NC * j, r.n[j]); sm.st(SL::F0 + SL::NC * j + 1, r.q[j]);
+          if (MODEL == MODEL_TRAPS) sm.st(SL::F0 + SL::NC * j + 2, r.t[j]);
         }
       }
+    }
+    if (phase != PH_STAGE) {
+      // ---- start (or restart) a step from u with step size h; stage 1 right-hand side is f(u) ----
+      if (phase == PH_RETRY) {
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          r.n[j] = sm.ld(SL::F0 + SL::NC * j); r.q[j] = sm.ld(SL::F0 + SL::NC * j + 1);
+          if (MODEL == MODEL_TRAPS) r.t[j] = sm.ld(SL::F0 + SL::NC * j + 2);
+        }
+        if (MODEL != MODEL_TRAPS) r.t[0] = splat(0.0);
+      }
+      if (n_acc + n_rej >= opt.max_steps) { status |= ST_MAX_STEPS; break; }
+      if (opt.hmax > 0.0) h = fmin(h, opt.hmax);
+      final_step = false;
+      if (t + 1.01 * h >= tend) { h = tend - t; final_step = true; }
+      if (h < h_min) { status |= ST_H_UNDERFLOW; break; }
+      gi = 1.0 / (RODAS4_GAMMA * h);
+      ih = 1.0 / h;
+      {
+        // W = 1/(gamma h) I - J, factorised
+        Blk A[NPL], B[NPL], C[NPL];
+        JacTraps<NPL> jt;
+        jacobian<NPL, MODEL>(c, m, u, A, B, C, jt);
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          A[j] = blk_neg(A[j]); C[j] = blk_neg(C[j]);
+          B[j].a00 = gi - B[j].a00; B[j].a01 = -B[j].a01; B[j].a10 = -B[j].a10; B[j].a11 = gi - B[j].a11;
+        }
+        // the front contact has no left neighbour (Q_0 is the fixed corner field)
+        A[0] = blk_sel(m.first_lane, blk_zero(), A[0]);
+        if (MODEL == MODEL_TRAPS) {
+          // condense the node-local trap occupancy out of the block rows
+          real g_n[NPL];
+          TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+            const real idt = rcp(gi - jt.ft_t[j]);
+            g_n[j] = jt.ft_n[j] * idt;              // K_T = idt * r_T + g_n * K_N
+            sm.st(SL::TRAP + 5 * j + 0, idt);
+            sm.st(SL::TRAP + 5 * j + 1, g_n[j]);
+            sm.st(SL::TRAP + 5 * j + 2, jt.fn_t[j]);
+            sm.st(SL::TRAP + 5 * j + 3, jt.fq_t[j]);
+            sm.st(SL::TRAP + 5 * j + 4, jt.fq_tn[j]);
+          }
+          const real gn_next = shfl_down(g_n[0], 1);
+          TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+            const real gnn = (j == NPL - 1) ? gn_next : g_n[j + 1];
+            B[j].a00 = B[j].a00 - jt.fn_t[j] * g_n[j];
+            B[j].a10 = B[j].a10 - jt.fq_t[j] * g_n[j];
+            C[j].a10 = C[j].a10 - jt.fq_tn[j] * gnn;
+          }
+        }
+        bt_factor<NPL>(A, B, C, sm, SL::FAC, pf);
+      }
+      s = 0;
+    } else {
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+        r.n[j] = r.n[j] + cs.n[j]; r.q[j] = r.q[j] + cs.q[j];
+        if (MODEL == MODEL_TRAPS) r.t[j] = r.t[j] + cs.t[j];
+      }
+    }
+
+    // ---- K_s = W^{-1} r ----
+    V kk;
+    if (MODEL != MODEL_TRAPS) kk.t[0] = splat(0.0);
+    {
       V2 b[NPL];
       if (MODEL == MODEL_TRAPS) {
         real w[NPL];
@@ -427,45 +434,75 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) { b[j].x = r.n[j]; b[j].y = r.q[j]; }
         bt_solve<NPL>(b, sm, SL::FAC, pf);
       }
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) { kk.n[j] = b[j].x; kk.q[j] = b[j].y; }
+    }
+
+    if (s < 5) {
+      // ---- keep K_s, build the next stage argument and c-combination ----
       const int kb = SL::KBASE + s * SL::KSTRIDE;
       TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-        kk.n[j] = b[j].x; kk.q[j] = b[j].y;
-        if (s < SL::NKS) {
-          sm.st(kb + SL::NC * j, kk.n[j]); sm.st(kb + SL::NC * j + 1, kk.q[j]);
-          if (MODEL == MODEL_TRAPS) sm.st(kb + SL::NC * j + 2, kk.t[j]);
+        sm.st(kb + SL::NC * j, kk.n[j]); sm.st(kb + SL::NC * j + 1, kk.q[j]);
+        if (MODEL == MODEL_TRAPS) sm.st(kb + SL::NC * j + 2, kk.t[j]);
+      }
+      ++s;
+      // the newest increment is still in registers; older ones come back from shared memory
+      {
+        const double a = RODAS4_A[s][s - 1], cc = RODAS4_C[s][s - 1] * ih;
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          us.n[j] = fmadd(a, kk.n[j], u.n[j]); us.q[j] = fmadd(a, kk.q[j], u.q[j]);
+          cs.n[j] = cc * kk.n[j]; cs.q[j] = cc * kk.q[j];
+          if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kk.t[j], u.t[j]); cs.t[j] = cc * kk.t[j]; }
         }
       }
+      for (int p = 0; p < s - 1; ++p) {
+        const double a = RODAS4_A[s][p], cc = RODAS4_C[s][p] * ih;
+        const int pb = SL::KBASE + p * SL::KSTRIDE;
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          const real kn = sm.ld(pb + SL::NC * j), kq = sm.ld(pb + SL::NC * j + 1);
+          us.n[j] = fmadd(a, kn, us.n[j]); us.q[j] = fmadd(a, kq, us.q[j]);
+          cs.n[j] = fmadd(cc, kn, cs.n[j]); cs.q[j] = fmadd(cc, kq, cs.q[j]);
+          if (MODEL == MODEL_TRAPS) {
+            const real kt = sm.ld(pb + SL::NC * j + 2);
+            us.t[j] = fmadd(a, kt, us.t[j]); cs.t[j] = fmadd(cc, kt, cs.t[j]);
+          }
+        }
+      }
+      phase = PH_STAGE;
+      continue;
     }
-    // us = u + sum_{j<5} a_5j K_j is the embedded (3rd-order) solution's argument; u_new = us + K_6
+
+    // ---- stage 6 done: us is the embedded (3rd order) solution, u_new = us + K_6, error = K_6 ----
     real esum = splat(0.0);
     mask bad = mconst(false);
-    V un;
+    real pold[NPL];
+    holes<NPL, MODEL>(c, m, u, pold);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      un.n[j] = us.n[j] + kk.n[j]; un.q[j] = us.q[j] + kk.q[j];
-      const real scn = fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(un.n[j])), opt.atol);
-      const real scq = fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(aux0.p[j])), opt.atol);
-      const real en = kk.n[j] / scn, eq = kk.q[j] / scq;
+      us.n[j] = us.n[j] + kk.n[j]; us.q[j] = us.q[j] + kk.q[j];
+      const real iscn = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(us.n[j])), opt.atol));
+      const real iscq = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(pold[j])), opt.atol));
+      const real en = kk.n[j] * iscn, eq = kk.q[j] * iscq;
       real e2 = fmadd(en, en, eq * eq);
       if (MODEL == MODEL_TRAPS) {
-        un.t[j] = us.t[j] + kk.t[j];
-        const real sct = fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(un.t[j]), vabs(u.n[j]))), opt.atol);
-        const real et = kk.t[j] / sct;
+        us.t[j] = us.t[j] + kk.t[j];
+        const real isct = rcp(fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(us.t[j]), vabs(u.n[j]))), opt.atol));
+        const real et = kk.t[j] * isct;
         e2 = fmadd(et, et, e2);
       }
       esum = esum + sel(m.real_node[j], e2, 0.0);
-      bad = mor(bad, mand(m.real_node[j], mor(is_nan(un.n[j]), is_nan(un.q[j]))));
+      bad = mor(bad, mand(m.real_node[j], mor(is_nan(us.n[j]), is_nan(us.q[j]))));
     }
     const double err2 = uni(warp_sum(esum)) * inv_n;
     const bool nonfinite = warp_any(bad) || !(err2 == err2) || err2 > 1e300;
     const double err = nonfinite ? 1e10 : sqrt(err2);
 
     // ---- controller (Hairer's RODAS: standard + Gustafsson predictive) ----
-    double fac = fmax(0.2, fmin(6.0, pow(err, 0.25) / 0.9));
-    double h_new = h / fac;
+    const double root4 = sqrt(sqrt(err));
+    double fac = fmax(0.2, fmin(6.0, root4 / 0.9));
+    h_new = h / fac;
     if (err <= 1.0) {
       ++n_acc;
       if (!first) {
-        double fg = (h_acc / h) * pow(err * err / err_old, 0.25) / 0.9;
+        double fg = (h_acc / h) * sqrt(sqrt(err * err / err_old)) / 0.9;
         fg = fmax(0.2, fmin(6.0, fg));
         fac = fmax(fac, fg);
         h_new = h / fac;
@@ -474,26 +511,24 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       if (last_rejected) h_new = fmin(h_new, h);
       last_rejected = false;
       t = final_step ? tend : t + h;
-      u = un;
-      rhs<NPL, MODEL>(c, m, u, f0, aux0);
-      readout<NPL, MODEL>(c, m, md.meas_type, u, f0, aux0, val, dval);
-      H.t[0] = H.t[1]; H.v[0] = H.v[1]; H.d[0] = H.d[1];
-      H.t[1] = H.t[2]; H.v[1] = H.v[2]; H.d[1] = H.d[2];
-      H.t[2] = t; H.v[2] = val; H.d[2] = dval;
-      if (H.n < 3) ++H.n;
-      emit(t, false);
-      if (floored) break;       // the rest of the curve is DBL_MIN by definition
-      h = h_new;
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+        u.n[j] = us.n[j]; u.q[j] = us.q[j];
+        if (MODEL == MODEL_TRAPS) u.t[j] = us.t[j];
+      }
+      phase = PH_ACCEPTED;
     } else {
       ++n_rej;
       last_rejected = true;
-      if (nonfinite) { h *= 0.1; } else { h = h_new; }
+      h = nonfinite ? 0.1 * h : h_new;
+      phase = PH_RETRY;
     }
   }
-  // anything not emitted (failure, or floor reached): forward_solver.py:168 + :190-192 -> DBL_MIN
-  if (io < n_t) {
-    if (!floored && (status & (ST_MAX_STEPS | ST_H_UNDERFLOW))) { floored = true; }
-    emit(tend, true);
+  // anything not emitted (floor reached, or integrator failure): forward_solver.py:168 + :190-192
+  while (io < n_t) {
+    const ivec k = iadd(lane, io);
+    const mask take = k < n_t;
+    accumulate(k, take, splat(DBL_MIN));
+    io += 32;
   }
 
   // ---- likelihood (trial_move_evaluation.py:117-166) ----

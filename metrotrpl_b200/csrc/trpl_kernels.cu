@@ -42,7 +42,7 @@ struct KernelArgs {
   SolverOpts opt;
 };
 
-template <int NPL, int MODEL>
+template <int NPL, int MODEL, bool FULL>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(const KernelArgs a) {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5;
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
     in.curve = a.curves ? a.curves + (size_t)set * a.n_times_total + md->t_off : nullptr;
     TrajOut out;
-    run_trajectory<NPL, MODEL>(in, a.opt, sm, out);
+    run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out);
     if (lane == 0) {
       a.logll[3 * (size_t)traj + 0] = out.logll[0];
       a.logll[3 * (size_t)traj + 1] = out.logll[1];
@@ -127,7 +127,7 @@ struct trpl_handle {
   DevBuf<char> d_flush;
   cudaDeviceProp prop;
   int model = 0, n_meas = 0, n_times_total = 0, max_nx = 0;
-  bool have_vals = false, have_profiles = false;
+  bool have_vals = false, have_profiles = false, all_full = false;
   DevBuf<MeasDesc> d_meas;
   DevBuf<double> d_times, d_vals, d_uncs, d_profiles;
   DevBuf<double> d_params, d_aux, d_logll, d_curves;
@@ -140,10 +140,10 @@ struct trpl_handle {
 
 namespace {
 
-template <int NPL, int MODEL>
+template <int NPL, int MODEL, bool FULL>
 int launch(trpl_handle* h, const KernelArgs& a) {
   const size_t smem = (size_t)WARPS_PER_CTA * Slots<NPL, MODEL>::BYTES;
-  auto kern = trpl_forward_kernel<NPL, MODEL>;
+  auto kern = trpl_forward_kernel<NPL, MODEL, FULL>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS_PER_CTA, smem));
@@ -165,10 +165,13 @@ int launch(trpl_handle* h, const KernelArgs& a) {
 template <int MODEL>
 int launch_npl(trpl_handle* h, const KernelArgs& a) {
   const int nx = h->max_nx;
-  if (nx <= 32) return launch<1, MODEL>(h, a);
-  if (nx <= 64) return launch<2, MODEL>(h, a);
-  if (nx <= 128) return launch<4, MODEL>(h, a);
-  if (nx <= 256) return launch<8, MODEL>(h, a);
+  // the padding-free instantiation exists for the headline grid (nx = 128) and nx = 256
+  if (h->all_full && nx == 128) return launch<4, MODEL, true>(h, a);
+  if (h->all_full && nx == 256) return launch<8, MODEL, true>(h, a);
+  if (nx <= 32) return launch<1, MODEL, false>(h, a);
+  if (nx <= 64) return launch<2, MODEL, false>(h, a);
+  if (nx <= 128) return launch<4, MODEL, false>(h, a);
+  if (nx <= 256) return launch<8, MODEL, false>(h, a);
   return fail("nx > 256 is not supported by this build");
 }
 
@@ -274,6 +277,8 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
   }
   CU(cudaStreamSynchronize(h->stream));
   h->model = model; h->n_meas = n_meas; h->n_times_total = n_times_total; h->max_nx = max_nx;
+  h->all_full = true;
+  for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) h->all_full = false;
   return 0;
 }
 

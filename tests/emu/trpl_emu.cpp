@@ -11,7 +11,7 @@
 
 using namespace trpl;
 
-template <int NPL, int MODEL>
+template <int NPL, int MODEL, bool FULL>
 static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const double* times,
                     const double* vals, const double* uncs, const double* profiles, int n_sets,
                     const double* params, const double* aux, const SolverOpts& opt, double* logll,
@@ -35,7 +35,7 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
     in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
     in.curve = curves ? curves + (size_t)set * n_times_total + md->t_off : nullptr;
     TrajOut out;
-    run_trajectory<NPL, MODEL>(in, opt, sm, out);
+    run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out);
     for (int k = 0; k < 3; ++k) logll[3 * (size_t)traj + k] = out.logll[k];
     status[traj] = out.status;
     if (nsteps) { nsteps[2 * traj] = out.n_acc; nsteps[2 * traj + 1] = out.n_rej; }
@@ -48,11 +48,15 @@ static int dispatch(int max_nx, int n_meas, const MeasDesc* meas, int n_times_to
                     const double* profiles, int n_sets, const double* params, const double* aux,
                     const SolverOpts& opt, double* logll, int32_t* status, int32_t* nsteps,
                     double* curves) {
-#define GO(N) run_all<N, MODEL>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves)
-  if (max_nx <= 32) GO(1);
-  else if (max_nx <= 64) GO(2);
-  else if (max_nx <= 128) GO(4);
-  else if (max_nx <= 256) GO(8);
+#define GO(N, F) run_all<N, MODEL, F>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves)
+  bool all_full = true;
+  for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) all_full = false;
+  if (all_full && max_nx == 128) GO(4, true);
+  else if (all_full && max_nx == 256) GO(8, true);
+  else if (max_nx <= 32) GO(1, false);
+  else if (max_nx <= 64) GO(2, false);
+  else if (max_nx <= 128) GO(4, false);
+  else if (max_nx <= 256) GO(8, false);
   else return 1;
 #undef GO
   return 0;
