@@ -37,6 +37,20 @@ TRPL_FN Blk blk_mul(const Blk& x, const Blk& y) {
   r.a10 = fmadd(x.a10, y.a00, x.a11 * y.a10); r.a11 = fmadd(x.a10, y.a01, x.a11 * y.a11);
   return r;
 }
+// -(x*y), signs folded into the operands
+TRPL_FN Blk blk_mul_neg(const Blk& x, const Blk& y) {
+  Blk r;
+  r.a00 = fmadd(-x.a00, y.a00, -(x.a01 * y.a10)); r.a01 = fmadd(-x.a00, y.a01, -(x.a01 * y.a11));
+  r.a10 = fmadd(-x.a10, y.a00, -(x.a11 * y.a10)); r.a11 = fmadd(-x.a10, y.a01, -(x.a11 * y.a11));
+  return r;
+}
+// z + x*y
+TRPL_FN Blk blk_fma(const Blk& x, const Blk& y, const Blk& z) {
+  Blk r;
+  r.a00 = fmadd(x.a01, y.a10, fmadd(x.a00, y.a00, z.a00)); r.a01 = fmadd(x.a01, y.a11, fmadd(x.a00, y.a01, z.a01));
+  r.a10 = fmadd(x.a11, y.a10, fmadd(x.a10, y.a00, z.a10)); r.a11 = fmadd(x.a11, y.a11, fmadd(x.a10, y.a01, z.a11));
+  return r;
+}
 TRPL_FN Blk blk_sub(const Blk& x, const Blk& y) {
   Blk r; r.a00 = x.a00 - y.a00; r.a01 = x.a01 - y.a01; r.a10 = x.a10 - y.a10; r.a11 = x.a11 - y.a11; return r;
 }
@@ -109,7 +123,7 @@ struct PcrFac {
 // Factorise W given by (A, B, C) blocks of this lane's rows.  `base` is the first slot to use.
 template <int NPL>
 TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[NPL], LaneMem& sm,
-                       int base, PcrFac& pf) {
+                       int base, int xch, PcrFac& pf) {
   typedef FacSlots<NPL> S;
   constexpr int NI = NPL - 1;
   Blk ra, rb, rc;
@@ -150,21 +164,28 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
   } else {
     ra = A[0]; rb = B[0]; rc = C[0];
   }
-  // parallel cyclic reduction on (ra, rb, rc) across the 32 lanes
-  const ivec lane = lane_id();
+  // Parallel cyclic reduction on (ra, rb, rc) across the 32 lanes.  Neighbour rows travel through
+  // 2 x 12 scratch slots (double buffered, one warp_sync per level) instead of 24 64-bit shuffles.
+  // No masking at the ends: ra is an exact zero block on lanes < stride and rc on lanes >= 32 -
+  // stride (they are products with the zero sub/super-diagonal of the first/last row), and
+  // out-of-range reads are clamped to the lane's own (finite) row.
   TRPL_UNROLL for (int k = 0; k < 5; ++k) {
     const int s = 1 << k;
+    const int xb = xch + 12 * (k & 1);
     const Blk bi = blk_inv(rb);
-    const Blk bi_up = blk_shfl_up(bi, s), bi_dn = blk_shfl_down(bi, s);
-    const mask has_up = lane >= s;
-    const mask has_dn = lane < (32 - s);
-    Blk alpha = blk_neg(blk_mul(ra, bi_up));
-    Blk gamma = blk_neg(blk_mul(rc, bi_dn));
-    alpha = blk_sel(has_up, alpha, blk_zero());
-    gamma = blk_sel(has_dn, gamma, blk_zero());
-    const Blk ra_up = blk_shfl_up(ra, s), rc_up = blk_shfl_up(rc, s);
-    const Blk ra_dn = blk_shfl_down(ra, s), rc_dn = blk_shfl_down(rc, s);
-    rb = blk_add(rb, blk_add(blk_mul(alpha, rc_up), blk_mul(gamma, ra_dn)));
+    st_blk(sm, xb, bi); st_blk(sm, xb + 4, ra); st_blk(sm, xb + 8, rc);
+    warp_sync();
+    const ivec up = lane_minus(s), dn = lane_plus(s);
+    Blk bi_up, ra_up, rc_up, bi_dn, ra_dn, rc_dn;
+    bi_up.a00 = sm.ld_from(xb + 0, up); bi_up.a01 = sm.ld_from(xb + 1, up); bi_up.a10 = sm.ld_from(xb + 2, up); bi_up.a11 = sm.ld_from(xb + 3, up);
+    ra_up.a00 = sm.ld_from(xb + 4, up); ra_up.a01 = sm.ld_from(xb + 5, up); ra_up.a10 = sm.ld_from(xb + 6, up); ra_up.a11 = sm.ld_from(xb + 7, up);
+    rc_up.a00 = sm.ld_from(xb + 8, up); rc_up.a01 = sm.ld_from(xb + 9, up); rc_up.a10 = sm.ld_from(xb + 10, up); rc_up.a11 = sm.ld_from(xb + 11, up);
+    bi_dn.a00 = sm.ld_from(xb + 0, dn); bi_dn.a01 = sm.ld_from(xb + 1, dn); bi_dn.a10 = sm.ld_from(xb + 2, dn); bi_dn.a11 = sm.ld_from(xb + 3, dn);
+    ra_dn.a00 = sm.ld_from(xb + 4, dn); ra_dn.a01 = sm.ld_from(xb + 5, dn); ra_dn.a10 = sm.ld_from(xb + 6, dn); ra_dn.a11 = sm.ld_from(xb + 7, dn);
+    rc_dn.a00 = sm.ld_from(xb + 8, dn); rc_dn.a01 = sm.ld_from(xb + 9, dn); rc_dn.a10 = sm.ld_from(xb + 10, dn); rc_dn.a11 = sm.ld_from(xb + 11, dn);
+    const Blk alpha = blk_mul_neg(ra, bi_up);     // -(ra * bi_up)
+    const Blk gamma = blk_mul_neg(rc, bi_dn);
+    rb = blk_fma(gamma, ra_dn, blk_fma(alpha, rc_up, rb));
     ra = blk_mul(alpha, ra_up);
     rc = blk_mul(gamma, rc_dn);
     pf.al[k] = alpha;
@@ -176,7 +197,7 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
 
 // Solve W x = r in place.  r[j] / x[j] are this lane's NPL block rows.
 template <int NPL>
-TRPL_FN void bt_solve(V2 (&r)[NPL], const LaneMem& sm, int base, const PcrFac& pf) {
+TRPL_FN void bt_solve(V2 (&r)[NPL], LaneMem& sm, int base, int xch, const PcrFac& pf) {
   typedef FacSlots<NPL> S;
   constexpr int NI = NPL - 1;
   V2 g[NI > 0 ? NI : 1];
@@ -198,10 +219,14 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const LaneMem& sm, int base, const PcrFac& p
   }
   TRPL_UNROLL for (int k = 0; k < 5; ++k) {
     const int s = 1 << k;
+    const int xb = xch + 2 * (k & 1);
+    sm.st(xb, rr.x); sm.st(xb + 1, rr.y);
+    warp_sync();
+    const ivec lu = lane_minus(s), ld = lane_plus(s);
     V2 up, dn;
-    up.x = shfl_up(rr.x, s); up.y = shfl_up(rr.y, s);
-    dn.x = shfl_down(rr.x, s); dn.y = shfl_down(rr.y, s);
-    rr = add_mv(add_mv(rr, pf.al[k], up), pf.ga[k], dn);  // multipliers are zero where no neighbour
+    up.x = sm.ld_from(xb, lu); up.y = sm.ld_from(xb + 1, lu);
+    dn.x = sm.ld_from(xb, ld); dn.y = sm.ld_from(xb + 1, ld);
+    rr = add_mv(add_mv(rr, pf.al[k], up), pf.ga[k], dn);  // multipliers are exact zeros where no neighbour
   }
   const V2 z = blk_mv(pf.binv, rr);
   r[NPL - 1] = z;

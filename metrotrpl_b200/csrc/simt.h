@@ -87,12 +87,16 @@ TRPL_FN ivec iadd(ivec a, int b) { return a + b; }
 TRPL_FN ivec imul(ivec a, int b) { return a * b; }
 TRPL_FN ivec irsub(int a, ivec b) { return a - b; }
 TRPL_FN real to_real(ivec a) { return (double)a; }
+TRPL_FN ivec lane_minus(int d) { const int l = (int)(threadIdx.x & 31u); return l >= d ? l - d : l; }   // own lane if out of range
+TRPL_FN ivec lane_plus(int d) { const int l = (int)(threadIdx.x & 31u); return l + d < 32 ? l + d : l; }
 
 // per-warp scratch in shared memory, slot-major: slot s of lane l lives at base[s*32 + l]
 struct LaneMem {
   double* base;
   TRPL_FN real ld(int slot) const { return base[slot * 32 + (threadIdx.x & 31u)]; }
   TRPL_FN void st(int slot, real v) const { base[slot * 32 + (threadIdx.x & 31u)] = v; }
+  // read another lane's slot (lane exchange through shared memory; caller orders with warp_sync)
+  TRPL_FN real ld_from(int slot, ivec src) const { return base[slot * 32 + src]; }
 };
 TRPL_FN void warp_sync() { __syncwarp(); }
 }  // namespace simt
@@ -185,6 +189,8 @@ inline void scatter(double* p, const ivec& idx, const mask& m, const real& v) {
 inline ivec iadd(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] + b; return r; }
 inline ivec imul(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] * b; return r; }
 inline ivec irsub(int a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a - b.v[i]; return r; }
+inline ivec lane_minus(int d) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i >= d ? i - d : i; return r; }
+inline ivec lane_plus(int d) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i + d < 32 ? i + d : i; return r; }
 inline real to_real(const ivec& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (double)a.v[i]; return r; }
 
 struct LaneMem {
@@ -192,6 +198,7 @@ struct LaneMem {
   explicit LaneMem(int n) : slots(n) {}
   real ld(int slot) const { return slots[slot]; }
   void st(int slot, const real& v) { slots[slot] = v; }
+  real ld_from(int slot, const ivec& src) const { real r; for (int i = 0; i < 32; ++i) r.v[i] = slots[slot].v[src.v[i]]; return r; }
 };
 inline void warp_sync() {}
 }  // namespace simt

@@ -105,7 +105,11 @@ struct Slots {
   static constexpr int F0 = KBASE + NKS * KSTRIDE;             // f(u) of the current step (for retries)
   static constexpr int FAC = F0 + KSTRIDE;
   static constexpr int TRAP = FAC + FacSlots<NPL>::COUNT;      // traps: 5 condensation coefficients per node
-  static constexpr int COUNT = TRAP + ((MODEL == MODEL_TRAPS) ? 5 * NPL : 0);
+  // lane-exchange scratch: 4 slots for the solve; the factorisation needs 24 and borrows the K
+  // region (dead at that point) when that is large enough, else it gets its own
+  static constexpr int XCH = TRAP + ((MODEL == MODEL_TRAPS) ? 5 * NPL : 0);
+  static constexpr int XCH_FACTOR = (NKS * KSTRIDE >= 24) ? KBASE : XCH;
+  static constexpr int COUNT = XCH + ((NKS * KSTRIDE >= 24) ? 4 : 24);
   static constexpr int BYTES = COUNT * 32 * 8;
 };
 
@@ -274,7 +278,8 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   };
 
   double h = 0.0, h_new = 0.0, gi = 0.0, ih = 0.0;
-  double err_old = 1e-4, h_acc = 0.0;
+  float err_old = 1e-4f;
+  double h_acc = 0.0;
   bool first = true, last_rejected = false, final_step = false;
   const double inv_n = 1.0 / (2.0 * L + ((MODEL == MODEL_TRAPS) ? L : 0));
   const double h_min = 1e-14 * fmax(tend, 1e-300);
@@ -404,7 +409,7 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
             C[j].a10 = C[j].a10 - jt.fq_tn[j] * gnn;
           }
         }
-        bt_factor<NPL>(A, B, C, sm, SL::FAC, pf);
+        bt_factor<NPL>(A, B, C, sm, SL::FAC, SL::XCH_FACTOR, pf);
       }
       s = 0;
     } else {
@@ -428,11 +433,11 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
           b[j].x = fmadd(sm.ld(SL::TRAP + 5 * j + 2), w[j], r.n[j]);
           b[j].y = fmadd(sm.ld(SL::TRAP + 5 * j + 3), w[j], fmadd(sm.ld(SL::TRAP + 5 * j + 4), wn, r.q[j]));
         }
-        bt_solve<NPL>(b, sm, SL::FAC, pf);
+        bt_solve<NPL>(b, sm, SL::FAC, SL::XCH, pf);
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) kk.t[j] = fmadd(sm.ld(SL::TRAP + 5 * j + 1), b[j].x, w[j]);
       } else {
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) { b[j].x = r.n[j]; b[j].y = r.q[j]; }
-        bt_solve<NPL>(b, sm, SL::FAC, pf);
+        bt_solve<NPL>(b, sm, SL::FAC, SL::XCH, pf);
       }
       TRPL_UNROLL for (int j = 0; j < NPL; ++j) { kk.n[j] = b[j].x; kk.q[j] = b[j].y; }
     }
@@ -496,18 +501,19 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
     const double err = nonfinite ? 1e10 : sqrt(err2);
 
     // ---- controller (Hairer's RODAS: standard + Gustafsson predictive) ----
-    const double root4 = sqrt(sqrt(err));
-    double fac = fmax(0.2, fmin(6.0, root4 / 0.9));
-    h_new = h / fac;
+    // step-size factor in single precision (it only steers h)
+    const float errf = (float)fmin(err, 1e30);
+    float fac = fmaxf(0.2f, fminf(6.0f, sqrtf(sqrtf(errf)) * (1.0f / 0.9f)));
+    h_new = h / (double)fac;
     if (err <= 1.0) {
       ++n_acc;
       if (!first) {
-        double fg = (h_acc / h) * sqrt(sqrt(err * err / err_old)) / 0.9;
-        fg = fmax(0.2, fmin(6.0, fg));
-        fac = fmax(fac, fg);
-        h_new = h / fac;
+        float fg = (float)(h_acc / h) * sqrtf(sqrtf(errf * errf / err_old)) * (1.0f / 0.9f);
+        fg = fmaxf(0.2f, fminf(6.0f, fg));
+        fac = fmaxf(fac, fg);
+        h_new = h / (double)fac;
       }
-      first = false; h_acc = h; err_old = fmax(1e-2, err);
+      first = false; h_acc = h; err_old = fmaxf(1e-2f, errf);
       if (last_rejected) h_new = fmin(h_new, h);
       last_rejected = false;
       t = final_step ? tend : t + h;
