@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TRPL_ABI_VERSION 1
+#define TRPL_ABI_VERSION 2
 #define TRPL_NPARAM 16  /* doubles per parameter set, model units (nm, ns, V) */
 #define TRPL_NAUX 6     /* doubles per trajectory, see below */
 #define TRPL_NTEMP 3    /* likelihoods are returned for three temperatures per trajectory */
@@ -48,7 +48,7 @@ enum trpl_ini_mode { TRPL_INI_DENSITY = 0, TRPL_INI_FLUENCE = 1 };   /* forward_
 /* status bits per trajectory */
 enum trpl_status {
   TRPL_ST_OK = 0, TRPL_ST_MAX_STEPS = 1, TRPL_ST_H_UNDERFLOW = 2, TRPL_ST_NONFINITE = 4,
-  TRPL_ST_FLOORED = 8, TRPL_ST_NEG_FRAC = 16, TRPL_ST_NAN_LL = 32
+  TRPL_ST_FLOORED = 8, TRPL_ST_NEG_FRAC = 16, TRPL_ST_NAN_LL = 32, TRPL_ST_CONV_FAIL = 64
 };
 enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2 };
 
@@ -64,6 +64,9 @@ typedef struct trpl_meas_desc {
   int32_t n_t;        /* measurement times of this curve; times[t_off] must be 0 */
   int32_t t_off;      /* offset into times / vals / uncs / per-set curves */
   int32_t prof_off;   /* density mode: offset into profiles (cm^-3, nx values) */
+  int32_t irf_nk;     /* rows of this curve's IRF moment table (laplace.py:13-41); 0 = no convolution */
+  double irf_dt;      /* mean IRF time step [ns] (laplace.py:66) */
+  int32_t irf_off;    /* first row of the table in the array given to trpl_set_irf */
   int32_t pad_;
 } trpl_meas_desc;
 
@@ -91,6 +94,11 @@ int trpl_device_info(trpl_handle* h, int32_t* sm_count, int32_t* sm_clock_khz, c
 int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_meas_desc* meas,
                      int32_t n_times_total, const double* times, const double* vals,
                      const double* uncs, int32_t n_profile_total, const double* profiles);
+
+/* IRF moment tables of every wavelength in use, rows of {I^0, I^1, I^2} concatenated
+ * (shared_fields["_IRF_tables"], laplace.py:13-41).  Call after trpl_set_problem when any
+ * measurement has irf_nk > 0; the in-kernel convolution replaces laplace.py:44-129. */
+int trpl_set_irf(trpl_handle* h, int32_t n_rows_total, const double* moments);
 
 /* Whole-batch likelihood: n_sets parameter sets x n_meas measurements.
  *   params  [n_sets][TRPL_NPARAM]

@@ -26,7 +26,7 @@ MODEL_IDS = {"std": 0, "traps": 1}
 MEAS_IDS = {"TRPL": 0, "TRTS": 1}
 INI_IDS = {"density": 0, "fluence": 1}
 
-ST_MAX_STEPS, ST_H_UNDERFLOW, ST_NONFINITE, ST_FLOORED, ST_NEG_FRAC, ST_NAN_LL = 1, 2, 4, 8, 16, 32
+ST_MAX_STEPS, ST_H_UNDERFLOW, ST_NONFINITE, ST_FLOORED, ST_NEG_FRAC, ST_NAN_LL, ST_CONV_FAIL = 1, 2, 4, 8, 16, 32, 64
 OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD = 1, 2
 
 # Defaults of the integrator.  RTOL keeps the reference's default value and meaning
@@ -43,7 +43,8 @@ class MeasDesc(C.Structure):
     _fields_ = [("thickness", C.c_double), ("ini_a", C.c_double), ("ini_b", C.c_double),
                 ("nx", C.c_int32), ("meas_type", C.c_int32), ("ini_mode", C.c_int32),
                 ("ini_dir", C.c_int32), ("n_t", C.c_int32), ("t_off", C.c_int32),
-                ("prof_off", C.c_int32), ("pad_", C.c_int32)]
+                ("prof_off", C.c_int32), ("irf_nk", C.c_int32), ("irf_dt", C.c_double),
+                ("irf_off", C.c_int32), ("pad_", C.c_int32)]
 
 
 class SolverOpts(C.Structure):
@@ -79,6 +80,7 @@ class PackedProblem:
     t_off: np.ndarray
     n_t: np.ndarray
     meas_types: list = field(default_factory=list)
+    irf_moments: Optional[np.ndarray] = None     # [rows, 3] concatenated moment tables
 
     @property
     def n_times_total(self) -> int:
@@ -86,8 +88,12 @@ class PackedProblem:
 
 
 def pack_problem(sim_info, init_params, times, vals=None, uncs=None, model="std",
-                 ini_mode="density") -> PackedProblem:
-    """Flatten sim_info / _init_params / _times / _vals / _uncs (metropolis.py:317-326)."""
+                 ini_mode="density", irf_convolution=None, irf_tables=None) -> PackedProblem:
+    """Flatten sim_info / _init_params / _times / _vals / _uncs (metropolis.py:317-326).
+
+    irf_convolution : per-measurement wavelength (0 = none), shared_fields["irf_convolution"]
+    irf_tables      : {wavelength: (moments[nk,3], t_irf)}, shared_fields["_IRF_tables"]
+    """
     if model not in MODEL_IDS:
         raise ValueError(f"Invalid model {model}")
     if ini_mode not in INI_IDS:
@@ -97,6 +103,9 @@ def pack_problem(sim_info, init_params, times, vals=None, uncs=None, model="std"
     t_all, v_all, u_all, prof_all = [], [], [], []
     t_off = 0
     p_off = 0
+    irf_rows = {}
+    irf_blocks = []
+    n_irf_rows = 0
     for i in range(n_meas):
         t = np.ascontiguousarray(times[i], dtype=np.float64)
         if t.ndim != 1 or t.size < 1:
@@ -133,6 +142,16 @@ def pack_problem(sim_info, init_params, times, vals=None, uncs=None, model="std"
                 d.ini_dir = int(np.sign(int(ini[2]))) or 1                # sign 0 -> slice error -> unchanged
             except (IndexError, ValueError):
                 d.ini_dir = 1
+        if irf_convolution is not None and irf_convolution[i] != 0:
+            wave = int(irf_convolution[i])
+            mom, t_irf = irf_tables[wave]
+            if wave not in irf_rows:
+                irf_rows[wave] = n_irf_rows
+                irf_blocks.append(np.ascontiguousarray(mom, dtype=np.float64))
+                n_irf_rows += len(mom)
+            d.irf_off = irf_rows[wave]
+            d.irf_nk = len(mom)
+            d.irf_dt = float(np.mean(np.diff(t_irf)))                   # laplace.py:66
         t_all.append(t)
         if vals is not None:
             v = np.ascontiguousarray(vals[i], dtype=np.float64)
@@ -150,7 +169,8 @@ def pack_problem(sim_info, init_params, times, vals=None, uncs=None, model="std"
         profiles=np.concatenate(prof_all) if prof_all else None,
         t_off=np.array([d.t_off for d in descs], dtype=np.int64),
         n_t=np.array([d.n_t for d in descs], dtype=np.int64),
-        meas_types=list(sim_info["meas_types"]))
+        meas_types=list(sim_info["meas_types"]),
+        irf_moments=np.concatenate(irf_blocks) if irf_blocks else None)
 
 
 def pack_params(states, indexes, units=None, model="std") -> np.ndarray:
@@ -203,6 +223,7 @@ def load_library() -> C.CDLL:
     lib.trpl_device_info.argtypes = [H, ip, ip, C.c_char_p, C.c_int32]
     lib.trpl_set_problem.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(MeasDesc), C.c_int32, dp, dp,
                                      dp, C.c_int32, dp]
+    lib.trpl_set_irf.argtypes = [H, C.c_int32, dp]
     lib.trpl_loglik_batch.argtypes = [H, C.c_int32, dp, dp, C.POINTER(SolverOpts), dp, ip, ip, dp]
     lib.trpl_solve_batch.argtypes = [H, C.c_int32, dp, dp, C.POINTER(SolverOpts), dp, ip, ip]
     lib.trpl_upload_batch.argtypes = [H, C.c_int32, dp, dp]
@@ -228,7 +249,7 @@ class Context:
 
     def __init__(self, device: int = 0):
         self.lib = load_library()
-        if self.lib.trpl_abi_version() != 1:
+        if self.lib.trpl_abi_version() != 2:
             raise TrplError("ABI version mismatch")
         self.h = C.c_void_p()
         self._check(self.lib.trpl_create(int(device), C.byref(self.h)))
@@ -262,6 +283,9 @@ class Context:
             self.h, prob.model, prob.n_meas, prob.meas, prob.n_times_total,
             _ptr(prob.times, C.c_double), _ptr(prob.vals, C.c_double), _ptr(prob.uncs, C.c_double),
             nprof, _ptr(prob.profiles, C.c_double)))
+        if prob.irf_moments is not None:
+            self._check(self.lib.trpl_set_irf(self.h, int(prob.irf_moments.shape[0]),
+                                              _ptr(prob.irf_moments, C.c_double)))
         self.problem = prob
 
     # -- whole-batch calls (host buffers in, host buffers out) --

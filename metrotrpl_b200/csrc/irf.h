@@ -1,0 +1,202 @@
+// irf.h - instrument-response convolution and the final likelihood pass over a stored curve.
+//
+// Replaces, per trajectory and inside the kernel,
+//   laplace.py:44-86    do_irf_convolution (resample to dt_irf/2, moment convolution, max-shift)
+//   laplace.py:178-222  convolve
+//   laplace.py:89-129   post_conv_trim (cut to the convolved span, interpolate back)
+//   utils.py:16-32      set_min_y
+//   trial_move_evaluation.py:117-166  negative test, log10 residuals, weighted sum
+// The moment tables (laplace.py:13-41, make_I_tables) are a one-off host precompute
+// (metrotrpl_b200/laplace.py) uploaded with the problem.
+//
+// Work is spread over the lanes (resampled points, convolution outputs and measurement times are
+// independent); the three scratch arrays live in a per-warp slice of global memory that stays in L2.
+#pragma once
+#include <float.h>
+#include "simt.h"
+
+namespace trpl {
+using namespace simt;
+
+struct IrfDesc {
+  const double* mom;   // [nk][3] moment integrals I_m^n
+  int nk;              // rows of the table (= IRF samples); 0 = no convolution for this measurement
+  double dt;           // mean IRF time step
+  double* ry;          // scratch: resampled curve           [n_rs]
+  double* hk;          // scratch: convolved curve           [nk_conv + 1]
+  double* trim;        // scratch: convolved curve on the measurement times [n_t]
+};
+
+// np.interp(x, xp, fp) for one x per lane, xp ascending, xp[0] <= x <= xp[n-1]
+TRPL_FN real interp_lanes(const double* xp, const double* fp, int n, const real& x, const mask& take) {
+  ivec lo = isplat(0), hi = isplat(n - 1);
+  // invariant xp[lo] <= x; find the largest such lo (uniform trip count)
+  for (int span = n; span > 1; span = (span + 1) >> 1) {
+    const ivec mid = ishr1(iaddv(iaddv(lo, hi), isplat(1)));
+    const real xm = gather(xp, mid, take, 0.0);
+    const mask le = xm <= x;
+    lo = seli(le, mid, lo);
+    hi = seli(le, hi, iadd(mid, -1));
+  }
+  lo = iclamp(lo, 0, n - 2 > 0 ? n - 2 : 0);
+  const ivec lo1 = iadd(lo, n > 1 ? 1 : 0);
+  const real x0 = gather(xp, lo, take, 0.0), x1 = gather(xp, lo1, take, 1.0);
+  const real y0 = gather(fp, lo, take, 0.0), y1 = gather(fp, lo1, take, 0.0);
+  const real slope = (y1 - y0) / (x1 - x0);
+  real y = slope * (x - x0) + y0;
+  y = sel(x >= x1, y1, y);            // exact at the right end, as np.interp
+  return y;
+}
+
+// Returns false when the reference would have failed the convolution (-> likelihood -inf).
+// On success trim[0..n_c) holds the convolved, max-shifted signal on times[0..n_c).
+TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t, const IrfDesc& f,
+                               int& n_c) {
+  const ivec lane = lane_id();
+  const double tend = times[n_t - 1];
+  const double half = f.dt / 2;
+  const int n_rs = (int)ceil((tend + f.dt / 4) / half);      // len(np.arange(0, tend + dt/4, dt/2))
+  if (n_rs < 3) return false;
+  const int nk = (n_rs - 1) / 2;
+  const int last_rs = n_rs - 1;
+  // resampled abscissa j*half, the last one clamped to tend (laplace.py:68-72)
+  const double x_last = fmin((double)last_rs * half, tend);
+
+  // ---- 1. resample (laplace.py:68-74) ----
+  mask any_nan = mconst(false);
+  for (int j0 = 0; j0 < n_rs; j0 += 32) {
+    const ivec j = iadd(lane, j0);
+    const mask take = j < n_rs;
+    real x = to_real(j) * half;
+    x = sel(j == last_rs, x_last, x);
+    const real y = interp_lanes(times, curve, n_t, x, take);
+    any_nan = mor(any_nan, mand(take, is_nan(y)));
+    scatter(f.ry, j, take, y);
+  }
+  warp_sync();
+  if (warp_any(any_nan)) return false;
+
+  // ---- 2. moment convolution (laplace.py:178-222) ----
+  real best = splat(-DBL_MAX);
+  ivec best_k = isplat(0x7fffffff);
+  for (int k0 = 0; k0 <= nk; k0 += 32) {
+    const ivec k = iadd(lane, k0);
+    const mask take = k <= nk;
+    real acc = splat(0.0);
+    const int m_hi = (k0 + 31 < f.nk) ? k0 + 31 : f.nk;      // lags needed by the largest k of this batch
+    // c carries ry[2kp+2] of the previous lag (= ry[2kp] of this one shifted): two new loads per lag
+    real c = gather(f.ry, imul(k, 2), mand(take, k >= 1), 0.0);
+    for (int m = 0; m < m_hi; ++m) {
+      const mask on = mand(take, k > m);                      // kp = k-1-m >= 0
+      const ivec kp2 = imul(iadd(k, -1 - m), 2);
+      const real a = gather(f.ry, kp2, on, 0.0);
+      const real b = gather(f.ry, iadd(kp2, 1), on, 0.0);
+      const double m0 = f.mom[3 * m], m1 = f.mom[3 * m + 1], m2 = f.mom[3 * m + 2];
+      const real i1 = c - a;
+      const real i2 = 2.0 * ((c - 2.0 * b) + a);
+      const real term = fmadd(i2, m2, fmadd(i1, m1, b * m0));
+      acc = acc + sel(on, term, 0.0);
+      c = a;
+    }
+    scatter(f.hk, k, take, acc);
+    // running argmax, first occurrence
+    const mask better = mand(take, acc > best);
+    best = sel(better, acc, best);
+    best_k = seli(better, k, best_k);
+    any_nan = mor(any_nan, mand(take, is_nan(acc)));
+  }
+  warp_sync();
+  if (warp_any(any_nan)) return false;
+  // ---- 3. max-shift (laplace.py:80-84) ----
+  const double vmax_all = uni(warp_max(best));
+  const real cand = sel(best == vmax_all, to_real(best_k), 4e9);
+  const int kmax = (int)uni(warp_min(cand));
+  const double t_shift = (2 * kmax == last_rs) ? x_last : (double)(2 * kmax) * half;
+  const double x_end = (2 * nk == last_rs) ? x_last : (double)(2 * nk) * half;
+  const double max_ct = x_end - t_shift;                      // conv_t[-1]
+  if (max_ct == 0.0) return false;
+
+  // ---- 4. trim to the convolved span and interpolate back (laplace.py:119-127) ----
+  real cnt = splat(0.0);
+  for (int i0 = 0; i0 < n_t; i0 += 32) {
+    const ivec i = iadd(lane, i0);
+    const mask take = i < n_t;
+    const real te = gather(times, i, take, DBL_MAX);
+    cnt = cnt + sel(mand(take, te < max_ct), 1.0, 0.0);
+  }
+  n_c = (int)uni(warp_sum(cnt));                              // times ascend: a prefix
+  if (n_c < 1) return false;
+  for (int i0 = 0; i0 < n_c; i0 += 32) {
+    const ivec i = iadd(lane, i0);
+    const mask take = i < n_c;
+    const real x = gather(times, i, take, 0.0);
+    // conv_t[j] = fl(rt[2j] - t_shift); start from the arithmetic guess and fix the rounding
+    ivec j = to_int_floor((x + t_shift) / f.dt);
+    j = iclamp(j, 0, nk - 1);
+    TRPL_UNROLL for (int fix = 0; fix < 2; ++fix) {
+      const real tj = sel(imul(j, 2) == last_rs, x_last, to_real(imul(j, 2)) * half) - t_shift;
+      j = seli(mand(tj > x, j > 0), iadd(j, -1), j);
+    }
+    TRPL_UNROLL for (int fix = 0; fix < 2; ++fix) {
+      const ivec jn = iadd(j, 1);
+      const real tn = sel(imul(jn, 2) == last_rs, x_last, to_real(imul(jn, 2)) * half) - t_shift;
+      j = seli(mand(tn <= x, jn < nk), jn, j);
+    }
+    const ivec j1 = iadd(j, 1);
+    const real x0 = sel(imul(j, 2) == last_rs, x_last, to_real(imul(j, 2)) * half) - t_shift;
+    const real x1 = sel(imul(j1, 2) == last_rs, x_last, to_real(imul(j1, 2)) * half) - t_shift;
+    const real y0 = gather(f.hk, j, take, 0.0), y1 = gather(f.hk, j1, take, 0.0);
+    const real slope = (y1 - y0) / (x1 - x0);
+    real y = slope * (x - x0) + y0;
+    y = sel(x >= x1, y1, y);
+    scatter(f.trim, i, take, y);
+  }
+  warp_sync();
+  return true;
+}
+
+// Likelihood of a stored signal sol[0..n_c) against vals/uncs[0..n_c): abs/negative count,
+// optional set_min_y floor, log10 residuals, three temperatures (trial_move_evaluation.py:117-166).
+TRPL_FN void array_loglik(const double* sol, int n_c, const double* vals, const double* uncs,
+                          double shift, const double* s2T, bool force_min_y, double* ll, double& n_neg) {
+  const ivec lane = lane_id();
+  int first_floor = n_c;
+  double floor_y = 0.0;
+  if (force_min_y) {
+    // utils.py:16-32: raise |sol| to 10**min(vals - shift) from the index np.searchsorted finds on
+    // -|sol| (a plain bisection, reproduced step for step)
+    real mn = splat(DBL_MAX);
+    for (int k0 = 0; k0 < n_c; k0 += 32) {
+      const ivec k = iadd(lane, k0);
+      mn = vmin(mn, gather(vals, k, k < n_c, DBL_MAX) - shift);
+    }
+    floor_y = pow(10.0, uni(warp_min(mn)));
+    int lo = 0, hi = n_c;
+    while (lo < hi) {
+      const int mid = lo + ((hi - lo) >> 1);
+      if (-fabs(sol[mid]) < -floor_y) lo = mid + 1; else hi = mid;
+    }
+    first_floor = lo;
+  }
+  real l0 = splat(0.0), l1 = splat(0.0), l2 = splat(0.0), neg = splat(0.0);
+  for (int k0 = 0; k0 < n_c; k0 += 32) {
+    const ivec k = iadd(lane, k0);
+    const mask take = k < n_c;
+    const real y = gather(sol, k, take, 1.0);
+    neg = neg + sel(mand(take, y < 0.0), 1.0, 0.0);
+    real ya = vabs(y);
+    ya = sel(k >= first_floor, floor_y, ya);
+    const real vk = gather(vals, k, take, 0.0);
+    const real uk = gather(uncs, k, take, 1.0);
+    const real r = (vlog10(ya) + shift) - vk;
+    const real r2 = r * r;
+    const real u2 = 2.0 * (uk * uk);
+    l0 = l0 + sel(take, r2 * rcp(s2T[0] + u2), 0.0);
+    l1 = l1 + sel(take, r2 * rcp(s2T[1] + u2), 0.0);
+    l2 = l2 + sel(take, r2 * rcp(s2T[2] + u2), 0.0);
+  }
+  ll[0] = -uni(warp_sum(l0)); ll[1] = -uni(warp_sum(l1)); ll[2] = -uni(warp_sum(l2));
+  n_neg = uni(warp_sum(neg));
+}
+
+}  // namespace trpl

@@ -86,6 +86,13 @@ TRPL_FN void scatter(double* p, ivec idx, mask m, real v) { if (m) p[idx] = v; }
 TRPL_FN ivec iadd(ivec a, int b) { return a + b; }
 TRPL_FN ivec imul(ivec a, int b) { return a * b; }
 TRPL_FN ivec irsub(int a, ivec b) { return a - b; }
+TRPL_FN ivec iaddv(ivec a, ivec b) { return a + b; }
+TRPL_FN ivec isubv(ivec a, ivec b) { return a - b; }
+TRPL_FN ivec ishr1(ivec a) { return a >> 1; }
+TRPL_FN ivec iclamp(ivec a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
+TRPL_FN ivec isplat(int a) { return a; }
+TRPL_FN ivec to_int_floor(real x) { return (int)floor(x); }
+TRPL_FN real warp_min(real x) { return -warp_max(-x); }
 TRPL_FN real to_real(ivec a) { return (double)a; }
 TRPL_FN ivec lane_minus(int d) { const int l = (int)(threadIdx.x & 31u); return l >= d ? l - d : l; }   // own lane if out of range
 TRPL_FN ivec lane_plus(int d) { const int l = (int)(threadIdx.x & 31u); return l + d < 32 ? l + d : l; }
@@ -176,6 +183,7 @@ inline real warp_max(real x) {
   for (int o = 16; o > 0; o >>= 1) { real y; for (int i = 0; i < 32; ++i) y.v[i] = fmax(x.v[i], x.v[i ^ o]); x = y; }
   return x;
 }
+inline real warp_min(const real& x) { return -warp_max(-x); }
 inline real warp_scan_incl(real x) {
   for (int o = 1; o < 32; o <<= 1) { real y = x; for (int i = o; i < 32; ++i) y.v[i] = x.v[i] + x.v[i - o]; x = y; }
   return x;
@@ -188,9 +196,15 @@ inline void scatter(double* p, const ivec& idx, const mask& m, const real& v) {
 }
 inline ivec iadd(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] + b; return r; }
 inline ivec imul(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] * b; return r; }
+inline ivec iaddv(const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline ivec isubv(const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] - b.v[i]; return r; }
+inline ivec ishr1(const ivec& a) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] >> 1; return r; }
+inline ivec iclamp(const ivec& a, int lo, int hi) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] < lo ? lo : (a.v[i] > hi ? hi : a.v[i]); return r; }
+inline ivec isplat(int a) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a; return r; }
 inline ivec irsub(int a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a - b.v[i]; return r; }
 inline ivec lane_minus(int d) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i >= d ? i - d : i; return r; }
 inline ivec lane_plus(int d) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i + d < 32 ? i + d : i; return r; }
+inline ivec to_int_floor(const real& x) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = (int)floor(x.v[i]); return r; }
 inline real to_real(const ivec& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (double)a.v[i]; return r; }
 
 struct LaneMem {

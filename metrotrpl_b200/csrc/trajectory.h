@@ -15,6 +15,7 @@
 #include "simt.h"
 #include "model.h"
 #include "blocktri.h"
+#include "irf.h"
 
 namespace trpl {
 using namespace simt;
@@ -51,7 +52,8 @@ enum StatusBits {
   ST_NONFINITE = 4,     // NaN/Inf state
   ST_FLOORED = 8,       // signal fell below DBL_MIN and was floored (forward_solver.py:190-192)
   ST_NEG_FRAC = 16,     // too many negative values (trial_move_evaluation.py:117-123) -> -inf
-  ST_NAN_LL = 32        // likelihood was NaN -> -inf (trial_move_evaluation.py:159-165)
+  ST_NAN_LL = 32,       // likelihood was NaN -> -inf (trial_move_evaluation.py:159-165)
+  ST_CONV_FAIL = 64     // IRF convolution failed -> -inf (trial_move_evaluation.py:83-87, :103-106)
 };
 
 enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2 };
@@ -74,6 +76,9 @@ struct MeasDesc {
   int n_t;               // number of measurement times (times[0] == 0)
   int t_off;             // offset of this measurement in times/vals/uncs
   int prof_off;          // offset of this measurement's profile (density mode)
+  int irf_nk;            // rows of this measurement's IRF moment table, 0 = no convolution
+  double irf_dt;         // mean IRF time step [ns]
+  int irf_off;           // first row of the table in the moments array
   int pad_;
 };
 
@@ -88,6 +93,7 @@ struct TrajIn {
   double s2T[3];         // model_uncertainty^2 * T for up to three temperatures
   double fl_mult, al_mult;
   double* curve;         // optional [n_t] simulated signal in measurement units
+  IrfDesc irf;           // irf.nk == 0: no convolution
 };
 
 struct TrajOut {
@@ -216,6 +222,8 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   const ivec node0 = imul(lane, NPL);
   const int n_t = md.n_t;
   const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
+  // min_y floor and IRF convolution need the whole curve: likelihood in a final pass over it
+  const bool post = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || in.irf.nk > 0);
 
   // ---- initial condition (forward_solver.py:100-122) ----
   V u;
@@ -264,7 +272,7 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   // likelihood contribution of a batch of emitted values (trial_move_evaluation.py:117-130, :147-156)
   auto accumulate = [&](const ivec& k, const mask& take, const real& y) {
     if (in.curve) scatter(in.curve, k, take, y);
-    if (want_ll) {
+    if (want_ll && !post) {
       nneg = nneg + sel(mand(take, y < 0.0), 1.0, 0.0);
       const real vk = gather(in.vals, k, take, 0.0);
       const real uk = gather(in.uncs, k, take, 1.0);
@@ -539,46 +547,35 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
 
   // ---- likelihood (trial_move_evaluation.py:117-166) ----
   out.status = status; out.n_acc = n_acc; out.n_rej = n_rej;
-  if (want_ll && (opt.flags & OPT_FORCE_MIN_Y) && in.curve) {
-    // utils.py:16-32 set_min_y: raise |sol| to 10**min(vals - shift) from the index np.searchsorted
-    // finds on -|sol| (a plain bisection, reproduced step for step), then redo the sum.
-    warp_sync();
-    real mn = splat(DBL_MAX);
-    for (int k0 = 0; k0 < n_t; k0 += 32) {
-      const ivec k = iadd(lane, k0);
-      mn = vmin(mn, gather(in.vals, k, k < n_t, DBL_MAX) - in.scale_shift);
-    }
-    const double floor_y = pow(10.0, -uni(warp_max(-mn)));
-    int lo = 0, hi = n_t;
-    while (lo < hi) {
-      const int mid = lo + ((hi - lo) >> 1);
-      if (-fabs(in.curve[mid]) < -floor_y) lo = mid + 1; else hi = mid;
-    }
-    ll0 = splat(0.0); ll1 = splat(0.0); ll2 = splat(0.0);
-    for (int k0 = 0; k0 < n_t; k0 += 32) {
-      const ivec k = iadd(lane, k0);
-      const mask take = k < n_t;
-      real ya = vabs(gather(in.curve, k, take, 1.0));
-      ya = sel(k >= lo, floor_y, ya);
-      const real vk = gather(in.vals, k, take, 0.0);
-      const real uk = gather(in.uncs, k, take, 1.0);
-      const real r = (vlog10(ya) + in.scale_shift) - vk;
-      const real r2 = r * r;
-      const real u2 = 2.0 * (uk * uk);
-      ll0 = ll0 + sel(take, r2 / (in.s2T[0] + u2), 0.0);
-      ll1 = ll1 + sel(take, r2 / (in.s2T[1] + u2), 0.0);
-      ll2 = ll2 + sel(take, r2 / (in.s2T[2] + u2), 0.0);
-    }
-  }
   if (want_ll) {
-    const double n_neg = uni(warp_sum(nneg));
-    double l0 = -uni(warp_sum(ll0)), l1 = -uni(warp_sum(ll1)), l2 = -uni(warp_sum(ll2));
+    double l[3];
+    double n_neg;
+    int n_c = n_t;
+    bool ok = true;
+    if (post) {
+      warp_sync();
+      const double* sol = in.curve;
+      if (in.irf.nk > 0) {
+        ok = irf_convolve_trim(in.times, in.curve, n_t, in.irf, n_c);
+        sol = in.irf.trim;
+        if (!ok) out.status |= ST_CONV_FAIL;
+      }
+      if (ok) array_loglik(sol, n_c, in.vals, in.uncs, in.scale_shift, in.s2T,
+                           (opt.flags & OPT_FORCE_MIN_Y) != 0, l, n_neg);
+    } else {
+      l[0] = -uni(warp_sum(ll0)); l[1] = -uni(warp_sum(ll1)); l[2] = -uni(warp_sum(ll2));
+      n_neg = uni(warp_sum(nneg));
+    }
     const double ninf = -HUGE_VAL;
-    if (!(n_neg < 0.2 * n_t)) { out.status |= ST_NEG_FRAC; l0 = l1 = l2 = ninf; }
-    if (l0 != l0) { out.status |= ST_NAN_LL; l0 = ninf; }
-    if (l1 != l1) l1 = ninf;
-    if (l2 != l2) l2 = ninf;
-    out.logll[0] = l0; out.logll[1] = l1; out.logll[2] = l2;
+    if (!ok) {
+      l[0] = l[1] = l[2] = ninf;
+    } else {
+      if (!(n_neg < 0.2 * n_c)) { out.status |= ST_NEG_FRAC; l[0] = l[1] = l[2] = ninf; }
+      if (l[0] != l[0]) { out.status |= ST_NAN_LL; l[0] = ninf; }
+      if (l[1] != l[1]) l[1] = ninf;
+      if (l[2] != l[2]) l[2] = ninf;
+    }
+    out.logll[0] = l[0]; out.logll[1] = l[1]; out.logll[2] = l[2];
   } else {
     out.logll[0] = out.logll[1] = out.logll[2] = 0.0;
   }

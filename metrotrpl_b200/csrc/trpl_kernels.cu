@@ -37,6 +37,9 @@ struct KernelArgs {
   int* status;               // [n_traj]
   int* nsteps;               // [n_traj][2]
   double* curves;            // [n_sets][n_times_total] or null
+  const double* irf_mom;     // [rows][3] or null
+  double* scratch;           // per-warp slices: resampled | convolved | trimmed
+  size_t scratch_stride, off_hk, off_trim;
   int* counter;              // work queue head
   int n_traj, n_meas, n_times_total;
   SolverOpts opt;
@@ -68,6 +71,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
     in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
     in.curve = a.curves ? a.curves + (size_t)set * a.n_times_total + md->t_off : nullptr;
+    in.irf.nk = (a.irf_mom && a.scratch) ? md->irf_nk : 0;
+    in.irf.dt = md->irf_dt;
+    in.irf.mom = a.irf_mom ? a.irf_mom + 3 * (size_t)md->irf_off : nullptr;
+    {
+      double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * a.scratch_stride : nullptr;
+      in.irf.ry = ws; in.irf.hk = ws ? ws + a.off_hk : nullptr; in.irf.trim = ws ? ws + a.off_trim : nullptr;
+    }
     TrajOut out;
     run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out);
     if (lane == 0) {
@@ -129,7 +139,10 @@ struct trpl_handle {
   int model = 0, n_meas = 0, n_times_total = 0, max_nx = 0;
   bool have_vals = false, have_profiles = false, all_full = false;
   DevBuf<MeasDesc> d_meas;
-  DevBuf<double> d_times, d_vals, d_uncs, d_profiles;
+  DevBuf<double> d_times, d_vals, d_uncs, d_profiles, d_irf, d_scratch;
+  bool any_irf = false, have_irf = false;
+  size_t max_nrs = 0, max_nt = 0;
+  int irf_rows_needed = 0;
   DevBuf<double> d_params, d_aux, d_logll, d_curves;
   DevBuf<int> d_status, d_nsteps, d_counter;
   int n_sets = 0;
@@ -251,6 +264,7 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
       return fail("Invalid ini_mode - must be 'density' or 'fluence'");
     }
     if (!(m.thickness > 0)) return fail("thickness must be positive");
+    if (m.irf_nk < 0 || (m.irf_nk > 0 && !(m.irf_dt > 0))) return fail("bad IRF descriptor");
     if (m.nx > max_nx) max_nx = m.nx;
   }
   // all measurements of one launch share the nodes-per-lane template: nx must fit 32*NPL and
@@ -276,9 +290,32 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
     CU(cudaMemcpyAsync(h->d_profiles.p, profiles, sizeof(double) * n_profile_total, cudaMemcpyHostToDevice, h->stream));
   }
   CU(cudaStreamSynchronize(h->stream));
+  h->any_irf = false; h->have_irf = false; h->max_nrs = 0; h->max_nt = 0; h->irf_rows_needed = 0;
+  for (int i = 0; i < n_meas; ++i) {
+    const trpl_meas_desc& m = meas[i];
+    if ((size_t)m.n_t > h->max_nt) h->max_nt = m.n_t;
+    if (m.irf_nk > 0) {
+      h->any_irf = true;
+      const double tend = times[m.t_off + m.n_t - 1];
+      const size_t n_rs = (size_t)ceil((tend + m.irf_dt / 4) / (m.irf_dt / 2));
+      if (n_rs > h->max_nrs) h->max_nrs = n_rs;
+      if (m.irf_off + m.irf_nk > h->irf_rows_needed) h->irf_rows_needed = m.irf_off + m.irf_nk;
+    }
+  }
   h->model = model; h->n_meas = n_meas; h->n_times_total = n_times_total; h->max_nx = max_nx;
   h->all_full = true;
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) h->all_full = false;
+  return 0;
+}
+
+int trpl_set_irf(trpl_handle* h, int32_t n_rows_total, const double* moments) {
+  if (!h || !moments || n_rows_total < 1) return fail("trpl_set_irf: bad arguments");
+  if (n_rows_total < h->irf_rows_needed) return fail("trpl_set_irf: table shorter than the measurement descriptors need");
+  CU(cudaSetDevice(h->device));
+  CU(h->d_irf.reserve((size_t)n_rows_total * 3));
+  CU(cudaMemcpyAsync(h->d_irf.p, moments, sizeof(double) * 3 * n_rows_total, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_irf = true;
   return 0;
 }
 
@@ -306,6 +343,9 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
   const bool want_ll = !(opts->flags & TRPL_OPT_NO_LIKELIHOOD);
   if (want_ll && !h->have_vals) return fail("likelihood requested but no measurement values uploaded");
   if (opts->flags & TRPL_OPT_FORCE_MIN_Y) want_curves = 1;   // the min_y pass re-reads the curve
+  const bool conv = want_ll && h->any_irf;
+  if (conv && !h->have_irf) return fail("measurements ask for IRF convolution but trpl_set_irf was not called");
+  if (conv) want_curves = 1;
   CU(cudaSetDevice(h->device));
   KernelArgs a;
   a.params = h->d_params.p; a.aux = h->d_aux.p; a.meas = h->d_meas.p; a.times = h->d_times.p;
@@ -318,6 +358,18 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
     a.curves = h->d_curves.p;
   }
   h->curves_valid = want_curves != 0;
+  a.irf_mom = nullptr; a.scratch = nullptr; a.scratch_stride = 0; a.off_hk = 0; a.off_trim = 0;
+  if (conv) {
+    // per-warp scratch: resampled curve | convolved curve | trimmed curve (all stay in L2)
+    const size_t n_hk = (h->max_nrs - 1) / 2 + 1;
+    a.off_hk = (h->max_nrs + 3) & ~(size_t)3;
+    a.off_trim = a.off_hk + ((n_hk + 3) & ~(size_t)3);
+    a.scratch_stride = a.off_trim + ((h->max_nt + 3) & ~(size_t)3);
+    const size_t warps = (size_t)h->prop.multiProcessorCount * 2 * WARPS_PER_CTA;
+    CU(h->d_scratch.reserve(warps * a.scratch_stride));
+    a.scratch = h->d_scratch.p;
+    a.irf_mom = h->d_irf.p;
+  }
   a.counter = h->d_counter.p;
   a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;
   memcpy(&a.opt, opts, sizeof(SolverOpts));

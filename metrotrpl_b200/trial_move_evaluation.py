@@ -39,14 +39,14 @@ class PathCache:
 
     def __init__(self, shared_fields, device=None):
         sf = shared_fields
-        if sf.get("irf_convolution", None) is not None and any(w != 0 for w in sf["irf_convolution"]):
-            raise NotImplementedError("IRF convolution is not in this build of the CUDA path")
         if any(m == "pa" for m in sf["_sim_info"]["meas_types"]):
             raise NotImplementedError("'pa' toy measurements are not simulations; not on the CUDA path")
         self.sf = sf
         self.prob = _capi.pack_problem(sf["_sim_info"], sf["_init_params"], sf["_times"], sf["_vals"],
                                        sf["_uncs"], model=sf.get("model", "std"),
-                                       ini_mode=sf.get("ini_mode", "density"))
+                                       ini_mode=sf.get("ini_mode", "density"),
+                                       irf_convolution=sf.get("irf_convolution", None),
+                                       irf_tables=sf.get("_IRF_tables", None))
         self.ctx = get_context(device)
         self.ctx.set_problem(self.prob)
         self.n_meas = self.prob.n_meas

@@ -33,7 +33,7 @@ def lib():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         _lib.trpl_emu_loglik_batch.argtypes = [C.c_int32, C.c_int32, C.POINTER(_capi.MeasDesc), C.c_int32,
                                                dp, dp, dp, dp, C.c_int32, dp, dp,
-                                               C.POINTER(_capi.SolverOpts), dp, ip, ip, dp]
+                                               C.POINTER(_capi.SolverOpts), dp, ip, ip, dp, dp]
     return _lib
 
 
@@ -51,7 +51,7 @@ def loglik_batch(prob, params, aux, opts, want_curves=True):
                                      p(prob.uncs, C.c_double), p(prob.profiles, C.c_double), n_sets,
                                      p(params, C.c_double), p(aux, C.c_double), C.byref(opts),
                                      p(logll, C.c_double), p(status, C.c_int32), p(nsteps, C.c_int32),
-                                     p(curves, C.c_double))
+                                     p(curves, C.c_double), p(prob.irf_moments, C.c_double))
     if rc:
         raise RuntimeError("emu failed")
     return logll, status, nsteps, curves

@@ -6,6 +6,7 @@
 #define TRPL_HOST_EMU 1
 #include <stdint.h>
 #include <string.h>
+#include <vector>
 #include "../../include/metrotrpl_b200.h"
 #include "../../metrotrpl_b200/csrc/trajectory.h"
 
@@ -15,7 +16,7 @@ template <int NPL, int MODEL, bool FULL>
 static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const double* times,
                     const double* vals, const double* uncs, const double* profiles, int n_sets,
                     const double* params, const double* aux, const SolverOpts& opt, double* logll,
-                    int32_t* status, int32_t* nsteps, double* curves) {
+                    int32_t* status, int32_t* nsteps, double* curves, const double* irf_mom) {
   const int n_traj = n_sets * n_meas;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int traj = 0; traj < n_traj; ++traj) {
@@ -34,6 +35,16 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
     in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
     in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
     in.curve = curves ? curves + (size_t)set * n_times_total + md->t_off : nullptr;
+    std::vector<double> ry, hk, trim;
+    in.irf.nk = irf_mom ? md->irf_nk : 0;
+    in.irf.dt = md->irf_dt;
+    in.irf.mom = irf_mom ? irf_mom + 3 * (size_t)md->irf_off : nullptr;
+    if (in.irf.nk > 0) {
+      const double tend = in.times[md->n_t - 1];
+      const size_t n_rs = (size_t)ceil((tend + md->irf_dt / 4) / (md->irf_dt / 2));
+      ry.resize(n_rs + 4); hk.resize(n_rs / 2 + 4); trim.resize(md->n_t + 4);
+    }
+    in.irf.ry = ry.data(); in.irf.hk = hk.data(); in.irf.trim = trim.data();
     TrajOut out;
     run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out);
     for (int k = 0; k < 3; ++k) logll[3 * (size_t)traj + k] = out.logll[k];
@@ -47,8 +58,8 @@ static int dispatch(int max_nx, int n_meas, const MeasDesc* meas, int n_times_to
                     const double* times, const double* vals, const double* uncs,
                     const double* profiles, int n_sets, const double* params, const double* aux,
                     const SolverOpts& opt, double* logll, int32_t* status, int32_t* nsteps,
-                    double* curves) {
-#define GO(N, F) run_all<N, MODEL, F>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves)
+                    double* curves, const double* irf_mom) {
+#define GO(N, F) run_all<N, MODEL, F>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom)
   bool all_full = true;
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) all_full = false;
   if (all_full && max_nx == 128) GO(4, true);
@@ -67,7 +78,7 @@ extern "C" int trpl_emu_loglik_batch(int32_t model, int32_t n_meas, const trpl_m
                                      const double* uncs, const double* profiles, int32_t n_sets,
                                      const double* params, const double* aux,
                                      const trpl_solver_opts* opts, double* logll, int32_t* status,
-                                     int32_t* nsteps, double* curves) {
+                                     int32_t* nsteps, double* curves, const double* irf_mom) {
   static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch");
   SolverOpts opt;
   memcpy(&opt, opts, sizeof(opt));
@@ -75,6 +86,6 @@ extern "C" int trpl_emu_loglik_batch(int32_t model, int32_t n_meas, const trpl_m
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx > max_nx) max_nx = meas[i].nx;
   const MeasDesc* md = reinterpret_cast<const MeasDesc*>(meas);
   if (model == TRPL_MODEL_STD)
-    return dispatch<MODEL_STD>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves);
-  return dispatch<MODEL_TRAPS>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves);
+    return dispatch<MODEL_STD>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom);
+  return dispatch<MODEL_TRAPS>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom);
 }

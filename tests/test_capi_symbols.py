@@ -25,11 +25,11 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.trpl_abi_version() == 1
+    assert lib.trpl_abi_version() == 2
 
 
 def test_struct_layouts():
-    assert C.sizeof(_capi.MeasDesc) == 56
+    assert C.sizeof(_capi.MeasDesc) == 72
     assert C.sizeof(_capi.SolverOpts) == 32
     assert _capi.MeasDesc.nx.offset == 24 and _capi.MeasDesc.prof_off.offset == 48
 

@@ -29,3 +29,7 @@ def test_closed_forms():
 
 def test_ragged_and_fluence_inputs():
     assert pc.check_edges(backend)
+
+
+def test_traps_model_with_irf_convolution_nx256():
+    print(pc.check_traps_irf(backend))
