@@ -41,7 +41,7 @@ struct KernelArgs {
   double* scratch;           // per-warp slices: resampled | convolved | trimmed
   size_t scratch_stride, off_hk, off_trim;
   int* counter;              // work queue head
-  int n_traj, n_meas, n_times_total;
+  int n_traj, n_meas, n_times_total, warps_per_cta;
   SolverOpts opt;
 };
 
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     in.irf.dt = md->irf_dt;
     in.irf.mom = a.irf_mom ? a.irf_mom + 3 * (size_t)md->irf_off : nullptr;
     {
-      double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * WARPS_PER_CTA + warp) * a.scratch_stride : nullptr;
+      double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * a.warps_per_cta + warp) * a.scratch_stride : nullptr;
       in.irf.ry = ws; in.irf.hk = ws ? ws + a.off_hk : nullptr; in.irf.trim = ws ? ws + a.off_trim : nullptr;
     }
     TrajOut out;
@@ -154,21 +154,32 @@ struct trpl_handle {
 namespace {
 
 template <int NPL, int MODEL, bool FULL>
-int launch(trpl_handle* h, const KernelArgs& a) {
-  const size_t smem = (size_t)WARPS_PER_CTA * Slots<NPL, MODEL>::BYTES;
+int launch(trpl_handle* h, KernelArgs a) {
+  // warps per CTA: as many as fit the 227 KB of one CTA (4 for nx <= 128, fewer for the larger grids)
+  const size_t per_warp = Slots<NPL, MODEL>::BYTES;
+  int wpc = WARPS_PER_CTA;
+  while (wpc > 1 && (size_t)wpc * per_warp > (size_t)h->prop.sharedMemPerBlockOptin) --wpc;
+  if ((size_t)wpc * per_warp > (size_t)h->prop.sharedMemPerBlockOptin)
+    return fail("trajectory state does not fit in shared memory");
+  const size_t smem = (size_t)wpc * per_warp;
+  a.warps_per_cta = wpc;
   auto kern = trpl_forward_kernel<NPL, MODEL, FULL>;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS_PER_CTA, smem));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * wpc, smem));
   if (per_sm < 1) return fail("trajectory kernel does not fit on an SM");
   const int warps_needed = a.n_traj;
   int grid = h->prop.multiProcessorCount * per_sm;
-  const int ctas_needed = (warps_needed + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+  const int ctas_needed = (warps_needed + wpc - 1) / wpc;
   if (grid > ctas_needed) grid = ctas_needed;
   if (grid < 1) grid = 1;
+  if (a.scratch) {
+    CU(h->d_scratch.reserve((size_t)grid * wpc * a.scratch_stride));
+    a.scratch = h->d_scratch.p;
+  }
   CU(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
   CU(cudaEventRecord(h->ev0, h->stream));
-  kern<<<grid, 32 * WARPS_PER_CTA, smem, h->stream>>>(a);
+  kern<<<grid, 32 * wpc, smem, h->stream>>>(a);
   CU(cudaGetLastError());
   CU(cudaEventRecord(h->ev1, h->stream));
   h->launches += 1;
@@ -365,9 +376,7 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
     a.off_hk = (h->max_nrs + 3) & ~(size_t)3;
     a.off_trim = a.off_hk + ((n_hk + 3) & ~(size_t)3);
     a.scratch_stride = a.off_trim + ((h->max_nt + 3) & ~(size_t)3);
-    const size_t warps = (size_t)h->prop.multiProcessorCount * 2 * WARPS_PER_CTA;
-    CU(h->d_scratch.reserve(warps * a.scratch_stride));
-    a.scratch = h->d_scratch.p;
+    a.scratch = reinterpret_cast<double*>(1);   // "wanted": sized and set in launch()
     a.irf_mom = h->d_irf.p;
   }
   a.counter = h->d_counter.p;
