@@ -50,7 +50,7 @@ enum trpl_status {
   TRPL_ST_OK = 0, TRPL_ST_MAX_STEPS = 1, TRPL_ST_H_UNDERFLOW = 2, TRPL_ST_NONFINITE = 4,
   TRPL_ST_FLOORED = 8, TRPL_ST_NEG_FRAC = 16, TRPL_ST_NAN_LL = 32, TRPL_ST_CONV_FAIL = 64
 };
-enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2 };
+enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2, TRPL_OPT_LADDER = 4 };
 
 /* one measurement (sim_info["lengths"/"nx"/"meas_types"][i] + its slice of the data arrays) */
 typedef struct trpl_meas_desc {
@@ -68,6 +68,7 @@ typedef struct trpl_meas_desc {
   double irf_dt;      /* mean IRF time step [ns] (laplace.py:66) */
   int32_t irf_off;    /* first row of the table in the array given to trpl_set_irf */
   int32_t pad_;
+  double min_y;       /* signal floor, Grid.min_y (sim_utils.py:281; forward_solver.py:190-192) */
 } trpl_meas_desc;
 
 typedef struct trpl_solver_opts {
@@ -99,6 +100,13 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
  * (shared_fields["_IRF_tables"], laplace.py:13-41).  Call after trpl_set_problem when any
  * measurement has irf_nk > 0; the in-kernel convolution replaces laplace.py:44-129. */
 int trpl_set_irf(trpl_handle* h, int32_t n_rows_total, const double* moments);
+
+/* Parallel-tempering ladder: with TRPL_OPT_LADDER every trajectory also returns its likelihood at
+ * each of these temperatures (the reference's ll_func(T), trial_move_evaluation.py:150-156), so the
+ * swap move (metropolis.py:66-90) needs no re-simulation.  aux slot TRPL_A_S2T1 must then hold
+ * model_uncertainty^2 (temperature 1).  Results: trpl_download_ladder, [n_sets][n_meas][n_temps]. */
+int trpl_set_ladder(trpl_handle* h, int32_t n_temps, const double* temps);
+int trpl_download_ladder(trpl_handle* h, double* out);
 
 /* Whole-batch likelihood: n_sets parameter sets x n_meas measurements.
  *   params  [n_sets][TRPL_NPARAM]

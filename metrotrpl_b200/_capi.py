@@ -27,7 +27,7 @@ MEAS_IDS = {"TRPL": 0, "TRTS": 1}
 INI_IDS = {"density": 0, "fluence": 1}
 
 ST_MAX_STEPS, ST_H_UNDERFLOW, ST_NONFINITE, ST_FLOORED, ST_NEG_FRAC, ST_NAN_LL, ST_CONV_FAIL = 1, 2, 4, 8, 16, 32, 64
-OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD = 1, 2
+OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD, OPT_LADDER = 1, 2, 4
 
 # Defaults of the integrator.  RTOL keeps the reference's default value and meaning
 # (forward_solver.py:18).  The reference's default ATOL (1e-10 nm^-3, forward_solver.py:19) is larger
@@ -44,7 +44,7 @@ class MeasDesc(C.Structure):
                 ("nx", C.c_int32), ("meas_type", C.c_int32), ("ini_mode", C.c_int32),
                 ("ini_dir", C.c_int32), ("n_t", C.c_int32), ("t_off", C.c_int32),
                 ("prof_off", C.c_int32), ("irf_nk", C.c_int32), ("irf_dt", C.c_double),
-                ("irf_off", C.c_int32), ("pad_", C.c_int32)]
+                ("irf_off", C.c_int32), ("pad_", C.c_int32), ("min_y", C.c_double)]
 
 
 class SolverOpts(C.Structure):
@@ -88,7 +88,7 @@ class PackedProblem:
 
 
 def pack_problem(sim_info, init_params, times, vals=None, uncs=None, model="std",
-                 ini_mode="density", irf_convolution=None, irf_tables=None) -> PackedProblem:
+                 ini_mode="density", irf_convolution=None, irf_tables=None, min_y=None) -> PackedProblem:
     """Flatten sim_info / _init_params / _times / _vals / _uncs (metropolis.py:317-326).
 
     irf_convolution : per-measurement wavelength (0 = none), shared_fields["irf_convolution"]
@@ -125,6 +125,7 @@ def pack_problem(sim_info, init_params, times, vals=None, uncs=None, model="std"
         d.n_t = t.size
         d.t_off = t_off
         d.ini_dir = 1
+        d.min_y = float(np.finfo(float).tiny if min_y is None else min_y[i])   # Grid.min_y, sim_utils.py:281
         if ini_mode == "density":
             if ini.size != nx:                                            # forward_solver.py:101-104
                 raise ValueError(
@@ -224,6 +225,8 @@ def load_library() -> C.CDLL:
     lib.trpl_set_problem.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(MeasDesc), C.c_int32, dp, dp,
                                      dp, C.c_int32, dp]
     lib.trpl_set_irf.argtypes = [H, C.c_int32, dp]
+    lib.trpl_set_ladder.argtypes = [H, C.c_int32, dp]
+    lib.trpl_download_ladder.argtypes = [H, dp]
     lib.trpl_loglik_batch.argtypes = [H, C.c_int32, dp, dp, C.POINTER(SolverOpts), dp, ip, ip, dp]
     lib.trpl_solve_batch.argtypes = [H, C.c_int32, dp, dp, C.POINTER(SolverOpts), dp, ip, ip]
     lib.trpl_upload_batch.argtypes = [H, C.c_int32, dp, dp]
@@ -287,6 +290,20 @@ class Context:
             self._check(self.lib.trpl_set_irf(self.h, int(prob.irf_moments.shape[0]),
                                               _ptr(prob.irf_moments, C.c_double)))
         self.problem = prob
+
+    def set_problem_if_needed(self, prob: PackedProblem):
+        if self.problem is not prob:
+            self.set_problem(prob)
+
+    def set_ladder(self, temps):
+        temps = np.ascontiguousarray(temps, dtype=np.float64)
+        self._check(self.lib.trpl_set_ladder(self.h, temps.size, _ptr(temps, C.c_double)))
+        self._n_ladder = temps.size
+
+    def download_ladder(self, n_sets):
+        out = np.empty((n_sets, self.problem.n_meas, self._n_ladder))
+        self._check(self.lib.trpl_download_ladder(self.h, _ptr(out, C.c_double)))
+        return out
 
     # -- whole-batch calls (host buffers in, host buffers out) --
     def loglik_batch(self, params, aux, opts: SolverOpts, want_curves=False):

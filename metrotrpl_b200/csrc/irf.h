@@ -158,7 +158,8 @@ TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t
 // Likelihood of a stored signal sol[0..n_c) against vals/uncs[0..n_c): abs/negative count,
 // optional set_min_y floor, log10 residuals, three temperatures (trial_move_evaluation.py:117-166).
 TRPL_FN void array_loglik(const double* sol, int n_c, const double* vals, const double* uncs,
-                          double shift, const double* s2T, bool force_min_y, double* ll, double& n_neg) {
+                          double shift, const double* s2T, bool force_min_y, double* ll, double& n_neg,
+                          double* r2_out, double* u2_out) {
   const ivec lane = lane_id();
   int first_floor = n_c;
   double floor_y = 0.0;
@@ -194,9 +195,31 @@ TRPL_FN void array_loglik(const double* sol, int n_c, const double* vals, const 
     l0 = l0 + sel(take, r2 * rcp(s2T[0] + u2), 0.0);
     l1 = l1 + sel(take, r2 * rcp(s2T[1] + u2), 0.0);
     l2 = l2 + sel(take, r2 * rcp(s2T[2] + u2), 0.0);
+    if (r2_out) { scatter(r2_out, k, take, r2); scatter(u2_out, k, take, u2); }
   }
   ll[0] = -uni(warp_sum(l0)); ll[1] = -uni(warp_sum(l1)); ll[2] = -uni(warp_sum(l2));
   n_neg = uni(warp_sum(neg));
+  if (r2_out) warp_sync();
+}
+
+// Likelihood of the same curve at every temperature of a tempering ladder:
+//   ll(T_j) = - sum_k r2_k / (sigma^2 T_j + 2 u_k^2)      (trial_move_evaluation.py:150-156, ll_func(T))
+// so that replica-exchange swaps (metropolis.py:66-90) never need a re-simulation.  Lanes take
+// temperatures, the residuals are broadcast.
+TRPL_FN void ladder_loglik(const double* r2, const double* u2, int n_c, double sigma2,
+                           const double* temps, int n_T, double* out, bool failed) {
+  const ivec lane = lane_id();
+  for (int j0 = 0; j0 < n_T; j0 += 32) {
+    const ivec j = iadd(lane, j0);
+    const mask take = j < n_T;
+    const real s = sigma2 * gather(temps, j, take, 1.0);
+    real acc = splat(0.0);
+    for (int k = 0; k < n_c; ++k) acc = fmadd(splat(r2[k]), rcp(s + u2[k]), acc);
+    real res = -acc;
+    res = sel(is_nan(res), -HUGE_VAL, res);
+    if (failed) res = splat(-HUGE_VAL);
+    scatter(out, j, take, res);
+  }
 }
 
 }  // namespace trpl

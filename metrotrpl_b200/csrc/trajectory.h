@@ -56,7 +56,7 @@ enum StatusBits {
   ST_CONV_FAIL = 64     // IRF convolution failed -> -inf (trial_move_evaluation.py:83-87, :103-106)
 };
 
-enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2 };
+enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2, OPT_LADDER = 4 };
 
 struct SolverOpts {
   double rtol, atol;
@@ -80,6 +80,7 @@ struct MeasDesc {
   double irf_dt;         // mean IRF time step [ns]
   int irf_off;           // first row of the table in the moments array
   int pad_;
+  double min_y;          // floor of the simulated signal (Grid.min_y, sim_utils.py:281)
 };
 
 struct TrajIn {
@@ -94,6 +95,12 @@ struct TrajIn {
   double fl_mult, al_mult;
   double* curve;         // optional [n_t] simulated signal in measurement units
   IrfDesc irf;           // irf.nk == 0: no convolution
+  // tempering ladder (OPT_LADDER): likelihood at every ladder temperature; s2T[1] holds sigma^2
+  const double* ladder_T;
+  int ladder_n;
+  double* ladder_out;    // [ladder_n]
+  double* r2_scratch;    // [n_t] per-warp
+  double* u2_scratch;    // [n_t] per-warp
 };
 
 struct TrajOut {
@@ -223,7 +230,9 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   const int n_t = md.n_t;
   const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
   // min_y floor and IRF convolution need the whole curve: likelihood in a final pass over it
-  const bool post = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || in.irf.nk > 0);
+  const bool ladder = want_ll && (opt.flags & OPT_LADDER) && in.ladder_n > 0 && in.r2_scratch;
+  const bool post = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || in.irf.nk > 0 || ladder);
+  const double min_y = md.min_y;
 
   // ---- initial condition (forward_solver.py:100-122) ----
   V u;
@@ -333,10 +342,10 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
             }
             // forward_solver.py:190-192: from the first value below DBL_MIN on, the curve is DBL_MIN
             const mask take = lane < cnt;
-            const unsigned low = warp_ballot(mand(take, y < DBL_MIN));
+            const unsigned low = warp_ballot(mand(take, y < min_y));
             if (low != 0u) {
               int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
-              y = sel(lane >= firstlow, DBL_MIN, y);
+              y = sel(lane >= firstlow, min_y, y);
               floored = true; status |= ST_FLOORED;
             }
             accumulate(k, take, y);
@@ -541,7 +550,7 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   while (io < n_t) {
     const ivec k = iadd(lane, io);
     const mask take = k < n_t;
-    accumulate(k, take, splat(DBL_MIN));
+    accumulate(k, take, splat(min_y));
     io += 32;
   }
 
@@ -561,7 +570,8 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
         if (!ok) out.status |= ST_CONV_FAIL;
       }
       if (ok) array_loglik(sol, n_c, in.vals, in.uncs, in.scale_shift, in.s2T,
-                           (opt.flags & OPT_FORCE_MIN_Y) != 0, l, n_neg);
+                           (opt.flags & OPT_FORCE_MIN_Y) != 0, l, n_neg,
+                           ladder ? in.r2_scratch : nullptr, ladder ? in.u2_scratch : nullptr);
     } else {
       l[0] = -uni(warp_sum(ll0)); l[1] = -uni(warp_sum(ll1)); l[2] = -uni(warp_sum(ll2));
       n_neg = uni(warp_sum(nneg));
@@ -576,6 +586,11 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       if (l[2] != l[2]) l[2] = ninf;
     }
     out.logll[0] = l[0]; out.logll[1] = l[1]; out.logll[2] = l[2];
+    if (ladder) {
+      const bool failed = !ok || !(n_neg < 0.2 * n_c);
+      ladder_loglik(in.r2_scratch, in.u2_scratch, failed ? 0 : n_c, in.s2T[1], in.ladder_T, in.ladder_n,
+                    in.ladder_out, failed);
+    }
   } else {
     out.logll[0] = out.logll[1] = out.logll[2] = 0.0;
   }

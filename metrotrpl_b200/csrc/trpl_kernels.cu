@@ -39,7 +39,10 @@ struct KernelArgs {
   double* curves;            // [n_sets][n_times_total] or null
   const double* irf_mom;     // [rows][3] or null
   double* scratch;           // per-warp slices: resampled | convolved | trimmed
-  size_t scratch_stride, off_hk, off_trim;
+  size_t scratch_stride, off_hk, off_trim, off_r2, off_u2;
+  const double* ladder_T;
+  double* ladder_out;        // [n_traj][n_ladder]
+  int n_ladder;
   int* counter;              // work queue head
   int n_traj, n_meas, n_times_total, warps_per_cta;
   SolverOpts opt;
@@ -77,7 +80,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     {
       double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * a.warps_per_cta + warp) * a.scratch_stride : nullptr;
       in.irf.ry = ws; in.irf.hk = ws ? ws + a.off_hk : nullptr; in.irf.trim = ws ? ws + a.off_trim : nullptr;
+      in.r2_scratch = (ws && a.n_ladder > 0) ? ws + a.off_r2 : nullptr;
+      in.u2_scratch = (ws && a.n_ladder > 0) ? ws + a.off_u2 : nullptr;
     }
+    in.ladder_T = a.ladder_T; in.ladder_n = a.n_ladder;
+    in.ladder_out = a.ladder_out ? a.ladder_out + (size_t)traj * a.n_ladder : nullptr;
     TrajOut out;
     run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out);
     if (lane == 0) {
@@ -139,7 +146,9 @@ struct trpl_handle {
   int model = 0, n_meas = 0, n_times_total = 0, max_nx = 0;
   bool have_vals = false, have_profiles = false, all_full = false;
   DevBuf<MeasDesc> d_meas;
-  DevBuf<double> d_times, d_vals, d_uncs, d_profiles, d_irf, d_scratch;
+  DevBuf<double> d_times, d_vals, d_uncs, d_profiles, d_irf, d_scratch, d_ladder_T, d_ladder_out;
+  int n_ladder = 0;
+  bool ladder_valid = false;
   bool any_irf = false, have_irf = false;
   size_t max_nrs = 0, max_nt = 0;
   int irf_rows_needed = 0;
@@ -276,6 +285,7 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
     }
     if (!(m.thickness > 0)) return fail("thickness must be positive");
     if (m.irf_nk < 0 || (m.irf_nk > 0 && !(m.irf_dt > 0))) return fail("bad IRF descriptor");
+    if (!(m.min_y >= 0)) return fail("min_y must be non-negative");
     if (m.nx > max_nx) max_nx = m.nx;
   }
   // all measurements of one launch share the nodes-per-lane template: nx must fit 32*NPL and
@@ -330,6 +340,26 @@ int trpl_set_irf(trpl_handle* h, int32_t n_rows_total, const double* moments) {
   return 0;
 }
 
+int trpl_set_ladder(trpl_handle* h, int32_t n_temps, const double* temps) {
+  if (!h || n_temps < 1 || !temps) return fail("trpl_set_ladder: bad arguments");
+  CU(cudaSetDevice(h->device));
+  CU(h->d_ladder_T.reserve(n_temps));
+  CU(cudaMemcpyAsync(h->d_ladder_T.p, temps, sizeof(double) * n_temps, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->n_ladder = n_temps;
+  return 0;
+}
+
+int trpl_download_ladder(trpl_handle* h, double* out) {
+  if (!h || !out) return fail("null argument");
+  if (!h->ladder_valid) return fail("the last run did not produce ladder likelihoods");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out, h->d_ladder_out.p, sizeof(double) * (size_t)h->n_sets * h->n_meas * h->n_ladder,
+                     cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 int trpl_upload_batch(trpl_handle* h, int32_t n_sets, const double* params, const double* aux) {
   if (!h) return fail("null handle");
   if (h->n_meas < 1) return fail("trpl_set_problem has not been called");
@@ -357,6 +387,9 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
   const bool conv = want_ll && h->any_irf;
   if (conv && !h->have_irf) return fail("measurements ask for IRF convolution but trpl_set_irf was not called");
   if (conv) want_curves = 1;
+  const bool ladder = want_ll && (opts->flags & TRPL_OPT_LADDER);
+  if (ladder && h->n_ladder < 1) return fail("TRPL_OPT_LADDER without trpl_set_ladder");
+  if (ladder) want_curves = 1;
   CU(cudaSetDevice(h->device));
   KernelArgs a;
   a.params = h->d_params.p; a.aux = h->d_aux.p; a.meas = h->d_meas.p; a.times = h->d_times.p;
@@ -370,14 +403,25 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
   }
   h->curves_valid = want_curves != 0;
   a.irf_mom = nullptr; a.scratch = nullptr; a.scratch_stride = 0; a.off_hk = 0; a.off_trim = 0;
-  if (conv) {
-    // per-warp scratch: resampled curve | convolved curve | trimmed curve (all stay in L2)
-    const size_t n_hk = (h->max_nrs - 1) / 2 + 1;
-    a.off_hk = (h->max_nrs + 3) & ~(size_t)3;
+  a.off_r2 = 0; a.off_u2 = 0; a.ladder_T = nullptr; a.ladder_out = nullptr; a.n_ladder = 0;
+  h->ladder_valid = false;
+  if (conv || ladder) {
+    // per-warp scratch: resampled | convolved | trimmed curve | residuals^2 | 2 unc^2 (all stay in L2)
+    const size_t nrs = conv ? h->max_nrs : 0;
+    const size_t n_hk = conv ? (h->max_nrs - 1) / 2 + 1 : 0;
+    const size_t nt4 = (h->max_nt + 3) & ~(size_t)3;
+    a.off_hk = (nrs + 3) & ~(size_t)3;
     a.off_trim = a.off_hk + ((n_hk + 3) & ~(size_t)3);
-    a.scratch_stride = a.off_trim + ((h->max_nt + 3) & ~(size_t)3);
+    a.off_r2 = a.off_trim + nt4;
+    a.off_u2 = a.off_r2 + nt4;
+    a.scratch_stride = a.off_u2 + nt4;
     a.scratch = reinterpret_cast<double*>(1);   // "wanted": sized and set in launch()
-    a.irf_mom = h->d_irf.p;
+    if (conv) a.irf_mom = h->d_irf.p;
+  }
+  if (ladder) {
+    CU(h->d_ladder_out.reserve((size_t)h->n_sets * h->n_meas * h->n_ladder));
+    a.ladder_T = h->d_ladder_T.p; a.ladder_out = h->d_ladder_out.p; a.n_ladder = h->n_ladder;
+    h->ladder_valid = true;
   }
   a.counter = h->d_counter.p;
   a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;

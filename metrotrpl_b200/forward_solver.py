@@ -67,7 +67,7 @@ def solve_batch(iniPars, grids, states, indexes, meas_types=None, units=None, mo
     sim_info = {"num_meas": n_meas, "lengths": [g.thickness for g in grids],
                 "nx": [g.nx for g in grids], "meas_types": list(meas_types)}
     prob = _capi.pack_problem(sim_info, iniPars, [g.tSteps for g in grids], None, None, model=model,
-                              ini_mode=ini_mode)
+                              ini_mode=ini_mode, min_y=[g.min_y for g in grids])
     params = _capi.pack_params(states, indexes, units, model=model)
     n_sets = params.shape[0]
     aux = _capi.default_aux(n_sets, n_meas, [1.0] * n_meas)

@@ -1,0 +1,247 @@
+"""Metropolis sampler driver: the reference's metro() with whole batches per iteration.
+
+Reference: metropolis.py.  What changes is *when* likelihoods are computed, not what is computed:
+
+  * reference (serial fallback, metropolis.py:93-137): for each chain in turn - propose, simulate
+    num_meas curves on the CPU, accept/reject; tempering swaps re-simulate both partners.
+  * here: the proposals of ALL chains of an iteration are drawn first (consuming the generator in
+    exactly the reference's serial order: chain m's proposal draws, then chain m's acceptance
+    draw), evaluated in ONE kernel launch (n_chains x num_meas trajectories), then accepted or
+    rejected.  The kernel also returns every proposal's likelihood at every ladder temperature
+    (the reference's ll_funcs), so swaps (metropolis.py:66-90) are pure host arithmetic.
+  * several GPUs: chains are sharded over ranks for the launch and the per-chain likelihood rows
+    are all-gathered (parallel.Comm); every rank then makes the same accept/swap decisions from
+    the same generator state, so results do not depend on the number of GPUs.
+
+One deliberate difference: the reference's serial swap `a[i], a[i+1] = a[i+1], a[i]` on NumPy
+views leaves both chains holding the upper chain's state (an aliasing slip; its MPI path swaps
+correctly).  Here the states are swapped.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import signal
+from time import perf_counter
+
+import numpy as np
+
+from . import _capi
+from .laplace import load_irf_tables
+from .mcmc_logging import start_logging, stop_logging
+from .parallel import Comm
+from .sim_utils import Ensemble
+from .trial_move_generation import make_trial_move
+
+MSG_FREQ = 100       # metropolis.py:31
+MSG_COOLDOWN = 3     # metropolis.py:32
+SEED = 235817049752375780   # metropolis.py:296
+
+
+def roll_acceptance(rng, logratio):
+    """metropolis.py:35-39."""
+    if isinstance(logratio, np.ndarray):
+        return rng.random(len(logratio)) < np.exp(logratio)
+    return rng.random() < np.exp(logratio)
+
+
+class CudaEvaluator:
+    """Likelihood of a batch of states at every ladder temperature, on this rank's GPU."""
+
+    def __init__(self, shared_fields, device=None):
+        from .trial_move_evaluation import PathCache
+        self.cache = PathCache(shared_fields, device=device)
+        self.ladder = np.asarray(shared_fields["_T"], dtype=np.float64)
+        self.cache.ctx.set_ladder(self.ladder)
+        self.flags = self.cache.flags | _capi.OPT_LADDER
+
+    def __call__(self, states, sigmas):
+        """states [n, n_params], sigmas: list of {meas_type: sigma}.  Returns [n, n_T]."""
+        n = states.shape[0]
+        params, aux = self.cache.pack(states, sigmas, np.ones((n, 3)))   # slot 1 = sigma^2 (T = 1)
+        sf = self.cache.sf
+        opts = _capi.make_opts(sf.get("rtol", None), sf.get("atol", None), flags=self.flags)
+        ctx = self.cache.ctx
+        ctx.set_problem_if_needed(self.cache.prob)
+        ctx.loglik_batch(params, aux, opts, want_curves=False)
+        lad = ctx.download_ladder(n)
+        tot = lad.sum(axis=1)
+        return np.where(np.isnan(tot), -np.inf, tot)
+
+
+def sharded_eval(evaluator, comm, states, sigmas):
+    """Evaluate all chains' states, each rank its own block; every rank gets all rows."""
+    n = states.shape[0]
+    lo, hi = comm.shard(n)
+    local = evaluator(states[lo:hi], sigmas[lo:hi]) if hi > lo else np.zeros((0, 0))
+    if comm.world == 1:
+        return local
+    if hi == lo:
+        raise ValueError("more ranks than chains")
+    return comm.allgather_rows(local, n)
+
+
+def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, shared_fields,
+                            unique_fields, RNG, logger, evaluator, comm, cur_ladder=None,
+                            need_initial_state=True):
+    """Batched twin of main_metro_loop_serial (metropolis.py:93-137).
+
+    states [n_chains, n_params, n_iters], logll/accept [n_chains, n_iters]; cur_ladder
+    [n_chains, n_T] holds each chain's current state's likelihood at every ladder temperature.
+    """
+    n_chains = shared_fields["_n_chains"]
+    T = np.asarray(shared_fields["_T"], dtype=float)
+    own = np.arange(n_chains)
+    sigmas = [uf["model_uncertainty"] for uf in unique_fields]
+    swap_accept = np.zeros(n_chains, dtype=int)
+    swap_attempts = np.zeros(n_chains, dtype=int)
+    if need_initial_state:
+        logger.info("Simulating initial state:")
+        cur_ladder = sharded_eval(evaluator, comm, np.ascontiguousarray(states[:, :, 0]), sigmas)
+        logll[:, 0] = cur_ladder[own, own]
+        starting_iter += 1
+    elif cur_ladder is None:
+        cur_ladder = sharded_eval(evaluator, comm,
+                                  np.ascontiguousarray(states[:, :, starting_iter - 1]), sigmas)
+    for k in range(starting_iter, num_iters):
+        if k % MSG_FREQ == 0 or k < starting_iter + MSG_COOLDOWN:
+            for m in range(n_chains):
+                logger.info(f"Iter {k} MetroState #{m} Current state: {states[m, :, k-1]} logll {logll[m, k-1]}")
+        # proposals and acceptance draws in the reference's generator order
+        proposals = np.empty((n_chains, states.shape[1]))
+        u = np.empty(n_chains)
+        for m in range(n_chains):
+            proposals[m] = make_trial_move(states[m, :, k - 1],
+                                           unique_fields[m]["_T"] ** 0.5 * shared_fields["base_trial_move"],
+                                           shared_fields, RNG, logger)
+            u[m] = RNG.random()
+        new_ladder = sharded_eval(evaluator, comm, proposals, sigmas)
+        new_ll = new_ladder[own, own]
+        logratio = new_ll - logll[:, k - 1]
+        logratio = np.where(np.isnan(logratio), -np.inf, logratio)
+        with np.errstate(over="ignore"):
+            accepted = u < np.exp(logratio)
+        for m in range(n_chains):
+            if accepted[m]:
+                logll[m, k] = new_ll[m]
+                states[m, :, k] = proposals[m]
+                accept[m, k] = 1
+                cur_ladder[m] = new_ladder[m]
+            else:
+                logll[m, k] = logll[m, k - 1]
+                states[m, :, k] = states[m, :, k - 1]
+        if shared_fields["do_parallel_tempering"] and k % shared_fields["temper_freq"] == 0:
+            for _ in range(n_chains - 1):
+                i = RNG.integers(0, n_chains - 1)
+                swap_attempts[i] += 1
+                bi_ui, bj_ui = cur_ladder[i, i], cur_ladder[i, i + 1]
+                bi_uj, bj_uj = cur_ladder[i + 1, i], cur_ladder[i + 1, i + 1]
+                ratio = bi_ui + bj_uj - bi_uj - bj_ui
+                with np.errstate(over="ignore", invalid="ignore"):
+                    ok = RNG.random() < np.exp(-ratio)
+                if ok:
+                    swap_accept[i] += 1
+                    logll[i, k] = bi_uj
+                    logll[i + 1, k] = bj_ui
+                    tmp = states[i, :, k].copy()
+                    states[i, :, k] = states[i + 1, :, k]
+                    states[i + 1, :, k] = tmp
+                    cur_ladder[[i, i + 1]] = cur_ladder[[i + 1, i]]
+    return states, logll, accept, swap_attempts, swap_accept, cur_ladder
+
+
+def kill_from_cl(signal_n, frame):
+    raise KeyboardInterrupt("Terminate from command line")
+
+
+def all_signal_handler(func):
+    for s in signal.Signals:
+        try:
+            signal.signal(s, func)
+        except (ValueError, OSError, RuntimeError):
+            continue
+
+
+def metro(sim_info, iniPar, e_data, MCMC_fields, param_info, verbose=False, export_path="",
+          **kwargs):
+    """Same call as the reference's metro() (metropolis.py:283-473).
+
+    Extra keyword arguments: evaluator_factory (tests), comm (a parallel.Comm), irf_dir,
+    install_signal_handlers (default True, as the reference).
+    """
+    clock0 = perf_counter()
+    comm = kwargs.get("comm", None) or Comm()
+    rank = comm.rank
+    if kwargs.get("install_signal_handlers", True):
+        all_signal_handler(kill_from_cl)
+    os.makedirs(MCMC_fields["output_path"], exist_ok=True)
+    load_checkpoint = MCMC_fields.get("load_checkpoint", None)
+    num_iters = MCMC_fields["num_iters"]
+    checkpoint_freq = MCMC_fields.get("checkpoint_freq", num_iters)
+    RNG = np.random.default_rng(SEED)
+    logger_name = kwargs.get("logger_name", "Ensemble0") + f"-rank{rank}-"
+    logger, handler = start_logging(log_dir=MCMC_fields["output_path"], name=logger_name, verbose=verbose)
+
+    starting_iter = 0
+    if load_checkpoint is None:
+        MS_list = Ensemble(param_info, sim_info, MCMC_fields, num_iters, verbose)
+        ef = MS_list.ensemble_fields
+        ef["_init_params"] = iniPar
+        ef["_times"], ef["_vals"], ef["_uncs"] = e_data
+        MS_list.random_state = RNG.bit_generator.state
+        if ef.get("irf_convolution", None) is not None:
+            ef["_IRF_tables"] = load_irf_tables(ef["irf_convolution"], kwargs.get("irf_dir", "IRFs"))
+        else:
+            ef["_IRF_tables"] = {}
+        if rank == 0:
+            MS_list.checkpoint(os.path.join(ef["output_path"], export_path))
+    else:
+        with open(os.path.join(MCMC_fields["output_path"], load_checkpoint), "rb") as f:
+            MS_list = pickle.load(f)
+        if "starting_iter" in MCMC_fields and MCMC_fields["starting_iter"] < MS_list.latest_iter:
+            starting_iter = MCMC_fields["starting_iter"]
+            MS_list.H.extend(starting_iter)
+        else:
+            starting_iter = MS_list.latest_iter
+            MS_list.H.extend(num_iters)
+            MS_list.ensemble_fields["num_iters"] = MCMC_fields["num_iters"]
+    shared_fields = MS_list.ensemble_fields
+    unique_fields = MS_list.unique_fields
+    RNG.bit_generator.state = MS_list.random_state
+    states, logll, accept = MS_list.H.states, MS_list.H.loglikelihood, MS_list.H.accept
+
+    factory = kwargs.get("evaluator_factory", None)
+    evaluator = factory(shared_fields) if factory is not None else CudaEvaluator(shared_fields, device=comm.local_rank)
+
+    need_initial_state = load_checkpoint is None
+    cur_ladder = None
+    ending_iter = min(starting_iter + checkpoint_freq, num_iters)
+    swap_att = swap_acc = None
+    while ending_iter <= num_iters:
+        logger.info(f"Simulating from {starting_iter} to {ending_iter}")
+        states, logll, accept, swap_att, swap_acc, cur_ladder = main_metro_loop_batched(
+            states, logll, accept, starting_iter, ending_iter, shared_fields, unique_fields, RNG, logger,
+            evaluator, comm, cur_ladder=cur_ladder, need_initial_state=need_initial_state)
+        MS_list.H.swap_attempts += swap_att
+        MS_list.H.swap_accept += swap_acc
+        if ending_iter == num_iters:
+            break
+        MS_list.latest_iter = ending_iter
+        MS_list.H.pack(states, logll, accept)
+        MS_list.random_state = RNG.bit_generator.state
+        if rank == 0:
+            logger.info(f"Saving checkpoint at k={ending_iter}")
+            MS_list.checkpoint(os.path.join(shared_fields["output_path"], export_path))
+        need_initial_state = False
+        starting_iter = ending_iter
+        ending_iter = min(ending_iter + checkpoint_freq, num_iters)
+    logger.info(f"Rank {rank} took {perf_counter() - clock0} s")
+    MS_list.latest_iter = ending_iter
+    MS_list.H.pack(states, logll, accept)
+    MS_list.random_state = RNG.bit_generator.state
+    if rank == 0:
+        logger.info(f"Swap accept rate: {MS_list.H.swap_accept} accepted of {MS_list.H.swap_attempts} attempts")
+        logger.info(f"Exporting to {shared_fields['output_path']}")
+        MS_list.checkpoint(os.path.join(shared_fields["output_path"], export_path))
+    stop_logging(logger, handler, 0)
+    return MS_list

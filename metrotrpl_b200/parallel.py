@@ -1,0 +1,83 @@
+"""One process per GPU: rank bookkeeping, work sharding and the one small collective the path has.
+
+Parameter sets (tempering replicas, dense-sampling points) are independent, so ranks take disjoint
+contiguous shards and there is no collective on the data path.  The only exchange is the
+all-gather of per-chain log-likelihood rows that replica-exchange swaps need
+(metropolis.py:204-261 of the reference does this with MPI send/recv pairs).  PyTorch is used for
+the plumbing only: NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+class Comm:
+    """Thin wrapper over torch.distributed (or nothing, when world == 1)."""
+
+    def __init__(self, backend=None, device=None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        self.backend = None
+        self.device = device
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                if backend is None:
+                    backend = "nccl" if torch.cuda.is_available() else "gloo"
+                if backend == "nccl":
+                    torch.cuda.set_device(self.local_rank)
+                    dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local_rank))
+                else:
+                    dist.init_process_group(backend=backend)
+            self.dist = dist
+            self.backend = dist.get_backend()
+            self.torch = torch
+
+    def _dev(self):
+        return f"cuda:{self.local_rank}" if self.backend == "nccl" else "cpu"
+
+    def shard(self, n):
+        """Contiguous block [lo, hi) of n items owned by this rank (sizes differ by at most one)."""
+        return shard_range(n, self.rank, self.world)
+
+    def allgather_rows(self, local, n_total):
+        """Concatenate every rank's rows (rank order).  local: [n_local, ...] float64."""
+        local = np.ascontiguousarray(local, dtype=np.float64)
+        if self.dist is None:
+            return local
+        torch = self.torch
+        tail = local.shape[1:]
+        counts = [shard_range(n_total, r, self.world) for r in range(self.world)]
+        width = max(hi - lo for lo, hi in counts)
+        pad = np.zeros((width,) + tail)
+        pad[:local.shape[0]] = local
+        send = torch.from_numpy(pad).to(self._dev())
+        recv = [torch.empty_like(send) for _ in range(self.world)]
+        self.dist.all_gather(recv, send)
+        parts = [recv[r][:counts[r][1] - counts[r][0]].cpu().numpy() for r in range(self.world)]
+        return np.concatenate(parts, axis=0)
+
+    def max(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self._dev())
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier(self):
+        if self.dist is not None:
+            if self.backend == "nccl":
+                self.dist.barrier(device_ids=[self.local_rank])
+            else:
+                self.dist.barrier()
+
+
+def shard_range(n, rank, world):
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -119,6 +119,7 @@ def eval_trial_moves(states, temps, sigmas, shared_fields, cache: Optional[PathC
     if temps.ndim == 1:
         temps = np.repeat(temps[:, None], 3, axis=1)
     params, aux = cache.pack(states, sigmas, temps)
+    cache.ctx.set_problem_if_needed(cache.prob)
     per, status, nsteps, curves = cache.ctx.loglik_batch(params, aux, cache.opts(honor_hmax),
                                                          want_curves=want_curves)
     logll = per[:, :, 0].sum(axis=1)

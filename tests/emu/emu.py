@@ -33,11 +33,11 @@ def lib():
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         _lib.trpl_emu_loglik_batch.argtypes = [C.c_int32, C.c_int32, C.POINTER(_capi.MeasDesc), C.c_int32,
                                                dp, dp, dp, dp, C.c_int32, dp, dp,
-                                               C.POINTER(_capi.SolverOpts), dp, ip, ip, dp, dp]
+                                               C.POINTER(_capi.SolverOpts), dp, ip, ip, dp, dp, dp, C.c_int32, dp]
     return _lib
 
 
-def loglik_batch(prob, params, aux, opts, want_curves=True):
+def loglik_batch(prob, params, aux, opts, want_curves=True, ladder=None):
     params = np.ascontiguousarray(params, dtype=np.float64)
     aux = np.ascontiguousarray(aux, dtype=np.float64)
     n_sets = params.shape[0]
@@ -46,12 +46,17 @@ def loglik_batch(prob, params, aux, opts, want_curves=True):
     nsteps = np.empty((n_sets, prob.n_meas, 2), dtype=np.int32)
     curves = np.empty((n_sets, prob.n_times_total)) if want_curves else None
     p = _capi._ptr
+    lad_T = None if ladder is None else np.ascontiguousarray(ladder, dtype=np.float64)
+    lad_out = None if ladder is None else np.empty((n_sets, prob.n_meas, lad_T.size))
     rc = lib().trpl_emu_loglik_batch(prob.model, prob.n_meas, prob.meas, prob.n_times_total,
                                      p(prob.times, C.c_double), p(prob.vals, C.c_double),
                                      p(prob.uncs, C.c_double), p(prob.profiles, C.c_double), n_sets,
                                      p(params, C.c_double), p(aux, C.c_double), C.byref(opts),
                                      p(logll, C.c_double), p(status, C.c_int32), p(nsteps, C.c_int32),
-                                     p(curves, C.c_double), p(prob.irf_moments, C.c_double))
+                                     p(curves, C.c_double), p(prob.irf_moments, C.c_double),
+                                     p(lad_T, C.c_double), 0 if ladder is None else lad_T.size, p(lad_out, C.c_double))
     if rc:
         raise RuntimeError("emu failed")
+    if ladder is not None:
+        return logll, status, nsteps, curves, lad_out
     return logll, status, nsteps, curves

@@ -16,7 +16,8 @@ template <int NPL, int MODEL, bool FULL>
 static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const double* times,
                     const double* vals, const double* uncs, const double* profiles, int n_sets,
                     const double* params, const double* aux, const SolverOpts& opt, double* logll,
-                    int32_t* status, int32_t* nsteps, double* curves, const double* irf_mom) {
+                    int32_t* status, int32_t* nsteps, double* curves, const double* irf_mom,
+                    const double* ladder_T, int n_ladder, double* ladder_out) {
   const int n_traj = n_sets * n_meas;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int traj = 0; traj < n_traj; ++traj) {
@@ -45,6 +46,10 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
       ry.resize(n_rs + 4); hk.resize(n_rs / 2 + 4); trim.resize(md->n_t + 4);
     }
     in.irf.ry = ry.data(); in.irf.hk = hk.data(); in.irf.trim = trim.data();
+    std::vector<double> r2(md->n_t + 4), u2(md->n_t + 4);
+    in.r2_scratch = n_ladder > 0 ? r2.data() : nullptr; in.u2_scratch = n_ladder > 0 ? u2.data() : nullptr;
+    in.ladder_T = ladder_T; in.ladder_n = n_ladder;
+    in.ladder_out = ladder_out ? ladder_out + (size_t)traj * n_ladder : nullptr;
     TrajOut out;
     run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out);
     for (int k = 0; k < 3; ++k) logll[3 * (size_t)traj + k] = out.logll[k];
@@ -58,8 +63,9 @@ static int dispatch(int max_nx, int n_meas, const MeasDesc* meas, int n_times_to
                     const double* times, const double* vals, const double* uncs,
                     const double* profiles, int n_sets, const double* params, const double* aux,
                     const SolverOpts& opt, double* logll, int32_t* status, int32_t* nsteps,
-                    double* curves, const double* irf_mom) {
-#define GO(N, F) run_all<N, MODEL, F>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom)
+                    double* curves, const double* irf_mom,
+                    const double* ladder_T, int n_ladder, double* ladder_out) {
+#define GO(N, F) run_all<N, MODEL, F>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom, ladder_T, n_ladder, ladder_out)
   bool all_full = true;
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) all_full = false;
   if (all_full && max_nx == 128) GO(4, true);
@@ -78,7 +84,8 @@ extern "C" int trpl_emu_loglik_batch(int32_t model, int32_t n_meas, const trpl_m
                                      const double* uncs, const double* profiles, int32_t n_sets,
                                      const double* params, const double* aux,
                                      const trpl_solver_opts* opts, double* logll, int32_t* status,
-                                     int32_t* nsteps, double* curves, const double* irf_mom) {
+                                     int32_t* nsteps, double* curves, const double* irf_mom,
+                                     const double* ladder_T, int32_t n_ladder, double* ladder_out) {
   static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch");
   SolverOpts opt;
   memcpy(&opt, opts, sizeof(opt));
@@ -86,6 +93,6 @@ extern "C" int trpl_emu_loglik_batch(int32_t model, int32_t n_meas, const trpl_m
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx > max_nx) max_nx = meas[i].nx;
   const MeasDesc* md = reinterpret_cast<const MeasDesc*>(meas);
   if (model == TRPL_MODEL_STD)
-    return dispatch<MODEL_STD>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom);
-  return dispatch<MODEL_TRAPS>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom);
+    return dispatch<MODEL_STD>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom, ladder_T, n_ladder, ladder_out);
+  return dispatch<MODEL_TRAPS>(max_nx, n_meas, md, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom, ladder_T, n_ladder, ladder_out);
 }

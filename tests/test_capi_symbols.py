@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts():
-    assert C.sizeof(_capi.MeasDesc) == 72
+    assert C.sizeof(_capi.MeasDesc) == 80
     assert C.sizeof(_capi.SolverOpts) == 32
     assert _capi.MeasDesc.nx.offset == 24 and _capi.MeasDesc.prof_off.offset == 48
 

@@ -1,0 +1,118 @@
+"""GPU tier: the batched callers of the path (eval_trial_move mirror, solve mirror, metro(),
+dense sampling) through the CUDA library."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from metrotrpl_b200 import _capi
+from metrotrpl_b200 import dense_sampling as ds
+from metrotrpl_b200.forward_solver import solve
+from metrotrpl_b200.metropolis import metro
+from metrotrpl_b200.sim_utils import Grid
+from metrotrpl_b200.trial_move_evaluation import eval_trial_move
+from oracle import trpl_oracle as orc
+from tests.test_metropolis_batched import GUESS, NAMES, UNITS, emu_factory, small_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def test_solve_mirror_matches_reference_unit_test():
+    """Tests/test_metropolis.py:93-190 (test_solve): high-injection radiative decay, PL and TRTS,
+    undefined measurement / solver raise NotImplementedError, state is left untouched."""
+    g = Grid(thickness=1000, nx=100, tSteps=np.linspace(0, 100, 1001), hmax=4)
+    names = ["n0", "p0", "mu_n", "mu_p", "ks", "tauN", "tauP", "Cn", "Cp", "Sf", "Sb", "eps", "Tm"]
+    uc = {"n0": 1e-21, "p0": 1e-21, "mu_n": 1e5, "mu_p": 1e5, "ks": 1e12, "Sf": 1e-2, "Sb": 1e-2}
+    vals = {"n0": 0, "p0": 0, "mu_n": 0, "mu_p": 0, "ks": 1e-11, "Cn": 0, "Cp": 0, "tauN": 1e99,
+            "tauP": 1e99, "Sf": 0, "Sb": 0, "Tm": 300, "eps": 1}
+    idx = {n: i for i, n in enumerate(names)}
+    state = [vals[n] for n in names]
+    units = np.array([uc.get(n, 1) for n in names], dtype=float)
+    init_dN = 1e20 * np.ones(g.nx)
+    pl = solve(init_dN, g, state, idx, meas="TRPL", units=units, RTOL=1e-10, ATOL=1e-14)
+    out_dN = 0.0009900990095719482
+    expect = 1e-11 * 1e12 * out_dN ** 2 * 1000 * 1e23
+    assert abs(pl[-1] / expect - 1) < 1e-7
+    vals2 = dict(vals, mu_n=10, mu_p=10)
+    state2 = [vals2[n] for n in names]
+    trts = solve(init_dN, g, state2, idx, meas="TRTS", units=units)
+    expect = orc.Q_C * (2 * 10 * 1e5) * 0.0009900986886696803 * 1000 * 1e9
+    assert abs(trts[-1] / expect - 1) < 1e-6
+    assert state2 == [vals2[n] for n in names]
+    with pytest.raises(NotImplementedError):
+        solve(init_dN, g, state, idx, meas="something else")
+    with pytest.raises(NotImplementedError):
+        solve(init_dN, g, state, idx, meas="TRPL", solver=("somethign else",))
+    # Tests/test_metropolis.py:192-251 (test_solve_depletion): a raised Grid.min_y truncates the tail
+    vals3 = dict(vals, mu_n=1, mu_p=1, ks=2e-10)
+    st3 = [vals3[n] for n in names]
+    pl0 = 2e-10 * (1e18) ** 2 * 1000e-7
+    g.min_y = pl0 * 1e-2
+    pl = solve(1e18 * np.ones(g.nx), g, st3, idx, meas="TRPL", units=units, RTOL=1e-10, ATOL=1e-14)
+    assert min(pl) >= g.min_y
+    np.testing.assert_equal(pl[-10:], g.min_y)
+    # Tests/test_metropolis.py:314-365 (test_solve_iniPar): fluence mode == explicit profile
+    g2 = Grid(thickness=1000, nx=100, tSteps=np.linspace(0, 100, 1001), hmax=4)
+    prof = 1e15 * 6e4 * np.exp(-6e4 * g2.xSteps * 1e-7)
+    a = solve(prof, g2, state, idx, units=units, RTOL=1e-10, ATOL=1e-14)
+    b = solve([1e15, 6e4], g2, state, idx, units=units, ini_mode="fluence", RTOL=1e-10, ATOL=1e-14)
+    np.testing.assert_allclose(a / a.max(), b / a.max(), atol=1e-7)
+
+
+def test_eval_trial_move_mirror_and_ll_funcs():
+    tmp = tempfile.mkdtemp()
+    sim_info, ini, e_data, MCMC, param_info = small_problem(tmp)
+    idx = {n: i for i, n in enumerate(NAMES)}
+    units = np.array([UNITS.get(n, 1) for n in NAMES], dtype=float)
+    state = np.array([GUESS[n] for n in NAMES], dtype=float)
+    sf = {"_sim_info": sim_info, "_init_params": ini, "_times": e_data[0], "_vals": e_data[1],
+          "_uncs": e_data[2], "_param_indexes": idx, "units": units, "model": "std",
+          "ini_mode": "density", "hmax": 4, "rtol": 1e-8, "atol": None}
+    uf = {"model_uncertainty": {"TRPL": 0.05}, "_T": 2.0, "_T_alt": (1.0, 4.0)}
+    ll, funcs = eval_trial_move(state, uf, sf, None)
+    for T in (2.0, 1.0, 4.0):
+        want, per = orc.state_loglik(state, sim_info, ini, e_data[0], e_data[1], e_data[2], idx, units,
+                                     {"TRPL": 0.05}, T=T, rtol=1e-10, atol=1e-16)
+        got = sum(f(T) for f in funcs)
+        assert abs(got / want - 1) < 1e-5
+    assert abs(ll - sum(f(2.0) for f in funcs)) < 1e-12 * abs(ll)
+    with pytest.raises(KeyError):
+        funcs[0](3.0)
+
+
+def test_metro_on_gpu_matches_host_lockstep_run():
+    a = metro(*_args(tempfile.mkdtemp()), export_path="g.pik", install_signal_handlers=False)
+    b = metro(*_args(tempfile.mkdtemp()), export_path="e.pik", install_signal_handlers=False,
+              evaluator_factory=emu_factory)
+    np.testing.assert_allclose(a.H.loglikelihood[:, 0], b.H.loglikelihood[:, 0], rtol=1e-6)
+    # identical generator stream + likelihoods equal to rounding -> same decisions
+    np.testing.assert_array_equal(a.H.accept, b.H.accept)
+    np.testing.assert_allclose(a.H.states, b.H.states, rtol=1e-12)
+    np.testing.assert_array_equal(a.H.swap_accept, b.H.swap_accept)
+
+
+def _args(tmp):
+    sim_info, ini, e_data, MCMC, param_info = small_problem(tmp)
+    return sim_info, ini, e_data, MCMC, param_info
+
+
+def test_dense_sampling_on_gpu_against_oracle():
+    tmp = tempfile.mkdtemp()
+    sim_info, ini, e_data, MCMC, param_info = small_problem(tmp)
+    param_info["prior_dist"]["tauN"] = (100, 1000)
+    param_info["prior_dist"]["p0"] = (1e15, 1e16)
+    for n in NAMES:
+        if n not in ("tauN", "p0"):
+            param_info["active"][n] = 0
+    flags = {"num_iters": 6, "log_y": 1, "likel2move_ratio": {"TRPL": 1.0}, "model": "std",
+             "ini_mode": "density", "rtol": 1e-8}
+    np.random.seed(1)
+    N, P, X = ds.bayes(np.array([0]), None, ini, sim_info, e_data, flags, param_info)
+    idx = {n: i for i, n in enumerate(NAMES)}
+    units = np.array([UNITS.get(n, 1) for n in NAMES], dtype=float)
+    sigma = 0.05 * 1.0
+    for i in (0, 5):
+        want, _ = orc.state_loglik(X[i], sim_info, ini, e_data[0], e_data[1], e_data[2], idx, units,
+                                   {"TRPL": sigma}, rtol=1e-10, atol=1e-16)
+        assert abs(P[i] / want - 1) < 1e-5
