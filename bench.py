@@ -187,6 +187,17 @@ def allreduce_max(dist, local, x):
     return float(tns.item())
 
 
+def gather_rows(dist, local, row):
+    """[world, len(row)] on every rank (diagnostics only)."""
+    if dist is None:
+        return [list(map(float, row))]
+    import torch
+    t = torch.tensor(row, dtype=torch.float64, device=f"cuda:{local}")
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [o.cpu().tolist() for o in out]
+
+
 def barrier(dist, local):
     if dist is not None:
         import torch
@@ -251,6 +262,7 @@ def run_ours(args):
     ll, status, nsteps, _ = ctx.download()
     step_ms = allreduce_max(dist, local, total_ms / args.steps)
     value = world * n_traj / (step_ms * 1e-3)
+    per_rank = gather_rows(dist, local, [total_ms / args.steps, float(np.mean(kernel_ms)), float(nsteps.sum())])
 
     # ---- end to end through the public API (host numpy in, host numpy out) ----------------
     for _ in range(max(1, args.warmup // 2)):
@@ -271,8 +283,12 @@ def run_ours(args):
     k_ms = float(np.mean(kernel_ms))
     achieved = flops / (k_ms * 1e-3) / 1e12
     alg_bytes = h2d + d2h + ini.nbytes + 3 * 6 * len(t) * 8
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")
+    if os.path.exists(tpath) and args.sets == 4096:
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved / peak_tf, "traffic": None,
+            "frac": achieved / peak_tf, "traffic": traffic,
             "peak_source": "in-run DFMA probe (trpl_fp64_peak_probe); B200 nominal FP64 = 37 TFLOP/s; "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "kernel": "trpl_forward_kernel<4,std>", "kernel_ms": k_ms,
@@ -282,12 +298,17 @@ def run_ours(args):
             "hbm_gbs_if_all_traffic_were_dram": alg_bytes / (k_ms * 1e-3) / 1e9}
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier(device_ids=[local])
+            dist.destroy_process_group()
         return
+    if dist is not None:
+        dist.barrier(device_ids=[local])
     # ---- CPU baseline on the host cores (rank 0, N=1 semantics: a bounded sample) ----------
     cores = os.cpu_count() or 1
     n_cpu_sets = max(cores, min(args.cpu_sets, 6 * cores))
     cpu_states = states[:n_cpu_sets]
-    if args.no_cpu_baseline:
+    if args.no_cpu_baseline or world > 1:      # the CPU baseline is an N=1 figure
         cpu_val, cpu_dt, n_cpu_sets = None, 0.0, 0
     else:
         cpu_val, cpu_dt = cpu_throughput(cpu_states, ini, t, vals, uncs, cores)
@@ -315,9 +336,12 @@ def run_ours(args):
                   "mean_rejected": float(nsteps[..., 1].mean()),
                   "frac_floored": float(np.mean((status & 8) != 0)),
                   "frac_failed": float(np.mean((status & 7) != 0)),
-                  "kernel_ms_each": [float(x) for x in kernel_ms]},
+                  "kernel_ms_each": [float(x) for x in kernel_ms],
+                  "per_rank_[step_ms,kernel_ms,integrator_steps]": per_rank},
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def run_reference(args):
