@@ -79,39 +79,34 @@ TRPL_FN V2 add_mv(const V2& r, const Blk& m, const V2& v) {
   V2 o; o.x = fmadd(m.a01, v.y, fmadd(m.a00, v.x, r.x)); o.y = fmadd(m.a11, v.y, fmadd(m.a10, v.x, r.y)); return o;
 }
 
-// shared-memory slot map of one factorisation (per lane; every entry is one double slot).
-// Structural zeros are not stored: super-diagonal blocks have a01 == 0 (dN_i/dt does not see
-// Q_{i+2}), sub-diagonal blocks have a10 == 0 (dQ_{i+1}/dt does not see N_{i-1}).
+// Shared-memory map of one factorisation, in PAIRS (16 bytes per lane each).  A 2x2 block is two
+// pairs {a00,a01},{a10,a11}; triangular blocks (super-diagonal blocks have a01 == 0: dN_i/dt does
+// not see Q_{i+2}; sub-diagonal blocks have a10 == 0: dQ_{i+1}/dt does not see N_{i-1}) are stored
+// as full blocks so that every access stays a 128-bit one.
 template <int NPL>
 struct FacSlots {
   static constexpr int NI = NPL - 1;                 // interior rows per lane
-  static constexpr int DINV = 0;                     // NI full blocks
-  static constexpr int LMUL = DINV + 4 * NI;         // NI-1 full blocks (rows 1..NI-1)
-  static constexpr int CSUP = LMUL + 4 * (NI > 0 ? NI - 1 : 0);   // NI lower-triangular blocks (3 entries)
-  static constexpr int VSPK = CSUP + 3 * NI;         // NI full blocks
-  static constexpr int WSPK = VSPK + 4 * NI;         // NI full blocks
-  static constexpr int AZ = WSPK + 4 * NI;           // upper-triangular (3 entries)
-  static constexpr int CZ = AZ + 3;                  // lower-triangular (3 entries)
-  static constexpr int COUNT = CZ + 3;
+  static constexpr int DINV = 0;                     // NI blocks
+  static constexpr int LMUL = DINV + 2 * NI;         // NI-1 blocks (rows 1..NI-1)
+  static constexpr int CSUP = LMUL + 2 * (NI > 0 ? NI - 1 : 0);   // NI blocks
+  static constexpr int VSPK = CSUP + 2 * NI;         // NI blocks
+  static constexpr int WSPK = VSPK + 2 * NI;         // NI blocks
+  static constexpr int AZ = WSPK + 2 * NI;           // 1 block
+  static constexpr int CZ = AZ + 2;                  // 1 block
+  static constexpr int COUNT = CZ + 2;               // pairs
 };
 
-TRPL_FN void st_blk(LaneMem& sm, int slot, const Blk& b) {
-  sm.st(slot, b.a00); sm.st(slot + 1, b.a01); sm.st(slot + 2, b.a10); sm.st(slot + 3, b.a11);
+TRPL_FN void st_blk(LaneMem& sm, int p, const Blk& b) { sm.st2(p, b.a00, b.a01); sm.st2(p + 1, b.a10, b.a11); }
+TRPL_FN Blk ld_blk(const LaneMem& sm, int p) { Blk b; sm.ld2(p, b.a00, b.a01); sm.ld2(p + 1, b.a10, b.a11); return b; }
+TRPL_FN Blk ld_blk_from(const LaneMem& sm, int p, const ivec& src) {
+  Blk b; sm.ld2_from(p, src, b.a00, b.a01); sm.ld2_from(p + 1, src, b.a10, b.a11); return b;
 }
-TRPL_FN Blk ld_blk(const LaneMem& sm, int slot) {
-  Blk b; b.a00 = sm.ld(slot); b.a01 = sm.ld(slot + 1); b.a10 = sm.ld(slot + 2); b.a11 = sm.ld(slot + 3); return b;
-}
-// triangular blocks: {a00, off-diagonal, a11}
-struct Tri { real a00, off, a11; };
-TRPL_FN void st_lower(LaneMem& sm, int slot, const Blk& b) { sm.st(slot, b.a00); sm.st(slot + 1, b.a10); sm.st(slot + 2, b.a11); }
-TRPL_FN void st_upper(LaneMem& sm, int slot, const Blk& b) { sm.st(slot, b.a00); sm.st(slot + 1, b.a01); sm.st(slot + 2, b.a11); }
-TRPL_FN Tri ld_tri(const LaneMem& sm, int slot) { Tri t; t.a00 = sm.ld(slot); t.off = sm.ld(slot + 1); t.a11 = sm.ld(slot + 2); return t; }
 // r - M v for M lower triangular (a01 == 0) / upper triangular (a10 == 0)
-TRPL_FN V2 sub_mv_lower(const V2& r, const Tri& m, const V2& v) {
-  V2 o; o.x = fmadd(-m.a00, v.x, r.x); o.y = fmadd(-m.a11, v.y, fmadd(-m.off, v.x, r.y)); return o;
+TRPL_FN V2 sub_mv_lower(const V2& r, const Blk& m, const V2& v) {
+  V2 o; o.x = fmadd(-m.a00, v.x, r.x); o.y = fmadd(-m.a11, v.y, fmadd(-m.a10, v.x, r.y)); return o;
 }
-TRPL_FN V2 sub_mv_upper(const V2& r, const Tri& m, const V2& v) {
-  V2 o; o.x = fmadd(-m.off, v.y, fmadd(-m.a00, v.x, r.x)); o.y = fmadd(-m.a11, v.y, r.y); return o;
+TRPL_FN V2 sub_mv_upper(const V2& r, const Blk& m, const V2& v) {
+  V2 o; o.x = fmadd(-m.a01, v.y, fmadd(-m.a00, v.x, r.x)); o.y = fmadd(-m.a11, v.y, r.y); return o;
 }
 
 // register-resident part of the factorisation (PCR multipliers of the reduced system)
@@ -120,7 +115,8 @@ struct PcrFac {
   Blk binv;
 };
 
-// Factorise W given by (A, B, C) blocks of this lane's rows.  `base` is the first slot to use.
+// Factorise W given by (A, B, C) blocks of this lane's rows.  `base` is the first pair to use,
+// `xch` 12 scratch pairs for the lane exchange.
 template <int NPL>
 TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[NPL], LaneMem& sm,
                        int base, int xch, PcrFac& pf) {
@@ -136,53 +132,46 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
     }
     // spikes: T V = [A_0; 0; ...], T W = [...; 0; C_{NI-1}]
     Blk v[NI > 0 ? NI : 1], w[NI > 0 ? NI : 1];
-    // forward sweep
     v[0] = A[0];
-    TRPL_UNROLL for (int j = 1; j < NI; ++j) v[j] = blk_neg(blk_mul(lm[j], v[j - 1]));
-    // backward sweep
+    TRPL_UNROLL for (int j = 1; j < NI; ++j) v[j] = blk_mul_neg(lm[j], v[j - 1]);
     v[NI - 1] = blk_mul(dinv[NI - 1], v[NI - 1]);
     w[NI - 1] = blk_mul(dinv[NI - 1], C[NI - 1]);
     TRPL_UNROLL for (int j = NI - 2; j >= 0; --j) {
       v[j] = blk_mul(dinv[j], blk_sub(v[j], blk_mul(C[j], v[j + 1])));
-      w[j] = blk_neg(blk_mul(dinv[j], blk_mul(C[j], w[j + 1])));
+      w[j] = blk_mul_neg(dinv[j], blk_mul(C[j], w[j + 1]));
     }
     TRPL_UNROLL for (int j = 0; j < NI; ++j) {
-      st_blk(sm, base + S::DINV + 4 * j, dinv[j]);
-      if (j > 0) st_blk(sm, base + S::LMUL + 4 * (j - 1), lm[j]);
-      st_lower(sm, base + S::CSUP + 3 * j, C[j]);
-      st_blk(sm, base + S::VSPK + 4 * j, v[j]);
-      st_blk(sm, base + S::WSPK + 4 * j, w[j]);
+      st_blk(sm, base + S::DINV + 2 * j, dinv[j]);
+      if (j > 0) st_blk(sm, base + S::LMUL + 2 * (j - 1), lm[j]);
+      st_blk(sm, base + S::CSUP + 2 * j, C[j]);
+      st_blk(sm, base + S::VSPK + 2 * j, v[j]);
+      st_blk(sm, base + S::WSPK + 2 * j, w[j]);
     }
-    st_upper(sm, base + S::AZ, A[NPL - 1]);
-    st_lower(sm, base + S::CZ, C[NPL - 1]);
+    st_blk(sm, base + S::AZ, A[NPL - 1]);
+    st_blk(sm, base + S::CZ, C[NPL - 1]);
     // reduced (interface) row of this lane
     const Blk v0n = blk_shfl_down(v[0], 1);
     const Blk w0n = blk_shfl_down(w[0], 1);
-    ra = blk_neg(blk_mul(A[NPL - 1], v[NI - 1]));
+    ra = blk_mul_neg(A[NPL - 1], v[NI - 1]);
     rb = blk_sub(blk_sub(B[NPL - 1], blk_mul(A[NPL - 1], w[NI - 1])), blk_mul(C[NPL - 1], v0n));
-    rc = blk_neg(blk_mul(C[NPL - 1], w0n));
+    rc = blk_mul_neg(C[NPL - 1], w0n);
   } else {
     ra = A[0]; rb = B[0]; rc = C[0];
   }
   // Parallel cyclic reduction on (ra, rb, rc) across the 32 lanes.  Neighbour rows travel through
-  // 2 x 12 scratch slots (double buffered, one warp_sync per level) instead of 24 64-bit shuffles.
+  // 2 x 6 scratch pairs (double buffered, one warp_sync per level) instead of 24 64-bit shuffles.
   // No masking at the ends: ra is an exact zero block on lanes < stride and rc on lanes >= 32 -
   // stride (they are products with the zero sub/super-diagonal of the first/last row), and
   // out-of-range reads are clamped to the lane's own (finite) row.
   TRPL_UNROLL for (int k = 0; k < 5; ++k) {
     const int s = 1 << k;
-    const int xb = xch + 12 * (k & 1);
+    const int xb = xch + 6 * (k & 1);
     const Blk bi = blk_inv(rb);
-    st_blk(sm, xb, bi); st_blk(sm, xb + 4, ra); st_blk(sm, xb + 8, rc);
+    st_blk(sm, xb, bi); st_blk(sm, xb + 2, ra); st_blk(sm, xb + 4, rc);
     warp_sync();
     const ivec up = lane_minus(s), dn = lane_plus(s);
-    Blk bi_up, ra_up, rc_up, bi_dn, ra_dn, rc_dn;
-    bi_up.a00 = sm.ld_from(xb + 0, up); bi_up.a01 = sm.ld_from(xb + 1, up); bi_up.a10 = sm.ld_from(xb + 2, up); bi_up.a11 = sm.ld_from(xb + 3, up);
-    ra_up.a00 = sm.ld_from(xb + 4, up); ra_up.a01 = sm.ld_from(xb + 5, up); ra_up.a10 = sm.ld_from(xb + 6, up); ra_up.a11 = sm.ld_from(xb + 7, up);
-    rc_up.a00 = sm.ld_from(xb + 8, up); rc_up.a01 = sm.ld_from(xb + 9, up); rc_up.a10 = sm.ld_from(xb + 10, up); rc_up.a11 = sm.ld_from(xb + 11, up);
-    bi_dn.a00 = sm.ld_from(xb + 0, dn); bi_dn.a01 = sm.ld_from(xb + 1, dn); bi_dn.a10 = sm.ld_from(xb + 2, dn); bi_dn.a11 = sm.ld_from(xb + 3, dn);
-    ra_dn.a00 = sm.ld_from(xb + 4, dn); ra_dn.a01 = sm.ld_from(xb + 5, dn); ra_dn.a10 = sm.ld_from(xb + 6, dn); ra_dn.a11 = sm.ld_from(xb + 7, dn);
-    rc_dn.a00 = sm.ld_from(xb + 8, dn); rc_dn.a01 = sm.ld_from(xb + 9, dn); rc_dn.a10 = sm.ld_from(xb + 10, dn); rc_dn.a11 = sm.ld_from(xb + 11, dn);
+    const Blk bi_up = ld_blk_from(sm, xb, up), ra_up = ld_blk_from(sm, xb + 2, up), rc_up = ld_blk_from(sm, xb + 4, up);
+    const Blk bi_dn = ld_blk_from(sm, xb, dn), ra_dn = ld_blk_from(sm, xb + 2, dn), rc_dn = ld_blk_from(sm, xb + 4, dn);
     const Blk alpha = blk_mul_neg(ra, bi_up);     // -(ra * bi_up)
     const Blk gamma = blk_mul_neg(rc, bi_dn);
     rb = blk_fma(gamma, ra_dn, blk_fma(alpha, rc_up, rb));
@@ -195,7 +184,7 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
   warp_sync();
 }
 
-// Solve W x = r in place.  r[j] / x[j] are this lane's NPL block rows.
+// Solve W x = r in place.  r[j] / x[j] are this lane's NPL block rows; `xch` = 2 scratch pairs.
 template <int NPL>
 TRPL_FN void bt_solve(V2 (&r)[NPL], LaneMem& sm, int base, int xch, const PcrFac& pf) {
   typedef FacSlots<NPL> S;
@@ -203,39 +192,42 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], LaneMem& sm, int base, int xch, const PcrFac
   V2 g[NI > 0 ? NI : 1];
   V2 rr;
   if constexpr (NI > 0) {
-    // interior forward / backward sweep
-    g[0] = r[0];
-    TRPL_UNROLL for (int j = 1; j < NI; ++j) g[j] = sub_mv(r[j], ld_blk(sm, base + S::LMUL + 4 * (j - 1)), g[j - 1]);
-    g[NI - 1] = blk_mv(ld_blk(sm, base + S::DINV + 4 * (NI - 1)), g[NI - 1]);
-    TRPL_UNROLL for (int j = NI - 2; j >= 0; --j) {
-      const V2 t = sub_mv_lower(g[j], ld_tri(sm, base + S::CSUP + 3 * j), g[j + 1]);
-      g[j] = blk_mv(ld_blk(sm, base + S::DINV + 4 * j), t);
+    // every factor block of the interior sweep is fetched up front (independent of r)
+    Blk dinv[NI], csup[NI], lm[NI > 1 ? NI - 1 : 1];
+    TRPL_UNROLL for (int j = 0; j < NI; ++j) {
+      dinv[j] = ld_blk(sm, base + S::DINV + 2 * j);
+      csup[j] = ld_blk(sm, base + S::CSUP + 2 * j);
+      if (j > 0) lm[j - 1] = ld_blk(sm, base + S::LMUL + 2 * (j - 1));
     }
+    const Blk az = ld_blk(sm, base + S::AZ), cz = ld_blk(sm, base + S::CZ);
+    g[0] = r[0];
+    TRPL_UNROLL for (int j = 1; j < NI; ++j) g[j] = sub_mv(r[j], lm[j - 1], g[j - 1]);
+    g[NI - 1] = blk_mv(dinv[NI - 1], g[NI - 1]);
+    TRPL_UNROLL for (int j = NI - 2; j >= 0; --j) g[j] = blk_mv(dinv[j], sub_mv_lower(g[j], csup[j], g[j + 1]));
     V2 g0n; g0n.x = shfl_down(g[0].x, 1); g0n.y = shfl_down(g[0].y, 1);
-    rr = sub_mv_upper(r[NPL - 1], ld_tri(sm, base + S::AZ), g[NI - 1]);
-    rr = sub_mv_lower(rr, ld_tri(sm, base + S::CZ), g0n);      // CZ is zero on the last lane
+    rr = sub_mv_upper(r[NPL - 1], az, g[NI - 1]);
+    rr = sub_mv_lower(rr, cz, g0n);                          // cz is zero on the last lane
   } else {
     rr = r[0];
   }
   TRPL_UNROLL for (int k = 0; k < 5; ++k) {
     const int s = 1 << k;
-    const int xb = xch + 2 * (k & 1);
-    sm.st(xb, rr.x); sm.st(xb + 1, rr.y);
+    const int xb = xch + (k & 1);
+    sm.st2(xb, rr.x, rr.y);
     warp_sync();
-    const ivec lu = lane_minus(s), ld = lane_plus(s);
     V2 up, dn;
-    up.x = sm.ld_from(xb, lu); up.y = sm.ld_from(xb + 1, lu);
-    dn.x = sm.ld_from(xb, ld); dn.y = sm.ld_from(xb + 1, ld);
-    rr = add_mv(add_mv(rr, pf.al[k], up), pf.ga[k], dn);  // multipliers are exact zeros where no neighbour
+    sm.ld2_from(xb, lane_minus(s), up.x, up.y);
+    sm.ld2_from(xb, lane_plus(s), dn.x, dn.y);
+    rr = add_mv(add_mv(rr, pf.al[k], up), pf.ga[k], dn);     // multipliers are exact zeros where no neighbour
   }
   const V2 z = blk_mv(pf.binv, rr);
   r[NPL - 1] = z;
   if constexpr (NI > 0) {
+    // spike blocks first, then the arithmetic
+    Blk vs[NI], ws[NI];
+    TRPL_UNROLL for (int j = 0; j < NI; ++j) { vs[j] = ld_blk(sm, base + S::VSPK + 2 * j); ws[j] = ld_blk(sm, base + S::WSPK + 2 * j); }
     V2 zl; zl.x = shfl_up(z.x, 1); zl.y = shfl_up(z.y, 1);   // lane 0: V is zero there
-    TRPL_UNROLL for (int j = 0; j < NI; ++j) {
-      V2 x = sub_mv(g[j], ld_blk(sm, base + S::VSPK + 4 * j), zl);
-      r[j] = sub_mv(x, ld_blk(sm, base + S::WSPK + 4 * j), z);
-    }
+    TRPL_UNROLL for (int j = 0; j < NI; ++j) r[j] = sub_mv(sub_mv(g[j], vs[j], zl), ws[j], z);
   }
 }
 

@@ -97,13 +97,14 @@ TRPL_FN real to_real(ivec a) { return (double)a; }
 TRPL_FN ivec lane_minus(int d) { const int l = (int)(threadIdx.x & 31u); return l >= d ? l - d : l; }   // own lane if out of range
 TRPL_FN ivec lane_plus(int d) { const int l = (int)(threadIdx.x & 31u); return l + d < 32 ? l + d : l; }
 
-// per-warp scratch in shared memory, slot-major: slot s of lane l lives at base[s*32 + l]
+// Per-warp scratch in shared memory, pair-major: pair p of lane l is the 16-byte word
+// base[p*32 + l].  Every access is one 128-bit LDS/STS per lane, conflict-free across the warp.
 struct LaneMem {
-  double* base;
-  TRPL_FN real ld(int slot) const { return base[slot * 32 + (threadIdx.x & 31u)]; }
-  TRPL_FN void st(int slot, real v) const { base[slot * 32 + (threadIdx.x & 31u)] = v; }
-  // read another lane's slot (lane exchange through shared memory; caller orders with warp_sync)
-  TRPL_FN real ld_from(int slot, ivec src) const { return base[slot * 32 + src]; }
+  double2* base;
+  TRPL_FN void ld2(int p, real& a, real& b) const { const double2 v = base[p * 32 + (threadIdx.x & 31u)]; a = v.x; b = v.y; }
+  TRPL_FN void st2(int p, real a, real b) const { base[p * 32 + (threadIdx.x & 31u)] = make_double2(a, b); }
+  // read another lane's pair (lane exchange through shared memory; caller orders with warp_sync)
+  TRPL_FN void ld2_from(int p, ivec src, real& a, real& b) const { const double2 v = base[p * 32 + src]; a = v.x; b = v.y; }
 };
 TRPL_FN void warp_sync() { __syncwarp(); }
 }  // namespace simt
@@ -208,11 +209,13 @@ inline ivec to_int_floor(const real& x) { ivec r; for (int i = 0; i < 32; ++i) r
 inline real to_real(const ivec& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (double)a.v[i]; return r; }
 
 struct LaneMem {
-  std::vector<real> slots;
-  explicit LaneMem(int n) : slots(n) {}
-  real ld(int slot) const { return slots[slot]; }
-  void st(int slot, const real& v) { slots[slot] = v; }
-  real ld_from(int slot, const ivec& src) const { real r; for (int i = 0; i < 32; ++i) r.v[i] = slots[slot].v[src.v[i]]; return r; }
+  std::vector<real> slots;     // 2 per pair
+  explicit LaneMem(int n_pairs) : slots(2 * n_pairs) {}
+  void ld2(int p, real& a, real& b) const { a = slots[2 * p]; b = slots[2 * p + 1]; }
+  void st2(int p, const real& a, const real& b) { slots[2 * p] = a; slots[2 * p + 1] = b; }
+  void ld2_from(int p, const ivec& src, real& a, real& b) const {
+    for (int i = 0; i < 32; ++i) { a.v[i] = slots[2 * p].v[src.v[i]]; b.v[i] = slots[2 * p + 1].v[src.v[i]]; }
+  }
 };
 inline void warp_sync() {}
 }  // namespace simt

@@ -94,6 +94,12 @@ struct TrajIn {
   double s2T[3];         // model_uncertainty^2 * T for up to three temperatures
   double fl_mult, al_mult;
   double* curve;         // optional [n_t] simulated signal in measurement units
+  bool post_pass;        // likelihood is taken in finalize_trajectory (min_y floor, IRF, ladder)
+};
+
+// Everything only the final pass needs.  Built AFTER the integration loop so that none of it is
+// live (and spilled) across the hot loop.
+struct TailIn {
   IrfDesc irf;           // irf.nk == 0: no convolution
   // tempering ladder (OPT_LADDER): likelihood at every ladder temperature; s2T[1] holds sigma^2
   const double* ladder_T;
@@ -103,28 +109,56 @@ struct TrajIn {
   double* u2_scratch;    // [n_t] per-warp
 };
 
+// what the integration loop hands to the final pass
+struct TrajMid {
+  double l[3];           // streaming likelihood sums (valid when !post_pass)
+  double n_neg;
+};
+
 struct TrajOut {
   double logll[3];
   int status, n_acc, n_rej;
 };
 
-// shared-memory slot budget of one warp
+// shared-memory budget of one warp, in PAIRS (16 bytes per lane)
 template <int NPL, int MODEL>
 struct Slots {
-  static constexpr int NC = (MODEL == MODEL_TRAPS) ? 3 : 2;   // unknowns per node
-  static constexpr int KSTRIDE = NC * NPL;
-  static constexpr int KBASE = 0;
   static constexpr int NKS = 5;                                // stages kept (the 6th is consumed in registers)
-  static constexpr int F0 = KBASE + NKS * KSTRIDE;             // f(u) of the current step (for retries)
-  static constexpr int FAC = F0 + KSTRIDE;
-  static constexpr int TRAP = FAC + FacSlots<NPL>::COUNT;      // traps: 5 condensation coefficients per node
-  // lane-exchange scratch: 4 slots for the solve; the factorisation needs 24 and borrows the K
+  static constexpr int TPAIRS = (MODEL == MODEL_TRAPS) ? (NPL + 1) / 2 : 0;   // trap component, two nodes per pair
+  static constexpr int KSTRIDE = NPL + TPAIRS;                 // pairs per stage: (K_N, K_Q) per node [+ K_T]
+  static constexpr int KBASE = 0;
+  static constexpr int FAC = KBASE + NKS * KSTRIDE;
+  static constexpr int TRAP = FAC + FacSlots<NPL>::COUNT;      // traps: 5 condensation coefficients per node (3 pairs)
+  // lane-exchange scratch: 2 pairs for the solve; the factorisation needs 12 and borrows the K
   // region (dead at that point) when that is large enough, else it gets its own
-  static constexpr int XCH = TRAP + ((MODEL == MODEL_TRAPS) ? 5 * NPL : 0);
-  static constexpr int XCH_FACTOR = (NKS * KSTRIDE >= 24) ? KBASE : XCH;
-  static constexpr int COUNT = XCH + ((NKS * KSTRIDE >= 24) ? 4 : 24);
-  static constexpr int BYTES = COUNT * 32 * 8;
+  static constexpr int XCH = TRAP + ((MODEL == MODEL_TRAPS) ? 3 * NPL : 0);
+  static constexpr int XCH_FACTOR = (NKS * KSTRIDE >= 12) ? KBASE : XCH;
+  static constexpr int COUNT = XCH + ((NKS * KSTRIDE >= 12) ? 2 : 12);
+  static constexpr int BYTES = COUNT * 32 * 16;
 };
+
+// stage increment K_s <-> shared memory
+template <int NPL, int MODEL>
+TRPL_FN void store_k(LaneMem& sm, int kb, const Vec<NPL, MODEL>& k) {
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) sm.st2(kb + j, k.n[j], k.q[j]);
+  if (MODEL == MODEL_TRAPS) {
+    TRPL_UNROLL for (int j = 0; j < NPL; j += 2) sm.st2(kb + NPL + j / 2, k.t[j], (j + 1 < NPL) ? k.t[j + 1] : k.t[j]);
+  }
+}
+template <int NPL, int MODEL>
+TRPL_FN void load_k(const LaneMem& sm, int kb, Vec<NPL, MODEL>& k) {
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) sm.ld2(kb + j, k.n[j], k.q[j]);
+  if (MODEL == MODEL_TRAPS) {
+    TRPL_UNROLL for (int j = 0; j < NPL; j += 2) {
+      real a, b;
+      sm.ld2(kb + NPL + j / 2, a, b);
+      k.t[j] = a;
+      if (j + 1 < NPL) k.t[j + 1] = b;
+    }
+  } else {
+    k.t[0] = splat(0.0);
+  }
+}
 
 // ---- readout: signal and its time derivative, reduced over the warp --------------------------
 template <int NPL, int MODEL>
@@ -218,7 +252,8 @@ TRPL_FN real hermite_eval(const HermiteCoef& k, real tq) {
 enum Phase { PH_ACCEPTED = 0, PH_STAGE = 1, PH_RETRY = 2 };
 
 template <int NPL, int MODEL, bool FULL>
-TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm, TrajOut& out) {
+TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm, TrajOut& out,
+                            TrajMid& mid) {
   typedef Slots<NPL, MODEL> SL;
   typedef Vec<NPL, MODEL> V;
   const MeasDesc& md = *in.md;
@@ -230,8 +265,7 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   const int n_t = md.n_t;
   const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
   // min_y floor and IRF convolution need the whole curve: likelihood in a final pass over it
-  const bool ladder = want_ll && (opt.flags & OPT_LADDER) && in.ladder_n > 0 && in.r2_scratch;
-  const bool post = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || in.irf.nk > 0 || ladder);
+  const bool post = in.post_pass;
   const double min_y = md.min_y;
 
   // ---- initial condition (forward_solver.py:100-122) ----
@@ -310,7 +344,9 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
 
   for (;;) {
     V r;
-    if (phase != PH_RETRY) {
+    {
+      // PH_RETRY re-evaluates f(u) (us == u): rejections are rare (~0.5% of steps) and this keeps
+      // f(u) out of shared memory
       RhsAux<NPL> aux;
       rhs<NPL, MODEL>(c, m, us, r, aux);
       if (phase == PH_ACCEPTED) {
@@ -372,22 +408,10 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
         } else {
           h = h_new;
         }
-        // keep f(u) for a possible retry
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          sm.st(SL::F0 + SL::NC * j, r.n[j]); sm.st(SL::F0 + SL::NC * j + 1, r.q[j]);
-          if (MODEL == MODEL_TRAPS) sm.st(SL::F0 + SL::NC * j + 2, r.t[j]);
-        }
       }
     }
     if (phase != PH_STAGE) {
       // ---- start (or restart) a step from u with step size h; stage 1 right-hand side is f(u) ----
-      if (phase == PH_RETRY) {
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          r.n[j] = sm.ld(SL::F0 + SL::NC * j); r.q[j] = sm.ld(SL::F0 + SL::NC * j + 1);
-          if (MODEL == MODEL_TRAPS) r.t[j] = sm.ld(SL::F0 + SL::NC * j + 2);
-        }
-        if (MODEL != MODEL_TRAPS) r.t[0] = splat(0.0);
-      }
       if (n_acc + n_rej >= opt.max_steps) { status |= ST_MAX_STEPS; break; }
       if (opt.hmax > 0.0) h = fmin(h, opt.hmax);
       final_step = false;
@@ -412,11 +436,9 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
           TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
             const real idt = rcp(gi - jt.ft_t[j]);
             g_n[j] = jt.ft_n[j] * idt;              // K_T = idt * r_T + g_n * K_N
-            sm.st(SL::TRAP + 5 * j + 0, idt);
-            sm.st(SL::TRAP + 5 * j + 1, g_n[j]);
-            sm.st(SL::TRAP + 5 * j + 2, jt.fn_t[j]);
-            sm.st(SL::TRAP + 5 * j + 3, jt.fq_t[j]);
-            sm.st(SL::TRAP + 5 * j + 4, jt.fq_tn[j]);
+            sm.st2(SL::TRAP + 3 * j + 0, idt, g_n[j]);
+            sm.st2(SL::TRAP + 3 * j + 1, jt.fn_t[j], jt.fq_t[j]);
+            sm.st2(SL::TRAP + 3 * j + 2, jt.fq_tn[j], jt.fq_tn[j]);
           }
           const real gn_next = shfl_down(g_n[0], 1);
           TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
@@ -442,16 +464,22 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
     {
       V2 b[NPL];
       if (MODEL == MODEL_TRAPS) {
-        real w[NPL];
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) w[j] = sm.ld(SL::TRAP + 5 * j + 0) * r.t[j];   // idt * r_T
+        real w[NPL], gn[NPL], fnt[NPL], fqt[NPL], fqtn[NPL];
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+          real idt, dummy;
+          sm.ld2(SL::TRAP + 3 * j + 0, idt, gn[j]);
+          sm.ld2(SL::TRAP + 3 * j + 1, fnt[j], fqt[j]);
+          sm.ld2(SL::TRAP + 3 * j + 2, fqtn[j], dummy);
+          w[j] = idt * r.t[j];                                  // idt * r_T
+        }
         const real w_next = shfl_down(w[0], 1);
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
           const real wn = (j == NPL - 1) ? w_next : w[j + 1];
-          b[j].x = fmadd(sm.ld(SL::TRAP + 5 * j + 2), w[j], r.n[j]);
-          b[j].y = fmadd(sm.ld(SL::TRAP + 5 * j + 3), w[j], fmadd(sm.ld(SL::TRAP + 5 * j + 4), wn, r.q[j]));
+          b[j].x = fmadd(fnt[j], w[j], r.n[j]);
+          b[j].y = fmadd(fqt[j], w[j], fmadd(fqtn[j], wn, r.q[j]));
         }
         bt_solve<NPL>(b, sm, SL::FAC, SL::XCH, pf);
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) kk.t[j] = fmadd(sm.ld(SL::TRAP + 5 * j + 1), b[j].x, w[j]);
+        TRPL_UNROLL for (int j = 0; j < NPL; ++j) kk.t[j] = fmadd(gn[j], b[j].x, w[j]);
       } else {
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) { b[j].x = r.n[j]; b[j].y = r.q[j]; }
         bt_solve<NPL>(b, sm, SL::FAC, SL::XCH, pf);
@@ -461,11 +489,7 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
 
     if (s < 5) {
       // ---- keep K_s, build the next stage argument and c-combination ----
-      const int kb = SL::KBASE + s * SL::KSTRIDE;
-      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-        sm.st(kb + SL::NC * j, kk.n[j]); sm.st(kb + SL::NC * j + 1, kk.q[j]);
-        if (MODEL == MODEL_TRAPS) sm.st(kb + SL::NC * j + 2, kk.t[j]);
-      }
+      store_k<NPL, MODEL>(sm, SL::KBASE + s * SL::KSTRIDE, kk);
       ++s;
       // the newest increment is still in registers; older ones come back from shared memory
       {
@@ -478,15 +502,12 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       }
       for (int p = 0; p < s - 1; ++p) {
         const double a = RODAS4_A[s][p], cc = RODAS4_C[s][p] * ih;
-        const int pb = SL::KBASE + p * SL::KSTRIDE;
+        V kp;
+        load_k<NPL, MODEL>(sm, SL::KBASE + p * SL::KSTRIDE, kp);
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          const real kn = sm.ld(pb + SL::NC * j), kq = sm.ld(pb + SL::NC * j + 1);
-          us.n[j] = fmadd(a, kn, us.n[j]); us.q[j] = fmadd(a, kq, us.q[j]);
-          cs.n[j] = fmadd(cc, kn, cs.n[j]); cs.q[j] = fmadd(cc, kq, cs.q[j]);
-          if (MODEL == MODEL_TRAPS) {
-            const real kt = sm.ld(pb + SL::NC * j + 2);
-            us.t[j] = fmadd(a, kt, us.t[j]); cs.t[j] = fmadd(cc, kt, cs.t[j]);
-          }
+          us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
+          cs.n[j] = fmadd(cc, kp.n[j], cs.n[j]); cs.q[j] = fmadd(cc, kp.q[j], cs.q[j]);
+          if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kp.t[j], us.t[j]); cs.t[j] = fmadd(cc, kp.t[j], cs.t[j]); }
         }
       }
       phase = PH_STAGE;
@@ -543,6 +564,10 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       ++n_rej;
       last_rejected = true;
       h = nonfinite ? 0.1 * h : h_new;
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+        us.n[j] = u.n[j]; us.q[j] = u.q[j];
+        if (MODEL == MODEL_TRAPS) us.t[j] = u.t[j];
+      }
       phase = PH_RETRY;
     }
   }
@@ -554,27 +579,40 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
     io += 32;
   }
 
-  // ---- likelihood (trial_move_evaluation.py:117-166) ----
   out.status = status; out.n_acc = n_acc; out.n_rej = n_rej;
+  if (want_ll && !post) {
+    mid.l[0] = -uni(warp_sum(ll0)); mid.l[1] = -uni(warp_sum(ll1)); mid.l[2] = -uni(warp_sum(ll2));
+    mid.n_neg = uni(warp_sum(nneg));
+  } else {
+    mid.l[0] = mid.l[1] = mid.l[2] = 0.0; mid.n_neg = 0.0;
+  }
+}
+
+// ---- likelihood (trial_move_evaluation.py:117-166): streaming sums, or a pass over the curve ----
+TRPL_FN void finalize_trajectory(const TrajIn& in, const TailIn& tl, const SolverOpts& opt,
+                                 const TrajMid& mid, TrajOut& out) {
+  const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
+  const int n_t = in.md->n_t;
   if (want_ll) {
     double l[3];
     double n_neg;
     int n_c = n_t;
     bool ok = true;
-    if (post) {
+    const bool ladder = in.post_pass && (opt.flags & OPT_LADDER) && tl.ladder_n > 0 && tl.r2_scratch;
+    if (in.post_pass) {
       warp_sync();
       const double* sol = in.curve;
-      if (in.irf.nk > 0) {
-        ok = irf_convolve_trim(in.times, in.curve, n_t, in.irf, n_c);
-        sol = in.irf.trim;
+      if (tl.irf.nk > 0) {
+        ok = irf_convolve_trim(in.times, in.curve, n_t, tl.irf, n_c);
+        sol = tl.irf.trim;
         if (!ok) out.status |= ST_CONV_FAIL;
       }
       if (ok) array_loglik(sol, n_c, in.vals, in.uncs, in.scale_shift, in.s2T,
                            (opt.flags & OPT_FORCE_MIN_Y) != 0, l, n_neg,
-                           ladder ? in.r2_scratch : nullptr, ladder ? in.u2_scratch : nullptr);
+                           ladder ? tl.r2_scratch : nullptr, ladder ? tl.u2_scratch : nullptr);
     } else {
-      l[0] = -uni(warp_sum(ll0)); l[1] = -uni(warp_sum(ll1)); l[2] = -uni(warp_sum(ll2));
-      n_neg = uni(warp_sum(nneg));
+      l[0] = mid.l[0]; l[1] = mid.l[1]; l[2] = mid.l[2];
+      n_neg = mid.n_neg;
     }
     const double ninf = -HUGE_VAL;
     if (!ok) {
@@ -588,8 +626,8 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
     out.logll[0] = l[0]; out.logll[1] = l[1]; out.logll[2] = l[2];
     if (ladder) {
       const bool failed = !ok || !(n_neg < 0.2 * n_c);
-      ladder_loglik(in.r2_scratch, in.u2_scratch, failed ? 0 : n_c, in.s2T[1], in.ladder_T, in.ladder_n,
-                    in.ladder_out, failed);
+      ladder_loglik(tl.r2_scratch, tl.u2_scratch, failed ? 0 : n_c, in.s2T[1], tl.ladder_T, tl.ladder_n,
+                    tl.ladder_out, failed);
     }
   } else {
     out.logll[0] = out.logll[1] = out.logll[2] = 0.0;

@@ -50,10 +50,10 @@ struct KernelArgs {
 
 template <int NPL, int MODEL, bool FULL>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(const KernelArgs a) {
-  extern __shared__ double smem[];
+  extern __shared__ double2 smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  LaneMem sm{smem + warp * (Slots<NPL, MODEL>::COUNT * 32)};
+  LaneMem sm{smem + warp * (Slots<NPL, MODEL>::COUNT * 32)};   // COUNT pairs of 16 B per lane
   for (;;) {
     int traj = 0;
     if (lane == 0) traj = atomicAdd(a.counter, 1);
@@ -74,19 +74,27 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
     in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
     in.curve = a.curves ? a.curves + (size_t)set * a.n_times_total + md->t_off : nullptr;
-    in.irf.nk = (a.irf_mom && a.scratch) ? md->irf_nk : 0;
-    in.irf.dt = md->irf_dt;
-    in.irf.mom = a.irf_mom ? a.irf_mom + 3 * (size_t)md->irf_off : nullptr;
-    {
-      double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * a.warps_per_cta + warp) * a.scratch_stride : nullptr;
-      in.irf.ry = ws; in.irf.hk = ws ? ws + a.off_hk : nullptr; in.irf.trim = ws ? ws + a.off_trim : nullptr;
-      in.r2_scratch = (ws && a.n_ladder > 0) ? ws + a.off_r2 : nullptr;
-      in.u2_scratch = (ws && a.n_ladder > 0) ? ws + a.off_u2 : nullptr;
-    }
-    in.ladder_T = a.ladder_T; in.ladder_n = a.n_ladder;
-    in.ladder_out = a.ladder_out ? a.ladder_out + (size_t)traj * a.n_ladder : nullptr;
+    const bool want_ll = !(a.opt.flags & OPT_NO_LIKELIHOOD);
+    const bool conv = a.irf_mom && a.scratch && md->irf_nk > 0;
+    const bool ladder = (a.opt.flags & OPT_LADDER) && a.n_ladder > 0 && a.scratch;
+    in.post_pass = want_ll && in.curve && ((a.opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
     TrajOut out;
-    run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out);
+    TrajMid mid;
+    run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out, mid);
+    {
+      // tail-only addresses are formed here, after the loop, from the (constant-bank) launch arguments
+      TailIn tl;
+      tl.irf.nk = conv ? md->irf_nk : 0;
+      tl.irf.dt = md->irf_dt;
+      tl.irf.mom = a.irf_mom ? a.irf_mom + 3 * (size_t)md->irf_off : nullptr;
+      double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * a.warps_per_cta + warp) * a.scratch_stride : nullptr;
+      tl.irf.ry = ws; tl.irf.hk = ws ? ws + a.off_hk : nullptr; tl.irf.trim = ws ? ws + a.off_trim : nullptr;
+      tl.r2_scratch = (ws && ladder) ? ws + a.off_r2 : nullptr;
+      tl.u2_scratch = (ws && ladder) ? ws + a.off_u2 : nullptr;
+      tl.ladder_T = a.ladder_T; tl.ladder_n = a.n_ladder;
+      tl.ladder_out = a.ladder_out ? a.ladder_out + (size_t)traj * a.n_ladder : nullptr;
+      finalize_trajectory(in, tl, a.opt, mid, out);
+    }
     if (lane == 0) {
       a.logll[3 * (size_t)traj + 0] = out.logll[0];
       a.logll[3 * (size_t)traj + 1] = out.logll[1];

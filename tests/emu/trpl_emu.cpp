@@ -36,22 +36,29 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
     in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
     in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
     in.curve = curves ? curves + (size_t)set * n_times_total + md->t_off : nullptr;
+    const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
+    const bool conv = irf_mom && md->irf_nk > 0;
+    const bool ladder = (opt.flags & OPT_LADDER) && n_ladder > 0;
+    in.post_pass = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
+    TrajOut out;
+    TrajMid mid;
+    run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out, mid);
     std::vector<double> ry, hk, trim;
-    in.irf.nk = irf_mom ? md->irf_nk : 0;
-    in.irf.dt = md->irf_dt;
-    in.irf.mom = irf_mom ? irf_mom + 3 * (size_t)md->irf_off : nullptr;
-    if (in.irf.nk > 0) {
+    TailIn tl;
+    tl.irf.nk = conv ? md->irf_nk : 0;
+    tl.irf.dt = md->irf_dt;
+    tl.irf.mom = irf_mom ? irf_mom + 3 * (size_t)md->irf_off : nullptr;
+    if (tl.irf.nk > 0) {
       const double tend = in.times[md->n_t - 1];
       const size_t n_rs = (size_t)ceil((tend + md->irf_dt / 4) / (md->irf_dt / 2));
       ry.resize(n_rs + 4); hk.resize(n_rs / 2 + 4); trim.resize(md->n_t + 4);
     }
-    in.irf.ry = ry.data(); in.irf.hk = hk.data(); in.irf.trim = trim.data();
+    tl.irf.ry = ry.data(); tl.irf.hk = hk.data(); tl.irf.trim = trim.data();
     std::vector<double> r2(md->n_t + 4), u2(md->n_t + 4);
-    in.r2_scratch = n_ladder > 0 ? r2.data() : nullptr; in.u2_scratch = n_ladder > 0 ? u2.data() : nullptr;
-    in.ladder_T = ladder_T; in.ladder_n = n_ladder;
-    in.ladder_out = ladder_out ? ladder_out + (size_t)traj * n_ladder : nullptr;
-    TrajOut out;
-    run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out);
+    tl.r2_scratch = ladder ? r2.data() : nullptr; tl.u2_scratch = ladder ? u2.data() : nullptr;
+    tl.ladder_T = ladder_T; tl.ladder_n = n_ladder;
+    tl.ladder_out = ladder_out ? ladder_out + (size_t)traj * n_ladder : nullptr;
+    finalize_trajectory(in, tl, opt, mid, out);
     for (int k = 0; k < 3; ++k) logll[3 * (size_t)traj + k] = out.logll[k];
     status[traj] = out.status;
     if (nsteps) { nsteps[2 * traj] = out.n_acc; nsteps[2 * traj + 1] = out.n_rej; }
