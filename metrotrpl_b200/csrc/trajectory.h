@@ -514,19 +514,32 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       continue;
     }
 
-    // ---- stage 6 done: us is the embedded (3rd order) solution, u_new = us + K_6, error = K_6 ----
+    // ---- stage 6 done: u_new = u + sum_j m_j K_j, m = (a_6j, 1); the error estimate is K_6 ----
+    // (the stage argument `us` is rebuilt from the stored increments here so that it is not live
+    //  across the solves)
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+      us.n[j] = u.n[j] + kk.n[j]; us.q[j] = u.q[j] + kk.q[j];
+      if (MODEL == MODEL_TRAPS) us.t[j] = u.t[j] + kk.t[j];
+    }
+    TRPL_UNROLL for (int p = 0; p < 5; ++p) {
+      const double a = RODAS4_A[5][p];
+      V kp;
+      load_k<NPL, MODEL>(sm, SL::KBASE + p * SL::KSTRIDE, kp);
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+        us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
+        if (MODEL == MODEL_TRAPS) us.t[j] = fmadd(a, kp.t[j], us.t[j]);
+      }
+    }
     real esum = splat(0.0);
     mask bad = mconst(false);
     real pold[NPL];
     holes<NPL, MODEL>(c, m, u, pold);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      us.n[j] = us.n[j] + kk.n[j]; us.q[j] = us.q[j] + kk.q[j];
       const real iscn = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(us.n[j])), opt.atol));
       const real iscq = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(pold[j])), opt.atol));
       const real en = kk.n[j] * iscn, eq = kk.q[j] * iscq;
       real e2 = fmadd(en, en, eq * eq);
       if (MODEL == MODEL_TRAPS) {
-        us.t[j] = us.t[j] + kk.t[j];
         const real isct = rcp(fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(us.t[j]), vabs(u.n[j]))), opt.atol));
         const real et = kk.t[j] * isct;
         e2 = fmadd(et, et, e2);
