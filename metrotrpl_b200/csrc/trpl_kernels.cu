@@ -11,6 +11,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <cmath>
 
 #include "../../include/metrotrpl_b200.h"
 #include "trajectory.h"
@@ -44,6 +46,7 @@ struct KernelArgs {
   double* ladder_out;        // [n_traj][n_ladder]
   int n_ladder;
   int* counter;              // work queue head
+  const int* meas_order;     // [n_meas] measurement indices, most expensive first
   int n_traj, n_meas, n_times_total, warps_per_cta;
   SolverOpts opt;
 };
@@ -59,8 +62,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     if (lane == 0) traj = atomicAdd(a.counter, 1);
     traj = __shfl_sync(0xffffffffu, traj, 0);
     if (traj >= a.n_traj) break;
-    const int set = traj / a.n_meas;
-    const int mi = traj - set * a.n_meas;
+    // queue order is measurement-major with the (statically) most expensive curves first, so that
+    // the tail of the launch is made of the cheapest trajectories; results are indexed [set][meas]
+    const int n_sets_q = a.n_traj / a.n_meas;
+    const int qm = traj / n_sets_q;
+    const int set = traj - qm * n_sets_q;
+    const int mi = a.meas_order[qm];
+    traj = set * a.n_meas + mi;
     const MeasDesc* md = a.meas + mi;
     TrajIn in;
     in.par = a.params + (size_t)set * TRPL_NPARAM;
@@ -161,7 +169,7 @@ struct trpl_handle {
   size_t max_nrs = 0, max_nt = 0;
   int irf_rows_needed = 0;
   DevBuf<double> d_params, d_aux, d_logll, d_curves;
-  DevBuf<int> d_status, d_nsteps, d_counter;
+  DevBuf<int> d_status, d_nsteps, d_counter, d_order;
   int n_sets = 0;
   bool curves_valid = false;
   float last_ms = 0.f;
@@ -319,6 +327,22 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
     CU(cudaMemcpyAsync(h->d_profiles.p, profiles, sizeof(double) * n_profile_total, cudaMemcpyHostToDevice, h->stream));
   }
   CU(cudaStreamSynchronize(h->stream));
+  {
+    // static cost proxy: thicker films and stronger excitation take more integrator steps
+    std::vector<std::pair<double, int>> cost(n_meas);
+    for (int i = 0; i < n_meas; ++i) {
+      const trpl_meas_desc& m = meas[i];
+      double amp = m.ini_a;
+      if (m.ini_mode == TRPL_INI_DENSITY) { amp = 0; for (int x = 0; x < m.nx; ++x) amp = std::max(amp, profiles[m.prof_off + x]); }
+      cost[i] = {-(m.thickness * (double)m.n_t * (1.0 + 0.05 * log10(std::max(amp, 1.0)))), i};
+    }
+    std::sort(cost.begin(), cost.end());
+    std::vector<int> order(n_meas);
+    for (int i = 0; i < n_meas; ++i) order[i] = cost[i].second;
+    CU(h->d_order.reserve(n_meas));
+    CU(cudaMemcpyAsync(h->d_order.p, order.data(), sizeof(int) * n_meas, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   h->any_irf = false; h->have_irf = false; h->max_nrs = 0; h->max_nt = 0; h->irf_rows_needed = 0;
   for (int i = 0; i < n_meas; ++i) {
     const trpl_meas_desc& m = meas[i];
@@ -432,6 +456,7 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
     h->ladder_valid = true;
   }
   a.counter = h->d_counter.p;
+  a.meas_order = h->d_order.p;
   a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;
   memcpy(&a.opt, opts, sizeof(SolverOpts));
   if (h->model == TRPL_MODEL_STD) return launch_npl<MODEL_STD>(h, a);
