@@ -48,9 +48,11 @@ enum trpl_ini_mode { TRPL_INI_DENSITY = 0, TRPL_INI_FLUENCE = 1 };   /* forward_
 /* status bits per trajectory */
 enum trpl_status {
   TRPL_ST_OK = 0, TRPL_ST_MAX_STEPS = 1, TRPL_ST_H_UNDERFLOW = 2, TRPL_ST_NONFINITE = 4,
-  TRPL_ST_FLOORED = 8, TRPL_ST_NEG_FRAC = 16, TRPL_ST_NAN_LL = 32, TRPL_ST_CONV_FAIL = 64
+  TRPL_ST_FLOORED = 8, TRPL_ST_NEG_FRAC = 16, TRPL_ST_NAN_LL = 32, TRPL_ST_CONV_FAIL = 64,
+  TRPL_ST_EXPLICIT = 128 /* informational: non-stiff trajectory, integrated by the explicit RK path */
 };
-enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2, TRPL_OPT_LADDER = 4 };
+enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2, TRPL_OPT_LADDER = 4,
+                      TRPL_OPT_NO_EXPLICIT = 8 /* always use the Rosenbrock integrator */ };
 
 /* one measurement (sim_info["lengths"/"nx"/"meas_types"][i] + its slice of the data arrays) */
 typedef struct trpl_meas_desc {

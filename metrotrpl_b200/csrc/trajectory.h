@@ -53,10 +53,11 @@ enum StatusBits {
   ST_FLOORED = 8,       // signal fell below DBL_MIN and was floored (forward_solver.py:190-192)
   ST_NEG_FRAC = 16,     // too many negative values (trial_move_evaluation.py:117-123) -> -inf
   ST_NAN_LL = 32,       // likelihood was NaN -> -inf (trial_move_evaluation.py:159-165)
-  ST_CONV_FAIL = 64     // IRF convolution failed -> -inf (trial_move_evaluation.py:83-87, :103-106)
+  ST_CONV_FAIL = 64,    // IRF convolution failed -> -inf (trial_move_evaluation.py:83-87, :103-106)
+  ST_EXPLICIT = 128     // informational: integrated by the explicit Runge-Kutta path (explicit.h)
 };
 
-enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2, OPT_LADDER = 4 };
+enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2, OPT_LADDER = 4, OPT_NO_EXPLICIT = 8 };
 
 struct SolverOpts {
   double rtol, atol;
@@ -251,9 +252,14 @@ TRPL_FN real hermite_eval(const HermiteCoef& k, real tq) {
 //   PH_RETRY     step rejected: same u, same f(u) (kept in shared memory), new h
 enum Phase { PH_ACCEPTED = 0, PH_STAGE = 1, PH_RETRY = 2 };
 
+template <int NPL, int MODEL>
+TRPL_FN bool is_nonstiff(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u, double tend);   // explicit.h
+
+// Returns true (and does nothing else) when `allow_defer` is set and the trajectory is classified
+// non-stiff at t = 0: the caller hands it to the explicit Runge-Kutta path instead.
 template <int NPL, int MODEL, bool FULL>
-TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm, TrajOut& out,
-                            TrajMid& mid) {
+TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm, TrajOut& out,
+                            TrajMid& mid, bool allow_defer) {
   typedef Slots<NPL, MODEL> SL;
   typedef Vec<NPL, MODEL> V;
   const MeasDesc& md = *in.md;
@@ -301,9 +307,11 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) u.q[j] = sel(m.real_node[j], qloc[j] + excl, 0.0);
   }
 
+  const double tend = in.times[n_t - 1];
+  if (allow_defer && is_nonstiff<NPL, MODEL>(c, m, u, tend)) return true;
+
   // ---- bookkeeping ----
   double t = 0.0;
-  const double tend = in.times[n_t - 1];
   int io = 0;                       // next measurement index to emit
   int status = ST_OK, n_acc = 0, n_rej = 0;
   bool floored = false;
@@ -599,6 +607,7 @@ TRPL_FN void run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   } else {
     mid.l[0] = mid.l[1] = mid.l[2] = 0.0; mid.n_neg = 0.0;
   }
+  return false;
 }
 
 // ---- likelihood (trial_move_evaluation.py:117-166): streaming sums, or a pass over the curve ----

@@ -16,6 +16,7 @@
 
 #include "../../include/metrotrpl_b200.h"
 #include "trajectory.h"
+#include "explicit.h"
 
 namespace {
 
@@ -47,9 +48,60 @@ struct KernelArgs {
   int n_ladder;
   int* counter;              // work queue head
   const int* meas_order;     // [n_meas] measurement indices, most expensive first
+  int* defer_list;           // trajectories handed to the explicit path
+  int* defer_count;
   int n_traj, n_meas, n_times_total, warps_per_cta;
   SolverOpts opt;
 };
+
+__device__ __forceinline__ void setup_traj(const KernelArgs& a, int traj, TrajIn& in) {
+  const int set = traj / a.n_meas;
+  const int mi = traj - set * a.n_meas;
+  const MeasDesc* md = a.meas + mi;
+  in.par = a.params + (size_t)set * TRPL_NPARAM;
+  in.md = md;
+  in.times = a.times + md->t_off;
+  in.vals = a.vals ? a.vals + md->t_off : nullptr;
+  in.uncs = a.uncs ? a.uncs + md->t_off : nullptr;
+  in.profile = a.profiles ? a.profiles + md->prof_off : nullptr;
+  const double* ax = a.aux + (size_t)traj * TRPL_NAUX;
+  in.scale_shift = ax[TRPL_A_SCALE_SHIFT];
+  in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
+  in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
+  in.curve = a.curves ? a.curves + (size_t)set * a.n_times_total + md->t_off : nullptr;
+  const bool want_ll = !(a.opt.flags & OPT_NO_LIKELIHOOD);
+  const bool conv = a.irf_mom && a.scratch && md->irf_nk > 0;
+  const bool ladder = (a.opt.flags & OPT_LADDER) && a.n_ladder > 0 && a.scratch;
+  in.post_pass = want_ll && in.curve && ((a.opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
+}
+
+// tail-only addresses are formed after the loop from the (constant-bank) launch arguments
+__device__ __forceinline__ void finish_traj(const KernelArgs& a, int traj, int warp, const TrajIn& in,
+                                            const TrajMid& mid, TrajOut& out) {
+  const MeasDesc* md = in.md;
+  const bool conv = a.irf_mom && a.scratch && md->irf_nk > 0;
+  const bool ladder = (a.opt.flags & OPT_LADDER) && a.n_ladder > 0 && a.scratch;
+  TailIn tl;
+  tl.irf.nk = conv ? md->irf_nk : 0;
+  tl.irf.dt = md->irf_dt;
+  tl.irf.mom = a.irf_mom ? a.irf_mom + 3 * (size_t)md->irf_off : nullptr;
+  double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * a.warps_per_cta + warp) * a.scratch_stride : nullptr;
+  tl.irf.ry = ws; tl.irf.hk = ws ? ws + a.off_hk : nullptr; tl.irf.trim = ws ? ws + a.off_trim : nullptr;
+  tl.r2_scratch = (ws && ladder) ? ws + a.off_r2 : nullptr;
+  tl.u2_scratch = (ws && ladder) ? ws + a.off_u2 : nullptr;
+  tl.ladder_T = a.ladder_T; tl.ladder_n = a.n_ladder;
+  tl.ladder_out = a.ladder_out ? a.ladder_out + (size_t)traj * a.n_ladder : nullptr;
+  finalize_trajectory(in, tl, a.opt, mid, out);
+  if ((threadIdx.x & 31) == 0) {
+    a.logll[3 * (size_t)traj + 0] = out.logll[0];
+    a.logll[3 * (size_t)traj + 1] = out.logll[1];
+    a.logll[3 * (size_t)traj + 2] = out.logll[2];
+    a.status[traj] = out.status;
+    a.nsteps[2 * (size_t)traj + 0] = out.n_acc;
+    a.nsteps[2 * (size_t)traj + 1] = out.n_rej;
+  }
+  __syncwarp();
+}
 
 template <int NPL, int MODEL, bool FULL>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(const KernelArgs a) {
@@ -57,6 +109,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   LaneMem sm{smem + warp * (Slots<NPL, MODEL>::COUNT * 32)};   // COUNT pairs of 16 B per lane
+  const bool allow_defer = a.defer_list != nullptr;
   for (;;) {
     int traj = 0;
     if (lane == 0) traj = atomicAdd(a.counter, 1);
@@ -66,52 +119,40 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     // the tail of the launch is made of the cheapest trajectories; results are indexed [set][meas]
     const int n_sets_q = a.n_traj / a.n_meas;
     const int qm = traj / n_sets_q;
-    const int set = traj - qm * n_sets_q;
-    const int mi = a.meas_order[qm];
-    traj = set * a.n_meas + mi;
-    const MeasDesc* md = a.meas + mi;
+    traj = (traj - qm * n_sets_q) * a.n_meas + a.meas_order[qm];
     TrajIn in;
-    in.par = a.params + (size_t)set * TRPL_NPARAM;
-    in.md = md;
-    in.times = a.times + md->t_off;
-    in.vals = a.vals ? a.vals + md->t_off : nullptr;
-    in.uncs = a.uncs ? a.uncs + md->t_off : nullptr;
-    in.profile = a.profiles ? a.profiles + md->prof_off : nullptr;
-    const double* ax = a.aux + (size_t)traj * TRPL_NAUX;
-    in.scale_shift = ax[TRPL_A_SCALE_SHIFT];
-    in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
-    in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
-    in.curve = a.curves ? a.curves + (size_t)set * a.n_times_total + md->t_off : nullptr;
-    const bool want_ll = !(a.opt.flags & OPT_NO_LIKELIHOOD);
-    const bool conv = a.irf_mom && a.scratch && md->irf_nk > 0;
-    const bool ladder = (a.opt.flags & OPT_LADDER) && a.n_ladder > 0 && a.scratch;
-    in.post_pass = want_ll && in.curve && ((a.opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
+    setup_traj(a, traj, in);
     TrajOut out;
     TrajMid mid;
-    run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out, mid);
-    {
-      // tail-only addresses are formed here, after the loop, from the (constant-bank) launch arguments
-      TailIn tl;
-      tl.irf.nk = conv ? md->irf_nk : 0;
-      tl.irf.dt = md->irf_dt;
-      tl.irf.mom = a.irf_mom ? a.irf_mom + 3 * (size_t)md->irf_off : nullptr;
-      double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * a.warps_per_cta + warp) * a.scratch_stride : nullptr;
-      tl.irf.ry = ws; tl.irf.hk = ws ? ws + a.off_hk : nullptr; tl.irf.trim = ws ? ws + a.off_trim : nullptr;
-      tl.r2_scratch = (ws && ladder) ? ws + a.off_r2 : nullptr;
-      tl.u2_scratch = (ws && ladder) ? ws + a.off_u2 : nullptr;
-      tl.ladder_T = a.ladder_T; tl.ladder_n = a.n_ladder;
-      tl.ladder_out = a.ladder_out ? a.ladder_out + (size_t)traj * a.n_ladder : nullptr;
-      finalize_trajectory(in, tl, a.opt, mid, out);
+    if (run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out, mid, allow_defer)) {
+      if (lane == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = traj;     // non-stiff: explicit path
+      continue;
     }
-    if (lane == 0) {
-      a.logll[3 * (size_t)traj + 0] = out.logll[0];
-      a.logll[3 * (size_t)traj + 1] = out.logll[1];
-      a.logll[3 * (size_t)traj + 2] = out.logll[2];
-      a.status[traj] = out.status;
-      a.nsteps[2 * (size_t)traj + 0] = out.n_acc;
-      a.nsteps[2 * (size_t)traj + 1] = out.n_rej;
-    }
-    __syncwarp();
+    finish_traj(a, traj, warp, in, mid, out);
+  }
+}
+
+// second pass over the trajectories the first kernel classified non-stiff
+template <int NPL, int MODEL, bool FULL>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_explicit_kernel(const KernelArgs a) {
+  extern __shared__ double2 smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  LaneMem sm{smem + warp * (Slots<NPL, MODEL>::COUNT * 32)};
+  const int n = *a.defer_count;
+  for (;;) {
+    int q = 0;
+    if (lane == 0) q = atomicAdd(a.counter + 1, 1);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= n) break;
+    const int traj = a.defer_list[q];
+    TrajIn in;
+    setup_traj(a, traj, in);
+    TrajOut out;
+    TrajMid mid;
+    run_trajectory_explicit<NPL, MODEL, FULL>(in, a.opt, sm, out, mid);
+    out.status |= ST_EXPLICIT;
+    finish_traj(a, traj, warp, in, mid, out);
   }
 }
 
@@ -169,7 +210,7 @@ struct trpl_handle {
   size_t max_nrs = 0, max_nt = 0;
   int irf_rows_needed = 0;
   DevBuf<double> d_params, d_aux, d_logll, d_curves;
-  DevBuf<int> d_status, d_nsteps, d_counter, d_order;
+  DevBuf<int> d_status, d_nsteps, d_counter, d_order, d_defer;
   int n_sets = 0;
   bool curves_valid = false;
   float last_ms = 0.f;
@@ -202,12 +243,24 @@ int launch(trpl_handle* h, KernelArgs a) {
     CU(h->d_scratch.reserve((size_t)grid * wpc * a.scratch_stride));
     a.scratch = h->d_scratch.p;
   }
-  CU(cudaMemsetAsync(h->d_counter.p, 0, sizeof(int), h->stream));
+  CU(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(int), h->stream));
+  a.defer_list = nullptr; a.defer_count = h->d_counter.p + 2;
+  if (!(a.opt.flags & OPT_NO_EXPLICIT)) {
+    CU(h->d_defer.reserve(a.n_traj));
+    a.defer_list = h->d_defer.p;
+  }
   CU(cudaEventRecord(h->ev0, h->stream));
   kern<<<grid, 32 * wpc, smem, h->stream>>>(a);
   CU(cudaGetLastError());
-  CU(cudaEventRecord(h->ev1, h->stream));
   h->launches += 1;
+  if (a.defer_list) {
+    auto kern2 = trpl_explicit_kernel<NPL, MODEL, FULL>;
+    CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern2<<<grid, 32 * wpc, smem, h->stream>>>(a);
+    CU(cudaGetLastError());
+    h->launches += 1;
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
   return 0;
 }
 
@@ -249,7 +302,7 @@ int trpl_create(int device, trpl_handle** out) {
   CU(cudaEventCreate(&h->ev1));
   CU(cudaEventCreate(&h->tm0));
   CU(cudaEventCreate(&h->tm1));
-  CU(h->d_counter.reserve(1));
+  CU(h->d_counter.reserve(4));
   *out = h;
   return 0;
 }

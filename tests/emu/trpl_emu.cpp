@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../include/metrotrpl_b200.h"
 #include "../../metrotrpl_b200/csrc/trajectory.h"
+#include "../../metrotrpl_b200/csrc/explicit.h"
 
 using namespace trpl;
 
@@ -42,7 +43,10 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
     in.post_pass = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
     TrajOut out;
     TrajMid mid;
-    run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out, mid);
+    if (run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out, mid, !(opt.flags & OPT_NO_EXPLICIT))) {
+      run_trajectory_explicit<NPL, MODEL, FULL>(in, opt, sm, out, mid);
+      out.status |= ST_EXPLICIT;
+    }
     std::vector<double> ry, hk, trim;
     TailIn tl;
     tl.irf.nk = conv ? md->irf_nk : 0;

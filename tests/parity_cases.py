@@ -333,3 +333,36 @@ def check_traps_irf(backend):
     assert np.all(st == 0)
     rep["steps"] = ns[..., 0].tolist()
     return rep
+
+
+def check_explicit_path(backend):
+    """Non-stiff trajectories (no transport: the mobility-free cases of the reference's unit tests)
+    are classified at t = 0 and integrated by the embedded explicit Runge-Kutta pair; the result must
+    agree with the Rosenbrock path and with the converged reference, in fewer and cheaper steps."""
+    names, units, idx = _known_units()
+    t = np.linspace(0, 100, 1001)
+    sim = {"lengths": [2000, 2000], "nx": [128, 128], "meas_types": ["TRPL", "TRTS"], "num_meas": 2}
+    ini = np.array([1e15 * np.ones(128), 3e15 * np.exp(-np.arange(128) / 40.0)])
+    guess = dict(BASE, n0=1e8, p0=1e17, ks=1e-13, tauN=4, tauP=6, Cn=1e-29, Cp=1e-29)
+    stiff = dict(guess, mu_n=20, mu_p=20, Sf=10, Sb=10)
+    st = np.array([[guess[n] for n in names], [stiff[n] for n in names]], dtype=float)
+    params = _capi.pack_params(st, idx, units)
+    prob = _capi.pack_problem(sim, ini, [t, t], None, None)
+    aux = _capi.default_aux(2, 2, [1.0, 1.0])
+    base = _capi.OPT_NO_LIKELIHOOD
+    _, s_auto, n_auto, c_auto = backend(prob, params, aux, _capi.make_opts(RTOL=1e-8, flags=base), True)
+    _, s_ros, n_ros, c_ros = backend(prob, params, aux, _capi.make_opts(RTOL=1e-8, flags=base | _capi.OPT_NO_EXPLICIT), True)
+    assert np.all(s_auto[0] & _capi.ST_EXPLICIT) and not np.any(s_auto[1] & _capi.ST_EXPLICIT)
+    assert not np.any(s_ros & _capi.ST_EXPLICIT)
+    # same stiff trajectories either way, bit for bit
+    np.testing.assert_array_equal(c_auto[1], c_ros[1])
+    ok = c_ros[0] > 1e-6 * c_ros[0].max()
+    np.testing.assert_allclose(c_auto[0][ok], c_ros[0][ok], rtol=2e-7)
+    assert n_auto[0, :, 0].sum() < 0.7 * n_ros[0, :, 0].sum()
+    for m, meas in enumerate(("TRPL", "TRTS")):
+        g = orc.Grid(2000, 128, t, 4)
+        ref = orc.simulate(ini[m], g, st[0], idx, meas=meas, units=units, RTOL=1e-11, ATOL=1e-18)
+        mine = c_auto[0, m * 1001:(m + 1) * 1001]
+        okm = ref > 1e-6 * ref[0]
+        np.testing.assert_allclose(mine[okm], ref[okm], rtol=2e-6)
+    return {"explicit_steps": n_auto[0, :, 0].tolist(), "rosenbrock_steps": n_ros[0, :, 0].tolist()}

@@ -33,3 +33,7 @@ def test_ragged_and_fluence_inputs():
 
 def test_traps_model_with_irf_convolution_nx256():
     print(pc.check_traps_irf(backend))
+
+
+def test_explicit_rk_path_for_nonstiff_trajectories():
+    print(pc.check_explicit_path(backend))

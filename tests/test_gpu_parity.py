@@ -57,6 +57,10 @@ def test_traps_model_with_irf_convolution_nx256(ctx):
     print(pc.check_traps_irf(make_backend(ctx)))
 
 
+def test_explicit_rk_path_for_nonstiff_trajectories(ctx):
+    print(pc.check_explicit_path(make_backend(ctx)))
+
+
 def test_gpu_matches_host_lockstep_build(ctx):
     """Same source, two compilers: device results equal the host lock-step build to rounding."""
     from tests.emu import emu

@@ -61,3 +61,46 @@ if __name__ == "__main__":
     alpha, G, bh = to_classic(A, C, g, mhat)
     for k, v in order_residuals(alpha, G, bh).items():
         print("emb ", k, f"{v:.3e}")
+
+
+def dopri5():
+    """Dormand-Prince 5(4) tableau used by the explicit path (csrc/explicit.h)."""
+    from fractions import Fraction as F
+    c = [F(0), F(1, 5), F(3, 10), F(4, 5), F(8, 9), F(1), F(1)]
+    a = [[], [F(1, 5)], [F(3, 40), F(9, 40)], [F(44, 45), F(-56, 15), F(32, 9)],
+         [F(19372, 6561), F(-25360, 2187), F(64448, 6561), F(-212, 729)],
+         [F(9017, 3168), F(-355, 33), F(46732, 5247), F(49, 176), F(-5103, 18656)],
+         [F(35, 384), F(0), F(500, 1113), F(125, 192), F(-2187, 6784), F(11, 84)]]
+    b5 = a[6] + [F(0)]
+    b4 = [F(5179, 57600), F(0), F(7571, 16695), F(393, 640), F(-92097, 339200), F(187, 2100), F(1, 40)]
+    return c, a, b5, b4
+
+
+def check_dopri5():
+    from fractions import Fraction as F
+    c, a, b5, b4 = dopri5()
+    s = 7
+    A = [[(a[i][j] if j < len(a[i]) else F(0)) for j in range(s)] for i in range(s)]
+    for i in range(s):
+        assert sum(A[i]) == c[i], i
+    def dot(x, y): return sum(p * q for p, q in zip(x, y))
+    Ac = [dot(A[i], c) for i in range(s)]
+    Ac2 = [dot(A[i], [x * x for x in c]) for i in range(s)]
+    AAc = [dot(A[i], Ac) for i in range(s)]
+    for name, b, order in (("b5", b5, 5), ("b4", b4, 4)):
+        conds = {"1": (dot(b, [1] * s), F(1)), "2": (dot(b, c), F(1, 2)), "3a": (dot(b, [x**2 for x in c]), F(1, 3)),
+                 "3b": (dot(b, Ac), F(1, 6)), "4a": (dot(b, [x**3 for x in c]), F(1, 4)),
+                 "4b": (dot(b, [c[i] * Ac[i] for i in range(s)]), F(1, 8)), "4c": (dot(b, Ac2), F(1, 12)),
+                 "4d": (dot(b, AAc), F(1, 24))}
+        if order >= 5:
+            conds["5a"] = (dot(b, [x**4 for x in c]), F(1, 5))
+            conds["5b"] = (dot(b, [c[i]**2 * Ac[i] for i in range(s)]), F(1, 10))
+            conds["5c"] = (dot(b, [Ac[i]**2 for i in range(s)]), F(1, 20))
+        for k, (lhs, rhs) in conds.items():
+            assert lhs == rhs, (name, k, lhs, rhs)
+    print("DOPRI5: order conditions hold exactly (rational arithmetic); error weights:",
+          [str(x - y) for x, y in zip(b5, b4)])
+
+
+if __name__ == "__main__":
+    check_dopri5()
