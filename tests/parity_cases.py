@@ -366,3 +366,21 @@ def check_explicit_path(backend):
         okm = ref > 1e-6 * ref[0]
         np.testing.assert_allclose(mine[okm], ref[okm], rtol=2e-6)
     return {"explicit_steps": n_auto[0, :, 0].tolist(), "rosenbrock_steps": n_ros[0, :, 0].tolist()}
+
+
+def check_hmax_option(backend):
+    """`hmax` (the reference's LSODA max_step, sim_utils.py:17) is accepted and, when asked for,
+    imposed as a cap on the step size: same curves, at least t_end / hmax steps."""
+    g, prob, params, aux = staub_problem()
+    t = g["t"]
+    free = _capi.make_opts(RTOL=1e-7)
+    capped = _capi.make_opts(RTOL=1e-7, hmax=4.0, honor_hmax=True)
+    assert free.hmax == 0.0 and capped.hmax == 4.0
+    _, s0, n0, c0 = backend(prob, params[:1], aux[:1], free, True)
+    _, s1, n1, c1 = backend(prob, params[:1], aux[:1], capped, True)
+    assert np.all(n1[..., 0] >= int(t[-1] / 4.0))
+    assert np.all(n0[..., 0] < n1[..., 0])
+    np.testing.assert_allclose(c1, c0, rtol=5e-7)
+    T = g["pl_tight"][0].reshape(-1)
+    np.testing.assert_allclose(c1[0], T, rtol=5e-7)
+    return {"free_steps": n0[0, :, 0].tolist(), "capped_steps": n1[0, :, 0].tolist()}

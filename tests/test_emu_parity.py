@@ -37,3 +37,7 @@ def test_traps_model_with_irf_convolution_nx256():
 
 def test_explicit_rk_path_for_nonstiff_trajectories():
     print(pc.check_explicit_path(backend))
+
+
+def test_hmax_is_honoured_on_request():
+    print(pc.check_hmax_option(backend))

@@ -61,6 +61,10 @@ def test_explicit_rk_path_for_nonstiff_trajectories(ctx):
     print(pc.check_explicit_path(make_backend(ctx)))
 
 
+def test_hmax_is_honoured_on_request(ctx):
+    print(pc.check_hmax_option(make_backend(ctx)))
+
+
 def test_gpu_matches_host_lockstep_build(ctx):
     """Same source, two compilers: device results equal the host lock-step build to rounding."""
     from tests.emu import emu
