@@ -282,6 +282,22 @@ def check_edges(backend):
     _, s, ns, cur = backend(prob, _capi.pack_params(st2, idx, units), _capi.default_aux(1, 2, [1.0] * 2),
                             _capi.make_opts(RTOL=1e-8, flags=_capi.OPT_NO_LIKELIHOOD), True)
     np.testing.assert_allclose(cur[0, :11], cur[0, 11:], rtol=1e-7)
+    # every nodes-per-lane instantiation, with padding: nx = 16 (1/lane), 200 (8/lane), 'traps' at 100 (4/lane)
+    for nx, model in ((16, "std"), (200, "std"), (100, "traps")):
+        names_m = names + (["kC", "Nt", "tauE"] if model == "traps" else [])
+        units_m = np.concatenate([units, [1e12, 1e-21, 1.0]]) if model == "traps" else units
+        idx_m = {n: i for i, n in enumerate(names_m)}
+        gm = dict(guess, kC=1e-8, Nt=1e15, tauE=50.0)
+        stm = np.array([[gm[n] for n in names_m]], dtype=float)
+        simn = {"lengths": [500.0], "nx": [nx], "meas_types": ["TRPL"], "num_meas": 1}
+        prob = _capi.pack_problem(simn, [inis[0]], [t_c], None, None, model=model, ini_mode="fluence")
+        _, s, ns, cur = backend(prob, _capi.pack_params(stm, idx_m, units_m, model=model),
+                                _capi.default_aux(1, 1, [1.0]),
+                                _capi.make_opts(RTOL=1e-8, flags=_capi.OPT_NO_LIKELIHOOD), True)
+        g = orc.Grid(500.0, nx, t_c, 4)
+        ref = orc.simulate(inis[0], g, stm[0], idx_m, units=units_m, model=model, ini_mode="fluence",
+                           RTOL=1e-10, ATOL=1e-16)
+        np.testing.assert_allclose(cur[0], ref, rtol=2e-6)
     return True
 
 
