@@ -134,7 +134,7 @@ TRPL_FN bool emitter_step(Emitter& e, const TrajIn& in, bool want_ll, double t, 
       y = splat(val);
     } else {
       if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
-      y = hermite_eval(hc, tq);
+      y = hermite_guard(H, tq, hermite_eval(hc, tq));
       y = sel(tq >= t, val, y);
     }
     const mask take = lane < cnt;

@@ -45,6 +45,15 @@ TRPL_CONST double RODAS4_C[6][6] = {
      -0.6058818238834054e+01, 0}};
 constexpr double RODAS4_GAMMA = 0.25;
 
+// Weight of the running-charge components in the error norm (see DESIGN.md section 2,
+// "Tolerances"): Q is slaved to the densities by dielectric relaxation (sub-picosecond), the
+// stiffly accurate integrator resolves it like an algebraic variable, and the embedded estimate
+// for such components is known to be pessimistic.
+#ifndef TRPL_Q_ERR_WEIGHT
+#define TRPL_Q_ERR_WEIGHT 0.03
+#endif
+constexpr double Q_ERR_WEIGHT = TRPL_Q_ERR_WEIGHT;
+
 enum StatusBits {
   ST_OK = 0,
   ST_MAX_STEPS = 1,     // step budget exhausted before the last measurement time
@@ -243,6 +252,25 @@ TRPL_FN real hermite_eval(const HermiteCoef& k, real tq) {
   return k.in_log ? vexp(p) : p;
 }
 
+// Guard for hermite_eval: a smooth signal stays inside the band spanned by the step's two end
+// values (plus one span of margin).  When the signal has decayed into rounding noise the
+// controller takes huge steps and the high-order interpolant of noisy data can overshoot by tens
+// of decades; those points fall back to (log-)linear interpolation between the two ends.  The
+// fallback arithmetic sits behind a warp-uniform branch that is almost never taken.
+TRPL_FN real hermite_guard(const History& H, const real& tq, const real& y) {
+  const double a = H.v[1], b = H.v[2];
+  const double mn = fmin(a, b), mx = fmax(a, b);
+  const double margin = (mx - mn) + 1e-6 * fabs(mx);
+  const mask outside = mnot(mand(y >= mn - margin, y <= mx + margin));    // true for NaN
+  if (!warp_any(outside)) return y;
+  const bool ends_log = a > 0.0 && b > 0.0;
+  const double e1 = ends_log ? log(a) : a, e2 = ends_log ? log(b) : b;
+  const real theta = (tq - H.t[1]) * (1.0 / (H.t[2] - H.t[1]));
+  const real lin = fmadd(theta, e2 - e1, e1);
+  const real fb = ends_log ? vexp(lin) : lin;
+  return sel(outside, fb, y);
+}
+
 // ---- the trajectory -------------------------------------------------------------------------
 // Control flow is a small state machine so that the right-hand side, the readout/emit block and the
 // linear solve each exist at exactly ONE code site (the kernel is instruction-cache sensitive):
@@ -381,7 +409,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
               y = splat(val);                                            // t == 0
             } else {
               if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
-              y = hermite_eval(hc, tq);
+              y = hermite_guard(H, tq, hermite_eval(hc, tq));
               y = sel(tq >= t, val, y);                                  // exact on the step end
             }
             // forward_solver.py:190-192: from the first value below DBL_MIN on, the curve is DBL_MIN
@@ -545,7 +573,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
       const real iscn = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(us.n[j])), opt.atol));
       const real iscq = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(pold[j])), opt.atol));
-      const real en = kk.n[j] * iscn, eq = kk.q[j] * iscq;
+      const real en = kk.n[j] * iscn, eq = kk.q[j] * (iscq * Q_ERR_WEIGHT);
       real e2 = fmadd(en, en, eq * eq);
       if (MODEL == MODEL_TRAPS) {
         const real isct = rcp(fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(us.t[j]), vabs(u.n[j]))), opt.atol));

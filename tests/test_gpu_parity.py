@@ -112,6 +112,41 @@ def test_full_size_batch_properties(ctx):
     print("steps: mean", ns[..., 0].mean(), "max", ns[..., 0].max(), "kernel ms", ctx.last_kernel_ms())
 
 
+def test_self_convergence_at_full_size(ctx):
+    """4096 random parameter sets from the whole prior box x 6 curves (BASELINE configs[1] size):
+    the default-tolerance run against a 100x tighter run of the same integrator.  With relative
+    local error control the error of a decaying signal grows with the number of e-folds it has
+    decayed (an error in the rate is multiplied by t/tau), so the bound is stated per e-fold:
+    |S7/S9 - 1| <= 3e-6 * (1 + ln(S_max/S)) in the top six decades, <= 1e-5 in the top three."""
+    import bench
+    g, prob, params, aux = pc.staub_problem()
+    states = bench.draw_states(4096, seed=99)
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    P = _capi.pack_params(states, idx, g["units"])
+    A = np.repeat(aux[:1], 4096, axis=0)
+    ctx.set_problem(prob)
+    _, st7, ns7, c7 = ctx.loglik_batch(P, A, _capi.make_opts(RTOL=1e-7), want_curves=True)
+    _, st9, ns9, c9 = ctx.loglik_batch(P, A, _capi.make_opts(RTOL=1e-9), want_curves=True)
+    c7 = c7.reshape(4096, 6, -1)
+    c9 = c9.reshape(4096, 6, -1)
+    with np.errstate(all="ignore"):
+        win6 = c9 > 1e-6 * c9[:, :, :1]
+        win3 = c9 > 1e-3 * c9[:, :, :1]
+        err = np.abs(c7 / c9 - 1)
+        efold = np.log(np.maximum(c9[:, :, :1] / c9, 1.0))
+    scaled = np.where(win6, err / (1.0 + efold), 0.0)
+    top3 = np.where(win3, err, 0.0)
+    print("max err per e-fold", scaled.max(), "max err top 3 decades", top3.max(),
+          "mean steps", ns7[..., 0].mean(), ns9[..., 0].mean())
+    assert scaled.max() < 3e-6
+    assert top3.max() < 1e-5
+    assert np.all((st7 & 7) == 0) and np.all((st9 & 7) == 0)
+    # every curve is finite and bounded by its initial value (no interpolation overshoot in the
+    # rounding-noise regime of fully decayed signals)
+    assert np.all(np.isfinite(c7)) and np.all(c7 <= c7[:, :, :1] * (1 + 1e-9))
+
+
 def test_no_device_no_fallback():
     with pytest.raises(_capi.TrplError):
         _capi.Context(99)
