@@ -79,94 +79,6 @@ TRPL_FN void initial_state(const TrajIn& in, const Coef& c, const NodeMask<NPL>&
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) u.q[j] = sel(m.real_node[j], qloc[j] + excl, 0.0);
 }
 
-// measurement times inside the last accepted step, likelihood sums (same logic as the implicit path)
-struct Emitter {
-  int io;
-  bool floored;
-  int status;
-  History H;
-  real ll0, ll1, ll2, nneg;
-};
-
-TRPL_FN void emitter_init(Emitter& e) {
-  e.io = 0; e.floored = false; e.status = ST_OK; e.H.n = 0;
-  for (int k = 0; k < 3; ++k) { e.H.t[k] = 0; e.H.v[k] = 0; e.H.d[k] = 0; }
-  e.ll0 = splat(0.0); e.ll1 = splat(0.0); e.ll2 = splat(0.0); e.nneg = splat(0.0);
-}
-
-TRPL_FN void emitter_accumulate(Emitter& e, const TrajIn& in, bool want_ll, const ivec& k, const mask& take, const real& y) {
-  if (in.curve) scatter(in.curve, k, take, y);
-  if (want_ll && !in.post_pass) {
-    e.nneg = e.nneg + sel(mand(take, y < 0.0), 1.0, 0.0);
-    const real vk = gather(in.vals, k, take, 0.0);
-    const real uk = gather(in.uncs, k, take, 1.0);
-    const real r = (vlog10(vabs(y)) + in.scale_shift) - vk;
-    const real r2 = r * r;
-    const real u2 = 2.0 * (uk * uk);
-    e.ll0 = e.ll0 + sel(take, r2 * rcp(in.s2T[0] + u2), 0.0);
-    e.ll1 = e.ll1 + sel(take, r2 * rcp(in.s2T[1] + u2), 0.0);
-    e.ll2 = e.ll2 + sel(take, r2 * rcp(in.s2T[2] + u2), 0.0);
-  }
-}
-
-// returns true when the trajectory is finished (all times emitted, or the signal hit its floor)
-TRPL_FN bool emitter_step(Emitter& e, const TrajIn& in, bool want_ll, double t, double val, double dval) {
-  const MeasDesc& md = *in.md;
-  const int n_t = md.n_t;
-  const ivec lane = lane_id();
-  History& H = e.H;
-  H.t[0] = H.t[1]; H.v[0] = H.v[1]; H.d[0] = H.d[1];
-  H.t[1] = H.t[2]; H.v[1] = H.v[2]; H.d[1] = H.d[2];
-  H.t[2] = t; H.v[2] = val; H.d[2] = dval;
-  if (H.n < 3) ++H.n;
-  HermiteCoef hc;
-  bool have_hc = false;
-  while (e.io < n_t) {
-    const ivec k = iadd(lane, e.io);
-    const mask in_range = k < n_t;
-    const real tq = gather(in.times, k, in_range, DBL_MAX);
-    const unsigned bits = warp_ballot(mand(in_range, tq <= t));
-    if (bits == 0u) break;
-    int cnt = 0;
-    { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }
-    real y;
-    if (H.n < 2) {
-      y = splat(val);
-    } else {
-      if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
-      y = hermite_guard(H, tq, hermite_eval(hc, tq));
-      y = sel(tq >= t, val, y);
-    }
-    const mask take = lane < cnt;
-    const unsigned low = warp_ballot(mand(take, y < md.min_y));
-    if (low != 0u) {
-      int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
-      y = sel(lane >= firstlow, md.min_y, y);
-      e.floored = true; e.status |= ST_FLOORED;
-    }
-    emitter_accumulate(e, in, want_ll, k, take, y);
-    e.io += cnt;
-    if (cnt < 32 || e.floored) break;
-  }
-  return e.io >= n_t || e.floored;
-}
-
-TRPL_FN void emitter_finish(Emitter& e, const TrajIn& in, bool want_ll, TrajMid& mid) {
-  const int n_t = in.md->n_t;
-  const ivec lane = lane_id();
-  while (e.io < n_t) {                              // floor reached or integrator failure
-    const ivec k = iadd(lane, e.io);
-    emitter_accumulate(e, in, want_ll, k, k < n_t, splat(in.md->min_y));
-    e.io += 32;
-  }
-  if (want_ll && !in.post_pass) {
-    mid.l[0] = -uni(warp_sum(e.ll0)); mid.l[1] = -uni(warp_sum(e.ll1)); mid.l[2] = -uni(warp_sum(e.ll2));
-    mid.n_neg = uni(warp_sum(e.nneg));
-  } else {
-    mid.l[0] = mid.l[1] = mid.l[2] = 0.0; mid.n_neg = 0.0;
-  }
-}
-
 // Dormand-Prince 5(4)
 TRPL_CONST double DP_A[7][6] = {
     {0, 0, 0, 0, 0, 0},

@@ -22,8 +22,10 @@ using namespace simt;
 
 #if defined(TRPL_FN) && defined(__CUDACC__) && !defined(TRPL_HOST_EMU)
 #define TRPL_CONST __constant__ const
+#define TRPL_NOINLINE __device__ __noinline__
 #else
 #define TRPL_CONST static const
+#define TRPL_NOINLINE static
 #endif
 
 // RODAS4 in the Hairer-Wanner "transformed" form:
@@ -105,7 +107,10 @@ struct TrajIn {
   double fl_mult, al_mult;
   double* curve;         // optional [n_t] simulated signal in measurement units
   bool post_pass;        // likelihood is taken in finalize_trajectory (min_y floor, IRF, ladder)
+  double* hist;          // per-warp scratch: (t, S, dS/dt) of accepted steps, HIST_CAP entries
 };
+
+constexpr int HIST_CAP = 1024;
 
 // Everything only the final pass needs.  Built AFTER the integration loop so that none of it is
 // live (and spilled) across the hot loop.
@@ -271,6 +276,104 @@ TRPL_FN real hermite_guard(const History& H, const real& tq, const real& y) {
   return sel(outside, fb, y);
 }
 
+// ---- emission: measurement times inside an accepted step, likelihood sums -------------------------
+struct Emitter {
+  int io;
+  bool floored;
+  int status;
+  History H;
+  real ll0, ll1, ll2, nneg;
+};
+
+TRPL_FN void emitter_init(Emitter& e) {
+  e.io = 0; e.floored = false; e.status = ST_OK; e.H.n = 0;
+  for (int k = 0; k < 3; ++k) { e.H.t[k] = 0; e.H.v[k] = 0; e.H.d[k] = 0; }
+  e.ll0 = splat(0.0); e.ll1 = splat(0.0); e.ll2 = splat(0.0); e.nneg = splat(0.0);
+}
+
+TRPL_FN void emitter_accumulate(Emitter& e, const TrajIn& in, bool want_ll, const ivec& k, const mask& take, const real& y) {
+  if (in.curve) scatter(in.curve, k, take, y);
+  if (want_ll && !in.post_pass) {
+    e.nneg = e.nneg + sel(mand(take, y < 0.0), 1.0, 0.0);
+    const real vk = gather(in.vals, k, take, 0.0);
+    const real uk = gather(in.uncs, k, take, 1.0);
+    const real r = (vlog10(vabs(y)) + in.scale_shift) - vk;
+    const real r2 = r * r;
+    const real u2 = 2.0 * (uk * uk);
+    e.ll0 = e.ll0 + sel(take, r2 * rcp(in.s2T[0] + u2), 0.0);
+    e.ll1 = e.ll1 + sel(take, r2 * rcp(in.s2T[1] + u2), 0.0);
+    e.ll2 = e.ll2 + sel(take, r2 * rcp(in.s2T[2] + u2), 0.0);
+  }
+}
+
+// returns true when the trajectory is finished (all times emitted, or the signal hit its floor)
+TRPL_FN bool emitter_step(Emitter& e, const TrajIn& in, bool want_ll, double t, double val, double dval) {
+  const MeasDesc& md = *in.md;
+  const int n_t = md.n_t;
+  const ivec lane = lane_id();
+  History& H = e.H;
+  H.t[0] = H.t[1]; H.v[0] = H.v[1]; H.d[0] = H.d[1];
+  H.t[1] = H.t[2]; H.v[1] = H.v[2]; H.d[1] = H.d[2];
+  H.t[2] = t; H.v[2] = val; H.d[2] = dval;
+  if (H.n < 3) ++H.n;
+  HermiteCoef hc;
+  bool have_hc = false;
+  while (e.io < n_t) {
+    const ivec k = iadd(lane, e.io);
+    const mask in_range = k < n_t;
+    const real tq = gather(in.times, k, in_range, DBL_MAX);
+    const unsigned bits = warp_ballot(mand(in_range, tq <= t));
+    if (bits == 0u) break;
+    int cnt = 0;
+    { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }
+    real y;
+    if (H.n < 2) {
+      y = splat(val);
+    } else {
+      if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
+      y = hermite_guard(H, tq, hermite_eval(hc, tq));
+      y = sel(tq >= t, val, y);
+    }
+    const mask take = lane < cnt;
+    const unsigned low = warp_ballot(mand(take, y < md.min_y));
+    if (low != 0u) {
+      int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
+      y = sel(lane >= firstlow, md.min_y, y);
+      e.floored = true; e.status |= ST_FLOORED;
+    }
+    emitter_accumulate(e, in, want_ll, k, take, y);
+    e.io += cnt;
+    if (cnt < 32 || e.floored) break;
+  }
+  return e.io >= n_t || e.floored;
+}
+
+TRPL_FN void emitter_finish(Emitter& e, const TrajIn& in, bool want_ll, TrajMid& mid) {
+  const int n_t = in.md->n_t;
+  const ivec lane = lane_id();
+  while (e.io < n_t) {                              // floor reached or integrator failure
+    const ivec k = iadd(lane, e.io);
+    emitter_accumulate(e, in, want_ll, k, k < n_t, splat(in.md->min_y));
+    e.io += 32;
+  }
+  if (want_ll && !in.post_pass) {
+    mid.l[0] = -uni(warp_sum(e.ll0)); mid.l[1] = -uni(warp_sum(e.ll1)); mid.l[2] = -uni(warp_sum(e.ll2));
+    mid.n_neg = uni(warp_sum(e.nneg));
+  } else {
+    mid.l[0] = mid.l[1] = mid.l[2] = 0.0; mid.n_neg = 0.0;
+  }
+}
+
+// Deferred emission.  The integration loop only appends (t, S, dS/dt) of every accepted step to a
+// per-warp history buffer; this routine replays the buffer.  It is deliberately NOT inlined: the
+// interpolation and likelihood arithmetic (log, exp, log10, gathers, ballots) then cannot disturb
+// the register allocation of the hot loop, and nothing it needs is live there.
+TRPL_NOINLINE void emit_history(const TrajIn& in, bool want_ll, const double* hist, int n, Emitter& e) {
+  for (int i = 0; i < n; ++i) {
+    if (emitter_step(e, in, want_ll, hist[3 * i], hist[3 * i + 1], hist[3 * i + 2])) break;
+  }
+}
+
 // ---- the trajectory -------------------------------------------------------------------------
 // Control flow is a small state machine so that the right-hand side, the readout/emit block and the
 // linear solve each exist at exactly ONE code site (the kernel is instruction-cache sensitive):
@@ -299,7 +402,6 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   const int n_t = md.n_t;
   const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
   // min_y floor and IRF convolution need the whole curve: likelihood in a final pass over it
-  const bool post = in.post_pass;
   const double min_y = md.min_y;
 
   // ---- initial condition (forward_solver.py:100-122) ----
@@ -340,29 +442,10 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
 
   // ---- bookkeeping ----
   double t = 0.0;
-  int io = 0;                       // next measurement index to emit
   int status = ST_OK, n_acc = 0, n_rej = 0;
-  bool floored = false;
-  real ll0 = splat(0.0), ll1 = splat(0.0), ll2 = splat(0.0);
-  real nneg = splat(0.0);
-  History H; H.n = 0;
-  TRPL_UNROLL for (int k = 0; k < 3; ++k) { H.t[k] = 0; H.v[k] = 0; H.d[k] = 0; }
-
-  // likelihood contribution of a batch of emitted values (trial_move_evaluation.py:117-130, :147-156)
-  auto accumulate = [&](const ivec& k, const mask& take, const real& y) {
-    if (in.curve) scatter(in.curve, k, take, y);
-    if (want_ll && !post) {
-      nneg = nneg + sel(mand(take, y < 0.0), 1.0, 0.0);
-      const real vk = gather(in.vals, k, take, 0.0);
-      const real uk = gather(in.uncs, k, take, 1.0);
-      const real r = (vlog10(vabs(y)) + in.scale_shift) - vk;
-      const real r2 = r * r;
-      const real u2 = 2.0 * (uk * uk);
-      ll0 = ll0 + sel(take, r2 * rcp(in.s2T[0] + u2), 0.0);
-      ll1 = ll1 + sel(take, r2 * rcp(in.s2T[1] + u2), 0.0);
-      ll2 = ll2 + sel(take, r2 * rcp(in.s2T[2] + u2), 0.0);
-    }
-  };
+  int nh = 0;                       // entries in the history buffer
+  Emitter em;                       // lives in local memory: only the (cold) emission touches it
+  emitter_init(em);
 
   double h = 0.0, h_new = 0.0, gi = 0.0, ih = 0.0;
   float err_old = 1e-4f;
@@ -386,46 +469,20 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       RhsAux<NPL> aux;
       rhs<NPL, MODEL>(c, m, us, r, aux);
       if (phase == PH_ACCEPTED) {
-        // ---- newly accepted state (us == u): readout, history, measurement times ----
+        // ---- newly accepted state (us == u): read the signal out and log it ----
         double val, dval;
         readout<NPL, MODEL>(c, m, md.meas_type, u, r, aux, val, dval);
-        H.t[0] = H.t[1]; H.v[0] = H.v[1]; H.d[0] = H.d[1];
-        H.t[1] = H.t[2]; H.v[1] = H.v[2]; H.d[1] = H.d[2];
-        H.t[2] = t; H.v[2] = val; H.d[2] = dval;
-        if (H.n < 3) ++H.n;
-        {
-          HermiteCoef hc;
-          bool have_hc = false;
-          while (io < n_t) {
-            const ivec k = iadd(lane, io);
-            const mask in_range = k < n_t;
-            const real tq = gather(in.times, k, in_range, DBL_MAX);
-            const unsigned bits = warp_ballot(mand(in_range, tq <= t));
-            if (bits == 0u) break;
-            int cnt = 0;
-            { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }   // contiguous from lane 0 (times ascend)
-            real y;
-            if (H.n < 2) {
-              y = splat(val);                                            // t == 0
-            } else {
-              if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
-              y = hermite_guard(H, tq, hermite_eval(hc, tq));
-              y = sel(tq >= t, val, y);                                  // exact on the step end
-            }
-            // forward_solver.py:190-192: from the first value below DBL_MIN on, the curve is DBL_MIN
-            const mask take = lane < cnt;
-            const unsigned low = warp_ballot(mand(take, y < min_y));
-            if (low != 0u) {
-              int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
-              y = sel(lane >= firstlow, min_y, y);
-              floored = true; status |= ST_FLOORED;
-            }
-            accumulate(k, take, y);
-            io += cnt;
-            if (cnt < 32 || floored) break;
-          }
+        if (nh == HIST_CAP) {
+          warp_sync();
+          emit_history(in, want_ll, in.hist, nh, em);
+          nh = 0;
+          if (em.floored) break;
         }
-        if (io >= n_t || floored) break;     // done, or the rest of the curve is DBL_MIN by definition
+        scatter(in.hist, iadd(lane, 3 * nh), lane < 3, sel(lane == 0, t, sel(lane == 1, val, dval)));
+        ++nh;
+        // done when the last measurement time is reached, or the signal fell through its floor
+        // (forward_solver.py:190-192: the rest of the curve is min_y by definition)
+        if (t >= tend || val < min_y) break;
         if (n_acc == 0) {
           // ---- initial step (Hairer's d0/d1 rule on the scaled norms) ----
           real s0 = splat(0.0), s1 = splat(0.0);
@@ -620,21 +677,12 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       phase = PH_RETRY;
     }
   }
-  // anything not emitted (floor reached, or integrator failure): forward_solver.py:168 + :190-192
-  while (io < n_t) {
-    const ivec k = iadd(lane, io);
-    const mask take = k < n_t;
-    accumulate(k, take, splat(min_y));
-    io += 32;
-  }
-
-  out.status = status; out.n_acc = n_acc; out.n_rej = n_rej;
-  if (want_ll && !post) {
-    mid.l[0] = -uni(warp_sum(ll0)); mid.l[1] = -uni(warp_sum(ll1)); mid.l[2] = -uni(warp_sum(ll2));
-    mid.n_neg = uni(warp_sum(nneg));
-  } else {
-    mid.l[0] = mid.l[1] = mid.l[2] = 0.0; mid.n_neg = 0.0;
-  }
+  // replay the logged steps: measurement times, floor, likelihood sums; anything not reached
+  // (floor, or integrator failure) is min_y: forward_solver.py:168 + :190-192
+  warp_sync();
+  emit_history(in, want_ll, in.hist, nh, em);
+  emitter_finish(em, in, want_ll, mid);
+  out.status = status | em.status; out.n_acc = n_acc; out.n_rej = n_rej;
   return false;
 }
 

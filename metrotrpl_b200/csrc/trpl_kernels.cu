@@ -48,13 +48,15 @@ struct KernelArgs {
   int n_ladder;
   int* counter;              // work queue head
   const int* meas_order;     // [n_meas] measurement indices, most expensive first
+  double* hist;              // per-warp step histories, 3 * HIST_CAP doubles each
   int* defer_list;           // trajectories handed to the explicit path
   int* defer_count;
   int n_traj, n_meas, n_times_total, warps_per_cta;
   SolverOpts opt;
 };
 
-__device__ __forceinline__ void setup_traj(const KernelArgs& a, int traj, TrajIn& in) {
+__device__ __forceinline__ void setup_traj(const KernelArgs& a, int traj, int warp, TrajIn& in) {
+  in.hist = a.hist + (size_t)(blockIdx.x * a.warps_per_cta + warp) * (3 * HIST_CAP);
   const int set = traj / a.n_meas;
   const int mi = traj - set * a.n_meas;
   const MeasDesc* md = a.meas + mi;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     const int qm = traj / n_sets_q;
     traj = (traj - qm * n_sets_q) * a.n_meas + a.meas_order[qm];
     TrajIn in;
-    setup_traj(a, traj, in);
+    setup_traj(a, traj, warp, in);
     TrajOut out;
     TrajMid mid;
     if (run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out, mid, allow_defer)) {
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_explicit_kernel(co
     if (q >= n) break;
     const int traj = a.defer_list[q];
     TrajIn in;
-    setup_traj(a, traj, in);
+    setup_traj(a, traj, warp, in);
     TrajOut out;
     TrajMid mid;
     run_trajectory_explicit<NPL, MODEL, FULL>(in, a.opt, sm, out, mid);
@@ -203,7 +205,7 @@ struct trpl_handle {
   int model = 0, n_meas = 0, n_times_total = 0, max_nx = 0;
   bool have_vals = false, have_profiles = false, all_full = false;
   DevBuf<MeasDesc> d_meas;
-  DevBuf<double> d_times, d_vals, d_uncs, d_profiles, d_irf, d_scratch, d_ladder_T, d_ladder_out;
+  DevBuf<double> d_times, d_vals, d_uncs, d_profiles, d_irf, d_scratch, d_ladder_T, d_ladder_out, d_hist;
   int n_ladder = 0;
   bool ladder_valid = false;
   bool any_irf = false, have_irf = false;
@@ -243,6 +245,8 @@ int launch(trpl_handle* h, KernelArgs a) {
     CU(h->d_scratch.reserve((size_t)grid * wpc * a.scratch_stride));
     a.scratch = h->d_scratch.p;
   }
+  CU(h->d_hist.reserve((size_t)grid * wpc * 3 * HIST_CAP));
+  a.hist = h->d_hist.p;
   CU(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(int), h->stream));
   a.defer_list = nullptr; a.defer_count = h->d_counter.p + 2;
   if (!(a.opt.flags & OPT_NO_EXPLICIT)) {

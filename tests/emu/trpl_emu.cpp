@@ -37,6 +37,8 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
     in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
     in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
     in.curve = curves ? curves + (size_t)set * n_times_total + md->t_off : nullptr;
+    std::vector<double> hist(3 * HIST_CAP);
+    in.hist = hist.data();
     const bool want_ll = !(opt.flags & OPT_NO_LIKELIHOOD);
     const bool conv = irf_mom && md->irf_nk > 0;
     const bool ladder = (opt.flags & OPT_LADDER) && n_ladder > 0;
