@@ -64,6 +64,25 @@ TRPL_FN Coef make_coef(const double* p, double thickness, int L) {
   return c;
 }
 
+// The coefficients are warp-uniform.  Kept in registers they would pin ~46 registers for the whole
+// trajectory; parked in one shared-memory slot they cost a handful of broadcast loads per use.
+TRPL_FN void park_coef(LaneMem& sm, int slot, const Coef& c) {
+  const double v[24] = {c.n0, c.p0, c.d0, c.an, c.ap, c.dn, c.dp, c.ld, c.ix, c.ks, c.cn, c.cp, c.taun,
+                        c.taup, c.sf, c.sb, c.n0p0, c.kc, c.nt, c.itaue, c.mun, c.mup, c.dx, (double)c.L};
+  TRPL_UNROLL for (int i = 0; i < 24; ++i) sm.ust(slot, i, v[i]);
+  warp_sync();
+}
+TRPL_FN Coef fetch_coef(const LaneMem& sm, int slot) {
+  Coef c;
+  c.n0 = sm.uld(slot, 0); c.p0 = sm.uld(slot, 1); c.d0 = sm.uld(slot, 2); c.an = sm.uld(slot, 3);
+  c.ap = sm.uld(slot, 4); c.dn = sm.uld(slot, 5); c.dp = sm.uld(slot, 6); c.ld = sm.uld(slot, 7);
+  c.ix = sm.uld(slot, 8); c.ks = sm.uld(slot, 9); c.cn = sm.uld(slot, 10); c.cp = sm.uld(slot, 11);
+  c.taun = sm.uld(slot, 12); c.taup = sm.uld(slot, 13); c.sf = sm.uld(slot, 14); c.sb = sm.uld(slot, 15);
+  c.n0p0 = sm.uld(slot, 16); c.kc = sm.uld(slot, 17); c.nt = sm.uld(slot, 18); c.itaue = sm.uld(slot, 19);
+  c.mun = sm.uld(slot, 20); c.mup = sm.uld(slot, 21); c.dx = sm.uld(slot, 22); c.L = (int)sm.uld(slot, 23);
+  return c;
+}
+
 // Per-lane node classification (constant for a trajectory).
 template <int NPL>
 struct NodeMask {

@@ -105,6 +105,9 @@ struct LaneMem {
   TRPL_FN void st2(int p, real a, real b) const { base[p * 32 + (threadIdx.x & 31u)] = make_double2(a, b); }
   // read another lane's pair (lane exchange through shared memory; caller orders with warp_sync)
   TRPL_FN void ld2_from(int p, ivec src, real& a, real& b) const { const double2 v = base[p * 32 + src]; a = v.x; b = v.y; }
+  // warp-uniform scalars parked in pair slot p (64 doubles): every lane reads the same word (broadcast)
+  TRPL_FN double uld(int p, int i) const { return reinterpret_cast<const double*>(base + p * 32)[i]; }
+  TRPL_FN void ust(int p, int i, double v) const { reinterpret_cast<double*>(base + p * 32)[i] = v; }
 };
 TRPL_FN void warp_sync() { __syncwarp(); }
 }  // namespace simt
@@ -216,6 +219,8 @@ struct LaneMem {
   void ld2_from(int p, const ivec& src, real& a, real& b) const {
     for (int i = 0; i < 32; ++i) { a.v[i] = slots[2 * p].v[src.v[i]]; b.v[i] = slots[2 * p + 1].v[src.v[i]]; }
   }
+  double uld(int p, int i) const { return slots[2 * p + (i & 1)].v[i >> 1]; }
+  void ust(int p, int i, double v) { slots[2 * p + (i & 1)].v[i >> 1] = v; }
 };
 inline void warp_sync() {}
 }  // namespace simt

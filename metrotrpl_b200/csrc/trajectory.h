@@ -148,7 +148,8 @@ struct Slots {
   // region (dead at that point) when that is large enough, else it gets its own
   static constexpr int XCH = TRAP + ((MODEL == MODEL_TRAPS) ? 3 * NPL : 0);
   static constexpr int XCH_FACTOR = (NKS * KSTRIDE >= 12) ? KBASE : XCH;
-  static constexpr int COUNT = XCH + ((NKS * KSTRIDE >= 12) ? 2 : 12);
+  static constexpr int UNI = XCH + ((NKS * KSTRIDE >= 12) ? 2 : 12);   // one slot of warp-uniform scalars (Coef)
+  static constexpr int COUNT = UNI + 1;
   static constexpr int BYTES = COUNT * 32 * 16;
 };
 
@@ -395,7 +396,10 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   typedef Vec<NPL, MODEL> V;
   const MeasDesc& md = *in.md;
   const int L = md.nx;
+  // The coefficients are formed once, parked in the uniform shared-memory slot and re-fetched by
+  // each block of the loop that needs them (broadcast loads), instead of pinning registers.
   const Coef c = make_coef(in.par, md.thickness, L);
+  park_coef(sm, SL::UNI, c);
   const NodeMask<NPL> m = make_mask<NPL, FULL>(L);
   const ivec lane = lane_id();
   const ivec node0 = imul(lane, NPL);
@@ -467,11 +471,12 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       // PH_RETRY re-evaluates f(u) (us == u): rejections are rare (~0.5% of steps) and this keeps
       // f(u) out of shared memory
       RhsAux<NPL> aux;
-      rhs<NPL, MODEL>(c, m, us, r, aux);
+      const Coef cr = fetch_coef(sm, SL::UNI);
+      rhs<NPL, MODEL>(cr, m, us, r, aux);
       if (phase == PH_ACCEPTED) {
         // ---- newly accepted state (us == u): read the signal out and log it ----
         double val, dval;
-        readout<NPL, MODEL>(c, m, md.meas_type, u, r, aux, val, dval);
+        readout<NPL, MODEL>(cr, m, md.meas_type, u, r, aux, val, dval);
         if (nh == HIST_CAP) {
           warp_sync();
           emit_history(in, want_ll, in.hist, nh, em);
@@ -516,7 +521,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
         // W = 1/(gamma h) I - J, factorised
         Blk A[NPL], B[NPL], C[NPL];
         JacTraps<NPL> jt;
-        jacobian<NPL, MODEL>(c, m, u, A, B, C, jt);
+        jacobian<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, u, A, B, C, jt);
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
           A[j] = blk_neg(A[j]); C[j] = blk_neg(C[j]);
           B[j].a00 = gi - B[j].a00; B[j].a01 = -B[j].a01; B[j].a10 = -B[j].a10; B[j].a11 = gi - B[j].a11;
@@ -626,7 +631,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
     real esum = splat(0.0);
     mask bad = mconst(false);
     real pold[NPL];
-    holes<NPL, MODEL>(c, m, u, pold);
+    holes<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, u, pold);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
       const real iscn = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(us.n[j])), opt.atol));
       const real iscq = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(pold[j])), opt.atol));
