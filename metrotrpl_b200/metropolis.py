@@ -31,7 +31,7 @@ from .laplace import load_irf_tables
 from .mcmc_logging import start_logging, stop_logging
 from .parallel import Comm
 from .sim_utils import Ensemble
-from .trial_move_generation import make_trial_move
+from .trial_move_generation import make_trial_move, make_trial_moves
 
 MSG_FREQ = 100       # metropolis.py:31
 MSG_COOLDOWN = 3     # metropolis.py:32
@@ -108,13 +108,8 @@ def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, sha
             for m in range(n_chains):
                 logger.info(f"Iter {k} MetroState #{m} Current state: {states[m, :, k-1]} logll {logll[m, k-1]}")
         # proposals and acceptance draws in the reference's generator order
-        proposals = np.empty((n_chains, states.shape[1]))
-        u = np.empty(n_chains)
-        for m in range(n_chains):
-            proposals[m] = make_trial_move(states[m, :, k - 1],
-                                           unique_fields[m]["_T"] ** 0.5 * shared_fields["base_trial_move"],
-                                           shared_fields, RNG, logger)
-            u[m] = RNG.random()
+        moves = np.sqrt(T)[:, None] * shared_fields["base_trial_move"][None, :]
+        proposals, u = make_trial_moves(states[:, :, k - 1], moves, shared_fields, RNG, logger)
         new_ladder = sharded_eval(evaluator, comm, proposals, sigmas)
         new_ll = new_ladder[own, own]
         logratio = new_ll - logll[:, k - 1]

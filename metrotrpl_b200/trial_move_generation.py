@@ -63,3 +63,75 @@ def make_trial_move(current_state, trial_move, shared_fields, RNG, logger=None):
         if logger is not None:
             logger.warning(f"Failed checks: {failed}")
     return np.where(do_log, 10 ** new_state, new_state)
+
+
+
+def _approve_rows(new_states, shared_fields):
+    """Vectorised approve_move: True where a (log-scaled) proposal passes every check."""
+    order = shared_fields["names"]
+    prior = shared_fields["prior_dist"]
+    idx = shared_fields["_param_indexes"]
+    do_log = np.asarray(shared_fields["do_log"], dtype=bool)
+    active = np.asarray(shared_fields["active"], dtype=bool)
+    linear = np.where(do_log[None, :], 10 ** new_states, new_states)
+    lo = np.array([prior[n][0] for n in order], dtype=float)
+    hi = np.array([prior[n][1] for n in order], dtype=float)
+    inside = (lo[None, :] < linear) & (linear < hi[None, :])
+    ok = np.all(inside | ~active[None, :], axis=1)
+    if "p0" in order and "n0" in order:
+        ok &= new_states[:, idx["p0"]] > new_states[:, idx["n0"]]
+    if "tauN" in order and "tauP" in order:
+        ltn = new_states[:, idx["tauN"]]
+        ltp = new_states[:, idx["tauP"]]
+        if not do_log[idx["tauN"]]:
+            ltn = np.log10(ltn)
+        if not do_log[idx["tauP"]]:
+            ltp = np.log10(ltp)
+        ok &= np.abs(ltn - ltp) <= 2
+    return ok
+
+
+def make_trial_moves(current_states, trial_moves, shared_fields, RNG, logger=None):
+    """All chains' proposals and acceptance draws of one iteration.
+
+    Consumes the generator exactly as the reference's serial loop does (metropolis.py:118-127):
+    for each chain in turn its proposal draws (one RNG.random(n_params) per attempt, retried under
+    hard bounds), then its acceptance draw.  The common case - first attempt admissible - is done for
+    all remaining chains with one matrix draw; a chain that needs retries is replayed one draw at a
+    time from the exact generator position (PCG64 `advance`), then the matrix draw resumes.
+
+    Returns (proposals [n_chains, n_params], u [n_chains]).
+    """
+    cur = np.asarray(current_states, dtype=float)
+    n_chains, n_par = cur.shape
+    proposals = np.empty_like(cur)
+    u = np.empty(n_chains)
+    bitgen = RNG.bit_generator
+    can_batch = shared_fields.get("do_mu_constraint", None) is None and hasattr(bitgen, "advance")
+    do_log = np.asarray(shared_fields["do_log"], dtype=bool)
+    hard = bool(shared_fields.get("hard_bounds", 0))
+    m = 0
+    while m < n_chains:
+        if not can_batch:
+            proposals[m] = make_trial_move(cur[m], trial_moves[m], shared_fields, RNG, logger)
+            u[m] = RNG.random()
+            m += 1
+            continue
+        state0 = bitgen.state
+        rest = n_chains - m
+        draws = RNG.random((rest, n_par + 1))
+        logcur = np.where(do_log[None, :], np.log10(cur[m:]), cur[m:])
+        new = logcur + trial_moves[m:] * (2 * draws[:, :n_par] - 1)
+        ok = _approve_rows(new, shared_fields) if hard else np.ones(rest, dtype=bool)
+        n_ok = rest if ok.all() else int(np.argmin(ok))
+        proposals[m:m + n_ok] = np.where(do_log[None, :], 10 ** new[:n_ok], new[:n_ok])
+        u[m:m + n_ok] = draws[:n_ok, n_par]
+        m += n_ok
+        if m < n_chains:
+            # chain m needs retries: rewind to just before its first attempt and replay serially
+            bitgen.state = state0
+            bitgen.advance(n_ok * (n_par + 1))
+            proposals[m] = make_trial_move(cur[m], trial_moves[m], shared_fields, RNG, logger)
+            u[m] = RNG.random()
+            m += 1
+    return proposals, u

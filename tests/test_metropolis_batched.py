@@ -105,6 +105,29 @@ def test_make_trial_move_respects_bounds_and_inactive():
     assert "tauN_size" in approve_move(bad, sf)
 
 
+def test_batched_proposals_consume_the_generator_like_the_serial_loop():
+    from metrotrpl_b200.trial_move_generation import make_trial_moves
+    sim_info, ini, e_data, MCMC, param_info = small_problem(tempfile.mkdtemp(), n_chains=12)
+    param_info["prior_dist"]["tauN"] = (400, 650)          # tight box: some chains need retries
+    param_info["prior_dist"]["p0"] = (1e15, 1e16)
+    ens = Ensemble(param_info, sim_info, MCMC, 5)
+    sf = ens.ensemble_fields
+    T = np.asarray(sf["_T"], dtype=float)
+    cur = np.repeat(ens.H.states[:, :, 0][:1], 12, axis=0) * (1 + 0.01 * np.arange(12))[:, None]
+    moves = np.sqrt(T)[:, None] * sf["base_trial_move"][None, :]
+    for seed in range(5):
+        r1 = np.random.default_rng(seed)
+        r2 = np.random.default_rng(seed)
+        ref_p, ref_u = [], []
+        for m in range(12):
+            ref_p.append(make_trial_move(cur[m], moves[m], sf, r1))
+            ref_u.append(r1.random())
+        got_p, got_u = make_trial_moves(cur, moves, sf, r2)
+        np.testing.assert_array_equal(got_p, np.array(ref_p))
+        np.testing.assert_array_equal(got_u, np.array(ref_u))
+        assert r1.random() == r2.random()                  # same generator position afterwards
+
+
 def test_metro_runs_checkpoints_and_is_deterministic():
     tmp = tempfile.mkdtemp()
     a = run_metro(tmp)
