@@ -205,6 +205,10 @@ _LIB_NAME = "libmetrotrpl_b200.so"
 
 
 def library_path() -> str:
+    # METROTRPL_B200_LIB: developer override to A/B another build of the same CUDA library
+    override = os.environ.get("METROTRPL_B200_LIB")
+    if override:
+        return os.path.abspath(override)
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 

@@ -218,7 +218,9 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], LaneMem& sm, int base, int xch, const PcrFac
     V2 up, dn;
     sm.ld2_from(xb, lane_minus(s), up.x, up.y);
     sm.ld2_from(xb, lane_plus(s), dn.x, dn.y);
-    rr = add_mv(add_mv(rr, pf.al[k], up), pf.ga[k], dn);     // multipliers are exact zeros where no neighbour
+    // two independent chains (multipliers are exact zeros where there is no neighbour)
+    const V2 lo = blk_mv(pf.al[k], up), hi = add_mv(rr, pf.ga[k], dn);
+    rr.x = lo.x + hi.x; rr.y = lo.y + hi.y;
   }
   const V2 z = blk_mv(pf.binv, rr);
   r[NPL - 1] = z;

@@ -117,7 +117,8 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, La
   rhs<NPL, MODEL>(c, m, u, k1, aux);
   double val, dval;
   readout<NPL, MODEL>(c, m, md.meas_type, u, k1, aux, val, dval);
-  bool done = emitter_step(em, in, want_ll, 0.0, val, dval);
+  int nh = 0;                       // entries in the step log (trajectory.h, "Deferred emission")
+  bool done = log_point(in, want_ll, em, nh, 0.0, val, dval) || 0.0 >= tend || val < md.min_y;
   if (!done) {
     real s0 = splat(0.0), s1 = splat(0.0);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
@@ -200,13 +201,15 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, La
         if (MODEL == MODEL_TRAPS) { u.t[j] = us.t[j]; k1.t[j] = kk.t[j]; }
       }
       readout<NPL, MODEL>(c, m, md.meas_type, u, k1, aux, val, dval);     // aux.p belongs to u_new
-      done = emitter_step(em, in, want_ll, t, val, dval);
+      done = log_point(in, want_ll, em, nh, t, val, dval) || t >= tend || val < md.min_y;
       h = h * (double)fac;
     } else {
       ++n_rej;
       h = nonfinite ? 0.1 * h : h * (double)fminf(fac, 1.0f);
     }
   }
+  warp_sync();
+  emit_history(in, want_ll, in.hist, nh, em, false);
   emitter_finish(em, in, want_ll, mid);
   out.status = em.status; out.n_acc = n_acc; out.n_rej = n_rej;
 }

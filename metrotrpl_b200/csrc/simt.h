@@ -56,6 +56,17 @@ TRPL_FN real rcp(real x) {
   r = fma(r, e, r);
   return r;
 }
+TRPL_FN real vdiv(real a, real b) { return a / b; }       // IEEE division (cold paths only)
+// Reciprocal to ~2^-23 (the hardware seed alone): for quantities that only steer the step size.
+TRPL_FN real rcp_approx(real x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+// max of two non-NaN values without fmax's NaN bookkeeping (NaN states are detected separately)
+TRPL_FN real vmax_fast(real a, real b) { return a > b ? a : b; }
+// x^y for the step-size controller (warp-uniform scalars, single precision, x > 0)
+TRPL_FN float ctl_powf(float x, float y) { return __powf(x, y); }
 TRPL_FN real vabs(real x) { return fabs(x); }
 TRPL_FN real vmax(real a, real b) { return fmax(a, b); }
 TRPL_FN real vmin(real a, real b) { return fmin(a, b); }
@@ -170,6 +181,10 @@ inline unsigned warp_ballot(const mask& m) { unsigned b = 0; for (int i = 0; i <
 inline mask lane_lt(const ivec& l, int k) { return l < k; }
 inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
 template <class A, class B, class C> inline real fmadd(const A& a, const B& b, const C& c) { return fmadd3(real(a), real(b), real(c)); }
+inline real vdiv(const real& a, const real& b) { return a / b; }
+inline real rcp_approx(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
+inline real vmax_fast(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] > b.v[i] ? a.v[i] : b.v[i]; return r; }
+inline float ctl_powf(float x, float y) { return powf(x, y); }
 inline real rcp(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
 #define TRPL_UN(name, expr) inline real name(const real& x) { real r; for (int i = 0; i < 32; ++i) { double a = x.v[i]; r.v[i] = (expr); } return r; }
 TRPL_UN(vabs, fabs(a)) TRPL_UN(vexp, exp(a)) TRPL_UN(vlog, log(a)) TRPL_UN(vlog10, log10(a)) TRPL_UN(vsqrt, sqrt(a))

@@ -30,21 +30,23 @@ using namespace simt;
 
 // RODAS4 in the Hairer-Wanner "transformed" form:
 //   (1/(gamma h) I - J) K_i = f(u + sum_j a_ij K_j) + sum_j (c_ij / h) K_j ,  u_new = u + sum m_i K_i
-TRPL_CONST double RODAS4_A[6][6] = {
-    {0, 0, 0, 0, 0, 0},
-    {0.1544000000000000e+01, 0, 0, 0, 0, 0},
-    {0.9466785280815826e+00, 0.2557011698983284e+00, 0, 0, 0, 0},
-    {0.3314825187068521e+01, 0.2896124015972201e+01, 0.9986419139977817e+00, 0, 0, 0},
-    {0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 0, 0},
-    {0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 1.0, 0}};
-TRPL_CONST double RODAS4_C[6][6] = {
-    {0, 0, 0, 0, 0, 0},
-    {-0.5668800000000000e+01, 0, 0, 0, 0, 0},
-    {-0.2430093356833875e+01, -0.2063599157091915e+00, 0, 0, 0, 0},
-    {-0.1073529058151375e+00, -0.9594562251023355e+01, -0.2047028614809616e+02, 0, 0, 0},
-    {0.7496443313967647e+01, -0.1024680431464352e+02, -0.3399990352819905e+02, 0.1170890893206160e+02, 0, 0},
-    {0.8083246795921522e+01, -0.7981132988064893e+01, -0.3152159432874371e+02, 0.1631930543123136e+02,
-     -0.6058818238834054e+01, 0}};
+struct Rodas4 {
+  static constexpr double A[6][6] = {
+      {0, 0, 0, 0, 0, 0},
+      {0.1544000000000000e+01, 0, 0, 0, 0, 0},
+      {0.9466785280815826e+00, 0.2557011698983284e+00, 0, 0, 0, 0},
+      {0.3314825187068521e+01, 0.2896124015972201e+01, 0.9986419139977817e+00, 0, 0, 0},
+      {0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 0, 0},
+      {0.1221224509226641e+01, 0.6019134481288629e+01, 0.1253708332932087e+02, -0.6878860361058950e+00, 1.0, 0}};
+  static constexpr double C[6][6] = {
+      {0, 0, 0, 0, 0, 0},
+      {-0.5668800000000000e+01, 0, 0, 0, 0, 0},
+      {-0.2430093356833875e+01, -0.2063599157091915e+00, 0, 0, 0, 0},
+      {-0.1073529058151375e+00, -0.9594562251023355e+01, -0.2047028614809616e+02, 0, 0, 0},
+      {0.7496443313967647e+01, -0.1024680431464352e+02, -0.3399990352819905e+02, 0.1170890893206160e+02, 0, 0},
+      {0.8083246795921522e+01, -0.7981132988064893e+01, -0.3152159432874371e+02, 0.1631930543123136e+02,
+       -0.6058818238834054e+01, 0}};
+};
 constexpr double RODAS4_GAMMA = 0.25;
 
 // Weight of the running-charge components in the error norm (see DESIGN.md section 2,
@@ -203,92 +205,73 @@ TRPL_FN void readout(const Coef& c, const NodeMask<NPL>& m, int meas_type, const
   dval = uni(warp_sum(dacc)) * scale;
 }
 
-// ---- Hermite history (warp-uniform scalars) -------------------------------------------------
-struct History {
-  double t[3], v[3], d[3];   // index 2 = newest
-  int n;
-};
-
-struct HermiteCoef {
-  double t1, t2, t0;
-  double c0, c1, c2, c3, c4, c5;
-  bool in_log;
-};
-
-// Newton form on the doubled nodes [t1,t1,t2,t2,t0,t0] (t1,t2 = last step; t0 = the step before)
-TRPL_FN HermiteCoef hermite_setup(const History& H) {
-  HermiteCoef k;
-  const bool three = H.n >= 3;
-  k.in_log = H.v[1] > 0.0 && H.v[2] > 0.0 && (!three || H.v[0] > 0.0);
-  double v0, v1, v2, d0, d1, d2;
-  if (k.in_log) {
-    v1 = log(H.v[1]); v2 = log(H.v[2]); d1 = H.d[1] / H.v[1]; d2 = H.d[2] / H.v[2];
-    v0 = three ? log(H.v[0]) : 0.0; d0 = three ? H.d[0] / H.v[0] : 0.0;
-  } else {
-    v1 = H.v[1]; v2 = H.v[2]; d1 = H.d[1]; d2 = H.d[2]; v0 = H.v[0]; d0 = H.d[0];
-  }
-  k.t1 = H.t[1]; k.t2 = H.t[2]; k.t0 = H.t[0];
-  const double i21 = 1.0 / (k.t2 - k.t1);
-  const double f12 = (v2 - v1) * i21;
-  const double f112 = (f12 - d1) * i21;
-  const double f122 = (d2 - f12) * i21;
-  const double f1122 = (f122 - f112) * i21;
-  k.c0 = v1; k.c1 = d1; k.c2 = f112; k.c3 = f1122; k.c4 = 0.0; k.c5 = 0.0;
-  if (three) {
-    const double i01 = 1.0 / (k.t0 - k.t1), i02 = 1.0 / (k.t0 - k.t2);
-    const double f20 = (v0 - v2) * i02;
-    const double f220 = (f20 - d2) * i02;
-    const double f200 = (d0 - f20) * i02;
-    const double f1220 = (f220 - f122) * i01;
-    const double f2200 = (f200 - f220) * i02;
-    const double f11220 = (f1220 - f1122) * i01;
-    const double f12200 = (f2200 - f1220) * i01;
-    k.c4 = f11220;
-    k.c5 = (f12200 - f11220) * i01;
-  }
-  return k;
-}
-
-TRPL_FN real hermite_eval(const HermiteCoef& k, real tq) {
-  const real a = tq - k.t1, b = tq - k.t2, e = tq - k.t0;
+// ---- dense output: per-lane Hermite interpolation through logged step points -----------------
+// Each lane interpolates its own measurement time.  Newton form on the doubled nodes
+// [t1,t1,t2,t2,t0,t0] (t1,t2 = the step containing the time; t0 = the step point before it);
+// `three` is false for the first step of a trajectory (cubic through two points).  Interpolation
+// is done on ln(signal) whenever all points involved are positive.
+TRPL_FN real hermite_lane(const real& tq, const mask& three, const real& t0, const real& y0, const real& s0,
+                          const real& t1, const real& y1, const real& s1, const real& t2, const real& y2,
+                          const real& s2) {
+  const mask in_log = mand(mand(y1 > 0.0, y2 > 0.0), mor(mnot(three), y0 > 0.0));
+  const mask log0 = mand(in_log, three);
+  const real v1 = sel(in_log, vlog(sel(in_log, y1, 1.0)), y1);
+  const real v2 = sel(in_log, vlog(sel(in_log, y2, 1.0)), y2);
+  const real v0 = sel(in_log, sel(three, vlog(sel(log0, y0, 1.0)), 0.0), y0);
+  const real d1 = sel(in_log, vdiv(s1, sel(in_log, y1, 1.0)), s1);
+  const real d2 = sel(in_log, vdiv(s2, sel(in_log, y2, 1.0)), s2);
+  const real d0 = sel(in_log, sel(three, vdiv(s0, sel(log0, y0, 1.0)), 0.0), s0);
+  const real i21 = vdiv(splat(1.0), t2 - t1);
+  const real f12 = (v2 - v1) * i21;
+  const real f112 = (f12 - d1) * i21;
+  const real f122 = (d2 - f12) * i21;
+  const real f1122 = (f122 - f112) * i21;
+  // the three-point part is garbage (and discarded) on lanes where `three` is false
+  const real i01 = vdiv(splat(1.0), sel(three, t0 - t1, 1.0)), i02 = vdiv(splat(1.0), sel(three, t0 - t2, 1.0));
+  const real f20 = (v0 - v2) * i02;
+  const real f220 = (f20 - d2) * i02;
+  const real f200 = (d0 - f20) * i02;
+  const real f1220 = (f220 - f122) * i01;
+  const real f2200 = (f200 - f220) * i02;
+  const real f11220 = (f1220 - f1122) * i01;
+  const real f12200 = (f2200 - f1220) * i01;
+  const real c4 = sel(three, f11220, 0.0);
+  const real c5 = sel(three, (f12200 - f11220) * i01, 0.0);
+  const real a = tq - t1, b = tq - t2, e = tq - t0;
   const real a2 = a * a, b2 = b * b;
-  real p = fmadd(e, k.c5, k.c4);          // c4 + c5 (t-t0)
-  p = fmadd(p, b2, fmadd(b, k.c3, k.c2)); // c2 + c3 (t-t2) + (t-t2)^2 (...)
-  p = fmadd(p, a2, fmadd(a, k.c1, k.c0)); // c0 + c1 (t-t1) + (t-t1)^2 (...)
-  return k.in_log ? vexp(p) : p;
-}
-
-// Guard for hermite_eval: a smooth signal stays inside the band spanned by the step's two end
-// values (plus one span of margin).  When the signal has decayed into rounding noise the
-// controller takes huge steps and the high-order interpolant of noisy data can overshoot by tens
-// of decades; those points fall back to (log-)linear interpolation between the two ends.  The
-// fallback arithmetic sits behind a warp-uniform branch that is almost never taken.
-TRPL_FN real hermite_guard(const History& H, const real& tq, const real& y) {
-  const double a = H.v[1], b = H.v[2];
-  const double mn = fmin(a, b), mx = fmax(a, b);
-  const double margin = (mx - mn) + 1e-6 * fabs(mx);
+  real p = fmadd(e, c5, c4);                  // c4 + c5 (t-t0)
+  p = fmadd(p, b2, fmadd(b, f1122, f112));    // c2 + c3 (t-t2) + (t-t2)^2 (...)
+  p = fmadd(p, a2, fmadd(a, d1, v1));         // c0 + c1 (t-t1) + (t-t1)^2 (...)
+  real y = sel(in_log, vexp(sel(in_log, p, 0.0)), p);
+  // Guard: a smooth signal stays inside the band spanned by the step's two end values (plus one
+  // span of margin).  When the signal has decayed into rounding noise the controller takes huge
+  // steps and the high-order interpolant of noisy data can overshoot by tens of decades; those
+  // points fall back to (log-)linear interpolation between the two ends.
+  const real mn = vmin(y1, y2), mx = vmax(y1, y2);
+  const real margin = (mx - mn) + 1e-6 * vabs(mx);
   const mask outside = mnot(mand(y >= mn - margin, y <= mx + margin));    // true for NaN
-  if (!warp_any(outside)) return y;
-  const bool ends_log = a > 0.0 && b > 0.0;
-  const double e1 = ends_log ? log(a) : a, e2 = ends_log ? log(b) : b;
-  const real theta = (tq - H.t[1]) * (1.0 / (H.t[2] - H.t[1]));
-  const real lin = fmadd(theta, e2 - e1, e1);
-  const real fb = ends_log ? vexp(lin) : lin;
-  return sel(outside, fb, y);
+  if (warp_any(outside)) {
+    const mask ends_log = mand(y1 > 0.0, y2 > 0.0);
+    const real e1 = sel(ends_log, vlog(sel(ends_log, y1, 1.0)), y1);
+    const real e2 = sel(ends_log, vlog(sel(ends_log, y2, 1.0)), y2);
+    const real lin = fmadd(a * i21, e2 - e1, e1);
+    const real fb = sel(ends_log, vexp(sel(ends_log, lin, 0.0)), lin);
+    y = sel(outside, fb, y);
+  }
+  return y;
 }
 
-// ---- emission: measurement times inside an accepted step, likelihood sums -------------------------
+// ---- emission: measurement times against the step log, likelihood sums ---------------------------
 struct Emitter {
-  int io;
+  int io;            // measurement times emitted so far
+  int base;          // trajectory-global index of log entry 0 (entries dropped by earlier flushes)
   bool floored;
   int status;
-  History H;
   real ll0, ll1, ll2, nneg;
 };
 
 TRPL_FN void emitter_init(Emitter& e) {
-  e.io = 0; e.floored = false; e.status = ST_OK; e.H.n = 0;
-  for (int k = 0; k < 3; ++k) { e.H.t[k] = 0; e.H.v[k] = 0; e.H.d[k] = 0; }
+  e.io = 0; e.base = 0; e.floored = false; e.status = ST_OK;
   e.ll0 = splat(0.0); e.ll1 = splat(0.0); e.ll2 = splat(0.0); e.nneg = splat(0.0);
 }
 
@@ -305,48 +288,6 @@ TRPL_FN void emitter_accumulate(Emitter& e, const TrajIn& in, bool want_ll, cons
     e.ll1 = e.ll1 + sel(take, r2 * rcp(in.s2T[1] + u2), 0.0);
     e.ll2 = e.ll2 + sel(take, r2 * rcp(in.s2T[2] + u2), 0.0);
   }
-}
-
-// returns true when the trajectory is finished (all times emitted, or the signal hit its floor)
-TRPL_FN bool emitter_step(Emitter& e, const TrajIn& in, bool want_ll, double t, double val, double dval) {
-  const MeasDesc& md = *in.md;
-  const int n_t = md.n_t;
-  const ivec lane = lane_id();
-  History& H = e.H;
-  H.t[0] = H.t[1]; H.v[0] = H.v[1]; H.d[0] = H.d[1];
-  H.t[1] = H.t[2]; H.v[1] = H.v[2]; H.d[1] = H.d[2];
-  H.t[2] = t; H.v[2] = val; H.d[2] = dval;
-  if (H.n < 3) ++H.n;
-  HermiteCoef hc;
-  bool have_hc = false;
-  while (e.io < n_t) {
-    const ivec k = iadd(lane, e.io);
-    const mask in_range = k < n_t;
-    const real tq = gather(in.times, k, in_range, DBL_MAX);
-    const unsigned bits = warp_ballot(mand(in_range, tq <= t));
-    if (bits == 0u) break;
-    int cnt = 0;
-    { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }
-    real y;
-    if (H.n < 2) {
-      y = splat(val);
-    } else {
-      if (!have_hc) { hc = hermite_setup(H); have_hc = true; }
-      y = hermite_guard(H, tq, hermite_eval(hc, tq));
-      y = sel(tq >= t, val, y);
-    }
-    const mask take = lane < cnt;
-    const unsigned low = warp_ballot(mand(take, y < md.min_y));
-    if (low != 0u) {
-      int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
-      y = sel(lane >= firstlow, md.min_y, y);
-      e.floored = true; e.status |= ST_FLOORED;
-    }
-    emitter_accumulate(e, in, want_ll, k, take, y);
-    e.io += cnt;
-    if (cnt < 32 || e.floored) break;
-  }
-  return e.io >= n_t || e.floored;
 }
 
 TRPL_FN void emitter_finish(Emitter& e, const TrajIn& in, bool want_ll, TrajMid& mid) {
@@ -366,15 +307,124 @@ TRPL_FN void emitter_finish(Emitter& e, const TrajIn& in, bool want_ll, TrajMid&
 }
 
 // Deferred emission.  The integration loop only appends (t, S, dS/dt) of every accepted step to a
-// per-warp history buffer; this routine replays the buffer.  It is deliberately NOT inlined: the
-// interpolation and likelihood arithmetic (log, exp, log10, gathers, ballots) then cannot disturb
-// the register allocation of the hot loop, and nothing it needs is live there.
-TRPL_NOINLINE void emit_history(const TrajIn& in, bool want_ll, const double* hist, int n, Emitter& e) {
-  for (int i = 0; i < n; ++i) {
-    if (emitter_step(e, in, want_ll, hist[3 * i], hist[3 * i + 1], hist[3 * i + 2])) break;
+// per-warp log; this routine evaluates the measurement times the log covers, 32 at a time: every
+// lane finds the step that contains its time by bisection of the log, interpolates
+// (hermite_lane), applies the min_y floor (forward_solver.py:190-192: from the first value below
+// min_y on, the curve IS min_y) and accumulates the likelihood sums.  It is deliberately NOT
+// inlined: the interpolation and likelihood arithmetic (log, exp, log10, gathers, ballots) then
+// cannot disturb the register allocation of the hot loop, and nothing it needs is live there.
+// With `carry` (the log is full, the trajectory goes on) the last two entries move to the front
+// so that later times can still see the two step points before their own step.
+TRPL_NOINLINE void emit_history(const TrajIn& in, bool want_ll, double* hist, int n, Emitter& e, bool carry) {
+  const MeasDesc& md = *in.md;
+  const int n_t = md.n_t;
+  const ivec lane = lane_id();
+  const double t_last = (n > 0) ? hist[3 * (n - 1)] : -1.0;
+  while (n > 0 && e.io < n_t && !e.floored) {
+    const ivec k = iadd(lane, e.io);
+    const mask in_range = k < n_t;
+    const real tq = gather(in.times, k, in_range, DBL_MAX);
+    const unsigned bits = warp_ballot(mand(in_range, tq <= t_last));
+    if (bits == 0u) break;
+    int cnt = 0;
+    { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }     // times ascend: the ready lanes are a prefix
+    const mask take = lane < cnt;
+    const real tqe = sel(take, tq, t_last);                        // idle lanes: a harmless exact hit
+    // newest point of the containing step: the first log entry with t >= tq
+    ivec pos = isplat(-1);
+    for (int step = HIST_CAP / 2; step > 0; step >>= 1) {
+      const ivec cand = iadd(pos, step);
+      const mask ok = cand < n;
+      const real tc = gather(hist, imul(cand, 3), ok, DBL_MAX);
+      pos = seli(mand(ok, tc < tqe), cand, pos);
+    }
+    const ivec i2 = iclamp(iadd(pos, 1), 0, n - 1);
+    const ivec i1 = iclamp(iadd(i2, -1), 0, n - 1), i0 = iclamp(iadd(i2, -2), 0, n - 1);
+    const mask all = mconst(true);
+    const real t2 = gather(hist, imul(i2, 3), all, 0.0), y2 = gather(hist, iadd(imul(i2, 3), 1), all, 0.0),
+               s2 = gather(hist, iadd(imul(i2, 3), 2), all, 0.0);
+    const real t1 = gather(hist, imul(i1, 3), all, 0.0), y1 = gather(hist, iadd(imul(i1, 3), 1), all, 0.0),
+               s1 = gather(hist, iadd(imul(i1, 3), 2), all, 0.0);
+    const real t0 = gather(hist, imul(i0, 3), all, 0.0), y0 = gather(hist, iadd(imul(i0, 3), 1), all, 0.0),
+               s0 = gather(hist, iadd(imul(i0, 3), 2), all, 0.0);
+    const ivec g = iadd(i2, e.base);                               // global index of the step's end point
+    // lanes with fewer than two points (g == 0: the initial state) or an exact hit take the logged value
+    const mask two = mand(g >= 1, i2 >= 1);
+    real y = hermite_lane(tqe, mand(g >= 2, i2 >= 2), t0, y0, s0, sel(two, t1, t2 - 1.0), y1, s1, t2, y2, s2);
+    y = sel(mor(mnot(two), tqe >= t2), y2, y);
+    const unsigned low = warp_ballot(mand(take, y < md.min_y));
+    if (low != 0u) {
+      int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
+      y = sel(lane >= firstlow, md.min_y, y);
+      e.floored = true; e.status |= ST_FLOORED;
+    }
+    emitter_accumulate(e, in, want_ll, k, take, y);
+    e.io += cnt;
+    if (cnt < 32) break;
+  }
+  if (carry && n >= 4) {
+    const real v = gather(hist, iadd(lane, 3 * (n - 2)), lane < 6, 0.0);
+    warp_sync();
+    scatter(hist, lane, lane < 6, v);
+    warp_sync();
+    e.base += n - 2;
   }
 }
 
+// append one accepted step to the log (flushing it when full); returns true once the floor was hit
+TRPL_FN bool log_point(const TrajIn& in, bool want_ll, Emitter& em, int& nh, double t, double val, double dval) {
+  if (nh == HIST_CAP) {
+    warp_sync();
+    emit_history(in, want_ll, in.hist, nh, em, true);
+    nh = 2;
+    if (em.floored) return true;
+  }
+  const ivec lane = lane_id();
+  scatter(in.hist, iadd(lane, 3 * nh), lane < 3, sel(lane == 0, t, sel(lane == 1, val, dval)));
+  ++nh;
+  return false;
+}
+
+// ---- stage combinations with compile-time coefficients ---------------------------------------
+// After stage S-1 (0-based) has produced K_{S-1} (`kk`, still in registers; older increments come
+// back from shared memory) build the argument and the c-combination of stage S:
+//     us = u + sum_{p<S} a_Sp K_p ,   cs = sum_{p<S} (c_Sp / h) K_p .
+// One instantiation per stage: the coefficients are immediates, every load is issued up front and
+// there is no loop control (the generic loop cost 10% of the kernel in branches and constant loads).
+template <int S, int P, int NPL, int MODEL>
+TRPL_FN void combine_term(const LaneMem& sm, double ih, Vec<NPL, MODEL>& us, Vec<NPL, MODEL>& cs) {
+  typedef Slots<NPL, MODEL> SL;
+  constexpr double a = Rodas4::A[S][P];
+  const double cc = Rodas4::C[S][P] * ih;
+  Vec<NPL, MODEL> kp;
+  load_k<NPL, MODEL>(sm, SL::KBASE + P * SL::KSTRIDE, kp);
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+    us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
+    cs.n[j] = fmadd(cc, kp.n[j], cs.n[j]); cs.q[j] = fmadd(cc, kp.q[j], cs.q[j]);
+    if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kp.t[j], us.t[j]); cs.t[j] = fmadd(cc, kp.t[j], cs.t[j]); }
+  }
+}
+template <int S, int NPL, int MODEL>
+TRPL_FN void stage_combine(LaneMem& sm, double ih, const Vec<NPL, MODEL>& u, const Vec<NPL, MODEL>& kk,
+                           Vec<NPL, MODEL>& us, Vec<NPL, MODEL>& cs) {
+  {
+    constexpr double a = Rodas4::A[S][S - 1];
+    const double cc = Rodas4::C[S][S - 1] * ih;
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+      us.n[j] = fmadd(a, kk.n[j], u.n[j]); us.q[j] = fmadd(a, kk.q[j], u.q[j]);
+      cs.n[j] = cc * kk.n[j]; cs.q[j] = cc * kk.q[j];
+      if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kk.t[j], u.t[j]); cs.t[j] = cc * kk.t[j]; }
+    }
+  }
+  if constexpr (S >= 2) combine_term<S, 0, NPL, MODEL>(sm, ih, us, cs);
+  if constexpr (S >= 3) combine_term<S, 1, NPL, MODEL>(sm, ih, us, cs);
+  if constexpr (S >= 4) combine_term<S, 2, NPL, MODEL>(sm, ih, us, cs);
+  if constexpr (S >= 5) combine_term<S, 3, NPL, MODEL>(sm, ih, us, cs);
+  // Row 6 of A is row 5 plus e_5, so the new state is (argument of stage 6) + K_6.  K_1..K_5 are
+  // dead once this combination is formed: park the stage-6 argument in K_1's slot instead of
+  // rebuilding it from five increments at the end of the step.
+  if constexpr (S == 5) store_k<NPL, MODEL>(sm, Slots<NPL, MODEL>::KBASE, us);
+}
 // ---- the trajectory -------------------------------------------------------------------------
 // Control flow is a small state machine so that the right-hand side, the readout/emit block and the
 // linear solve each exist at exactly ONE code site (the kernel is instruction-cache sensitive):
@@ -452,8 +502,8 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   emitter_init(em);
 
   double h = 0.0, h_new = 0.0, gi = 0.0, ih = 0.0;
-  float err_old = 1e-4f;
-  double h_acc = 0.0;
+  float err2_old = 1e-8f;           // squared error norm of the last accepted step (floored at 1e-4)
+  double ih_acc = 0.0;              // 1 / (size of the last accepted step)
   bool first = true, last_rejected = false, final_step = false;
   const double inv_n = 1.0 / (2.0 * L + ((MODEL == MODEL_TRAPS) ? L : 0));
   const double h_min = 1e-14 * fmax(tend, 1e-300);
@@ -477,14 +527,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
         // ---- newly accepted state (us == u): read the signal out and log it ----
         double val, dval;
         readout<NPL, MODEL>(cr, m, md.meas_type, u, r, aux, val, dval);
-        if (nh == HIST_CAP) {
-          warp_sync();
-          emit_history(in, want_ll, in.hist, nh, em);
-          nh = 0;
-          if (em.floored) break;
-        }
-        scatter(in.hist, iadd(lane, 3 * nh), lane < 3, sel(lane == 0, t, sel(lane == 1, val, dval)));
-        ++nh;
+        if (log_point(in, want_ll, em, nh, t, val, dval)) break;
         // done when the last measurement time is reached, or the signal fell through its floor
         // (forward_solver.py:190-192: the rest of the curve is min_y by definition)
         if (t >= tend || val < min_y) break;
@@ -502,7 +545,6 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
           h = (d1 > 0.0 && d0 > 0.0) ? 0.01 * d0 / d1 : 1e-6;
           h = fmin(h, 1e-3 * fmax(tend, 1e-300));
           if (!(h > 0.0)) h = 1e-6;
-          h_acc = h;
         } else {
           h = h_new;
         }
@@ -515,8 +557,8 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       final_step = false;
       if (t + 1.01 * h >= tend) { h = tend - t; final_step = true; }
       if (h < h_min) { status |= ST_H_UNDERFLOW; break; }
-      gi = 1.0 / (RODAS4_GAMMA * h);
-      ih = 1.0 / h;
+      ih = uni(rcp(splat(h)));
+      gi = (1.0 / RODAS4_GAMMA) * ih;
       {
         // W = 1/(gamma h) I - J, factorised
         Blk A[NPL], B[NPL], C[NPL];
@@ -589,80 +631,64 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
       // ---- keep K_s, build the next stage argument and c-combination ----
       store_k<NPL, MODEL>(sm, SL::KBASE + s * SL::KSTRIDE, kk);
       ++s;
-      // the newest increment is still in registers; older ones come back from shared memory
-      {
-        const double a = RODAS4_A[s][s - 1], cc = RODAS4_C[s][s - 1] * ih;
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          us.n[j] = fmadd(a, kk.n[j], u.n[j]); us.q[j] = fmadd(a, kk.q[j], u.q[j]);
-          cs.n[j] = cc * kk.n[j]; cs.q[j] = cc * kk.q[j];
-          if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kk.t[j], u.t[j]); cs.t[j] = cc * kk.t[j]; }
-        }
-      }
-      for (int p = 0; p < s - 1; ++p) {
-        const double a = RODAS4_A[s][p], cc = RODAS4_C[s][p] * ih;
-        V kp;
-        load_k<NPL, MODEL>(sm, SL::KBASE + p * SL::KSTRIDE, kp);
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
-          cs.n[j] = fmadd(cc, kp.n[j], cs.n[j]); cs.q[j] = fmadd(cc, kp.q[j], cs.q[j]);
-          if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kp.t[j], us.t[j]); cs.t[j] = fmadd(cc, kp.t[j], cs.t[j]); }
-        }
+      switch (s) {
+        case 1: stage_combine<1, NPL, MODEL>(sm, ih, u, kk, us, cs); break;
+        case 2: stage_combine<2, NPL, MODEL>(sm, ih, u, kk, us, cs); break;
+        case 3: stage_combine<3, NPL, MODEL>(sm, ih, u, kk, us, cs); break;
+        case 4: stage_combine<4, NPL, MODEL>(sm, ih, u, kk, us, cs); break;
+        default: stage_combine<5, NPL, MODEL>(sm, ih, u, kk, us, cs); break;
       }
       phase = PH_STAGE;
       continue;
     }
 
-    // ---- stage 6 done: u_new = u + sum_j m_j K_j, m = (a_6j, 1); the error estimate is K_6 ----
-    // (the stage argument `us` is rebuilt from the stored increments here so that it is not live
-    //  across the solves)
+    // ---- stage 6 done: u_new = u + sum_j m_j K_j = (stage-6 argument, parked by stage_combine<5>)
+    // + K_6; the error estimate is K_6 ----
+    load_k<NPL, MODEL>(sm, SL::KBASE, us);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      us.n[j] = u.n[j] + kk.n[j]; us.q[j] = u.q[j] + kk.q[j];
-      if (MODEL == MODEL_TRAPS) us.t[j] = u.t[j] + kk.t[j];
+      us.n[j] = us.n[j] + kk.n[j]; us.q[j] = us.q[j] + kk.q[j];
+      if (MODEL == MODEL_TRAPS) us.t[j] = us.t[j] + kk.t[j];
     }
-    TRPL_UNROLL for (int p = 0; p < 5; ++p) {
-      const double a = RODAS4_A[5][p];
-      V kp;
-      load_k<NPL, MODEL>(sm, SL::KBASE + p * SL::KSTRIDE, kp);
-      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-        us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
-        if (MODEL == MODEL_TRAPS) us.t[j] = fmadd(a, kp.t[j], us.t[j]);
-      }
-    }
+    // error norm: the scales only steer the step size, so their reciprocals are the 2^-23 hardware
+    // seed and the max() has no NaN bookkeeping (non-finite states are caught by `bad`)
     real esum = splat(0.0);
     mask bad = mconst(false);
     real pold[NPL];
     holes<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, u, pold);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      const real iscn = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(us.n[j])), opt.atol));
-      const real iscq = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(pold[j])), opt.atol));
+      const real iscn = rcp_approx(fmadd(opt.rtol, vmax_fast(vabs(u.n[j]), vabs(us.n[j])), opt.atol));
+      const real iscq = rcp_approx(fmadd(opt.rtol, vmax_fast(vabs(u.n[j]), vabs(pold[j])), opt.atol));
       const real en = kk.n[j] * iscn, eq = kk.q[j] * (iscq * Q_ERR_WEIGHT);
       real e2 = fmadd(en, en, eq * eq);
       if (MODEL == MODEL_TRAPS) {
-        const real isct = rcp(fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(us.t[j]), vabs(u.n[j]))), opt.atol));
+        const real isct = rcp_approx(fmadd(opt.rtol, vmax_fast(vabs(u.t[j]), vmax_fast(vabs(us.t[j]), vabs(u.n[j]))), opt.atol));
         const real et = kk.t[j] * isct;
         e2 = fmadd(et, et, e2);
       }
       esum = esum + sel(m.real_node[j], e2, 0.0);
       bad = mor(bad, mand(m.real_node[j], mor(is_nan(us.n[j]), is_nan(us.q[j]))));
     }
-    const double err2 = uni(warp_sum(esum)) * inv_n;
+    const double err2 = uni(warp_sum(esum)) * inv_n;            // err^2
     const bool nonfinite = warp_any(bad) || !(err2 == err2) || err2 > 1e300;
-    const double err = nonfinite ? 1e10 : sqrt(err2);
 
     // ---- controller (Hairer's RODAS: standard + Gustafsson predictive) ----
-    // step-size factor in single precision (it only steers h)
-    const float errf = (float)fmin(err, 1e30);
-    float fac = fmaxf(0.2f, fminf(6.0f, sqrtf(sqrtf(errf)) * (1.0f / 0.9f)));
-    h_new = h / (double)fac;
-    if (err <= 1.0) {
+    // Single precision, no divisions or square roots: with e2 = err^2 the standard factor is
+    //   h_new / h = 0.9 err^(-1/4) = 0.9 e2^(-1/8)           clamped to [1/6, 5],
+    // the predictive one (after an accepted step of size h_acc with error err_old)
+    //   h_new / h = 0.9 (h / h_acc) (err_old / err^2)^(1/4) = 0.9 (h / h_acc) e2^(-1/4) e2_old^(1/8),
+    // and the smaller of the two is taken.
+    const float e2f = nonfinite ? 1e20f : (float)fmax(fmin(err2, 1e30), 1e-30);
+    float ifac = fmaxf(1.0f / 6.0f, fminf(5.0f, 0.9f * ctl_powf(e2f, -0.125f)));
+    h_new = h * (double)ifac;
+    if (!nonfinite && err2 <= 1.0) {
       ++n_acc;
       if (!first) {
-        float fg = (float)(h_acc / h) * sqrtf(sqrtf(errf * errf / err_old)) * (1.0f / 0.9f);
-        fg = fmaxf(0.2f, fminf(6.0f, fg));
-        fac = fmaxf(fac, fg);
-        h_new = h / (double)fac;
+        float ifg = 0.9f * (float)(h * ih_acc) * ctl_powf(e2f, -0.25f) * ctl_powf(err2_old, 0.125f);
+        ifg = fmaxf(1.0f / 6.0f, fminf(5.0f, ifg));
+        ifac = fminf(ifac, ifg);
+        h_new = h * (double)ifac;
       }
-      first = false; h_acc = h; err_old = fmaxf(1e-2f, errf);
+      first = false; ih_acc = ih; err2_old = fmaxf(1e-4f, e2f);
       if (last_rejected) h_new = fmin(h_new, h);
       last_rejected = false;
       t = final_step ? tend : t + h;
@@ -685,7 +711,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, LaneMem& sm
   // replay the logged steps: measurement times, floor, likelihood sums; anything not reached
   // (floor, or integrator failure) is min_y: forward_solver.py:168 + :190-192
   warp_sync();
-  emit_history(in, want_ll, in.hist, nh, em);
+  emit_history(in, want_ll, in.hist, nh, em, false);
   emitter_finish(em, in, want_ll, mid);
   out.status = status | em.status; out.n_acc = n_acc; out.n_rej = n_rej;
   return false;

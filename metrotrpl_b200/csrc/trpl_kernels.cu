@@ -273,12 +273,16 @@ int launch_npl(trpl_handle* h, const KernelArgs& a) {
   const int nx = h->max_nx;
   // the padding-free instantiation exists for the headline grid (nx = 128) and nx = 256
   if (h->all_full && nx == 128) return launch<4, MODEL, true>(h, a);
+#ifdef TRPL_DEV_HEADLINE_ONLY   // developer builds of tuning variants: compile one instantiation only
+  return fail("this developer build only holds the nx=128 instantiation");
+#else
   if (h->all_full && nx == 256) return launch<8, MODEL, true>(h, a);
   if (nx <= 32) return launch<1, MODEL, false>(h, a);
   if (nx <= 64) return launch<2, MODEL, false>(h, a);
   if (nx <= 128) return launch<4, MODEL, false>(h, a);
   if (nx <= 256) return launch<8, MODEL, false>(h, a);
   return fail("nx > 256 is not supported by this build");
+#endif
 }
 
 }  // namespace
@@ -517,7 +521,11 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
   a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;
   memcpy(&a.opt, opts, sizeof(SolverOpts));
   if (h->model == TRPL_MODEL_STD) return launch_npl<MODEL_STD>(h, a);
+#ifdef TRPL_DEV_HEADLINE_ONLY
+  return fail("this developer build only holds the 'std' model");
+#else
   return launch_npl<MODEL_TRAPS>(h, a);
+#endif
 }
 
 int trpl_download_results(trpl_handle* h, double* logll, int32_t* status, int32_t* nsteps, double* curves) {
