@@ -86,18 +86,25 @@ TRPL_FN V2 add_mv(const V2& r, const Blk& m, const V2& v) {
 template <int NPL>
 struct FacSlots {
   static constexpr int NI = NPL - 1;                 // interior rows per lane
+  // first run: what the forward/backward interior sweep and the reduced right-hand side read
   static constexpr int DINV = 0;                     // NI blocks
   static constexpr int LMUL = DINV + 2 * NI;         // NI-1 blocks (rows 1..NI-1)
   static constexpr int CSUP = LMUL + 2 * (NI > 0 ? NI - 1 : 0);   // NI blocks
-  static constexpr int VSPK = CSUP + 2 * NI;         // NI blocks
-  static constexpr int WSPK = VSPK + 2 * NI;         // NI blocks
-  static constexpr int AZ = WSPK + 2 * NI;           // 1 block
+  static constexpr int AZ = CSUP + 2 * NI;           // 1 block
   static constexpr int CZ = AZ + 2;                  // 1 block
-  static constexpr int COUNT = CZ + 2;               // pairs
+  static constexpr int RUN1 = CZ + 2;                // pairs in the first run
+  // second run: the spikes, read after the reduced solve
+  static constexpr int VSPK = RUN1;                  // NI blocks
+  static constexpr int WSPK = VSPK + 2 * NI;         // NI blocks
+  static constexpr int RUN2 = 4 * NI;
+  static constexpr int COUNT = RUN1 + RUN2;          // pairs
 };
 
+// a block of the lane exchange (shared memory)
 TRPL_FN void st_blk(LaneMem& sm, int p, const Blk& b) { sm.st2(p, b.a00, b.a01); sm.st2(p + 1, b.a10, b.a11); }
-TRPL_FN Blk ld_blk(const LaneMem& sm, int p) { Blk b; sm.ld2(p, b.a00, b.a01); sm.ld2(p + 1, b.a10, b.a11); return b; }
+// a block inside a run of factor values staged in registers (pair index p of the run)
+TRPL_FN void put_blk(real* v, int p, const Blk& b) { v[2 * p] = b.a00; v[2 * p + 1] = b.a01; v[2 * p + 2] = b.a10; v[2 * p + 3] = b.a11; }
+TRPL_FN Blk get_blk(const real* v, int p) { Blk b; b.a00 = v[2 * p]; b.a01 = v[2 * p + 1]; b.a10 = v[2 * p + 2]; b.a11 = v[2 * p + 3]; return b; }
 TRPL_FN Blk ld_blk_from(const LaneMem& sm, int p, const ivec& src) {
   Blk b; sm.ld2_from(p, src, b.a00, b.a01); sm.ld2_from(p + 1, src, b.a10, b.a11); return b;
 }
@@ -115,11 +122,11 @@ struct PcrFac {
   Blk binv;
 };
 
-// Factorise W given by (A, B, C) blocks of this lane's rows.  `base` is the first pair to use,
-// `xch` 12 scratch pairs for the lane exchange.
-template <int NPL>
-TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[NPL], LaneMem& sm,
-                       int base, int xch, PcrFac& pf) {
+// Factorise W given by (A, B, C) blocks of this lane's rows.  `fm`/`base`: lane-private factor
+// storage and its first pair; `sm`/`xch`: 12 shared-memory scratch pairs for the lane exchange.
+template <int NPL, class FM>
+TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[NPL], FM& fm,
+                       int base, LaneMem& sm, int xch, PcrFac& pf) {
   typedef FacSlots<NPL> S;
   constexpr int NI = NPL - 1;
   Blk ra, rb, rc;
@@ -140,15 +147,24 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
       v[j] = blk_mul(dinv[j], blk_sub(v[j], blk_mul(C[j], v[j + 1])));
       w[j] = blk_mul_neg(dinv[j], blk_mul(C[j], w[j + 1]));
     }
-    TRPL_UNROLL for (int j = 0; j < NI; ++j) {
-      st_blk(sm, base + S::DINV + 2 * j, dinv[j]);
-      if (j > 0) st_blk(sm, base + S::LMUL + 2 * (j - 1), lm[j]);
-      st_blk(sm, base + S::CSUP + 2 * j, C[j]);
-      st_blk(sm, base + S::VSPK + 2 * j, v[j]);
-      st_blk(sm, base + S::WSPK + 2 * j, w[j]);
+    // the factor blocks leave in two runs of consecutive pairs (widest stores the memory has)
+    {
+      real f1[2 * S::RUN1];
+      TRPL_UNROLL for (int j = 0; j < NI; ++j) {
+        put_blk(f1, S::DINV + 2 * j, dinv[j]);
+        if (j > 0) put_blk(f1, S::LMUL + 2 * (j - 1), lm[j]);
+        put_blk(f1, S::CSUP + 2 * j, C[j]);
+      }
+      put_blk(f1, S::AZ, A[NPL - 1]);
+      put_blk(f1, S::CZ, C[NPL - 1]);
+      mem_st_pairs<S::RUN1>(fm, base, f1);
+      real f2[2 * S::RUN2];
+      TRPL_UNROLL for (int j = 0; j < NI; ++j) {
+        put_blk(f2, 2 * j, v[j]);
+        put_blk(f2, 2 * NI + 2 * j, w[j]);
+      }
+      mem_st_pairs<S::RUN2>(fm, base + S::RUN1, f2);
     }
-    st_blk(sm, base + S::AZ, A[NPL - 1]);
-    st_blk(sm, base + S::CZ, C[NPL - 1]);
     // reduced (interface) row of this lane
     const Blk v0n = blk_shfl_down(v[0], 1);
     const Blk w0n = blk_shfl_down(w[0], 1);
@@ -185,8 +201,8 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
 }
 
 // Solve W x = r in place.  r[j] / x[j] are this lane's NPL block rows; `xch` = 2 scratch pairs.
-template <int NPL>
-TRPL_FN void bt_solve(V2 (&r)[NPL], LaneMem& sm, int base, int xch, const PcrFac& pf) {
+template <int NPL, class FM>
+TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch, const PcrFac& pf) {
   typedef FacSlots<NPL> S;
   constexpr int NI = NPL - 1;
   V2 g[NI > 0 ? NI : 1];
@@ -194,12 +210,19 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], LaneMem& sm, int base, int xch, const PcrFac
   if constexpr (NI > 0) {
     // every factor block of the interior sweep is fetched up front (independent of r)
     Blk dinv[NI], csup[NI], lm[NI > 1 ? NI - 1 : 1];
-    TRPL_UNROLL for (int j = 0; j < NI; ++j) {
-      dinv[j] = ld_blk(sm, base + S::DINV + 2 * j);
-      csup[j] = ld_blk(sm, base + S::CSUP + 2 * j);
-      if (j > 0) lm[j - 1] = ld_blk(sm, base + S::LMUL + 2 * (j - 1));
+    Blk az, cz;
+    {
+      real f1[2 * S::RUN1];
+      mem_wait_st(fm);
+      mem_ld_pairs<S::RUN1>(fm, base, f1);
+      mem_wait_ld(fm);
+      TRPL_UNROLL for (int j = 0; j < NI; ++j) {
+        dinv[j] = get_blk(f1, S::DINV + 2 * j);
+        csup[j] = get_blk(f1, S::CSUP + 2 * j);
+        if (j > 0) lm[j - 1] = get_blk(f1, S::LMUL + 2 * (j - 1));
+      }
+      az = get_blk(f1, S::AZ); cz = get_blk(f1, S::CZ);
     }
-    const Blk az = ld_blk(sm, base + S::AZ), cz = ld_blk(sm, base + S::CZ);
     g[0] = r[0];
     TRPL_UNROLL for (int j = 1; j < NI; ++j) g[j] = sub_mv(r[j], lm[j - 1], g[j - 1]);
     g[NI - 1] = blk_mv(dinv[NI - 1], g[NI - 1]);
@@ -227,7 +250,12 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], LaneMem& sm, int base, int xch, const PcrFac
   if constexpr (NI > 0) {
     // spike blocks first, then the arithmetic
     Blk vs[NI], ws[NI];
-    TRPL_UNROLL for (int j = 0; j < NI; ++j) { vs[j] = ld_blk(sm, base + S::VSPK + 2 * j); ws[j] = ld_blk(sm, base + S::WSPK + 2 * j); }
+    {
+      real f2[2 * S::RUN2];
+      mem_ld_pairs<S::RUN2>(fm, base + S::RUN1, f2);
+      mem_wait_ld(fm);
+      TRPL_UNROLL for (int j = 0; j < NI; ++j) { vs[j] = get_blk(f2, 2 * j); ws[j] = get_blk(f2, 2 * NI + 2 * j); }
+    }
     V2 zl; zl.x = shfl_up(z.x, 1); zl.y = shfl_up(z.y, 1);   // lane 0: V is zero there
     TRPL_UNROLL for (int j = 0; j < NI; ++j) r[j] = sub_mv(sub_mv(g[j], vs[j], zl), ws[j], z);
   }

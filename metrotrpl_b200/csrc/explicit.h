@@ -92,7 +92,7 @@ TRPL_CONST double DP_E[7] = {71.0 / 57600.0, 0.0, -71.0 / 16695.0, 71.0 / 1920.0
                              22.0 / 525.0, -1.0 / 40.0};
 
 template <int NPL, int MODEL, bool FULL>
-TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, LaneMem& sm, TrajOut& out,
+TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, TrajMem& mem, TrajOut& out,
                                      TrajMid& mid) {
   typedef Slots<NPL, MODEL> SL;
   typedef Vec<NPL, MODEL> V;
@@ -110,7 +110,8 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, La
   double t = 0.0, h = 0.0;
   const double inv_n = 1.0 / (2.0 * L + ((MODEL == MODEL_TRAPS) ? L : 0));
   const double h_min = 1e-14 * fmax(tend, 1e-300);
-  static_assert(7 * SL::KSTRIDE <= SL::COUNT, "stage storage does not fit the warp's shared-memory slice");
+  static_assert(7 * SL::KSTRIDE <= SL::KCAP, "stage storage does not fit the memory that holds the increments");
+  auto& km = kmem<SL>(mem);
 
   // k1 = f(u)
   V k1; RhsAux<NPL> aux;
@@ -139,7 +140,7 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, La
     bool final_step = false;
     if (t + 1.01 * h >= tend) { h = tend - t; final_step = true; }
     if (h < h_min) { em.status |= ST_H_UNDERFLOW; break; }
-    store_k<NPL, MODEL>(sm, SL::KBASE, k1);
+    store_k<NPL, MODEL>(km, SL::KBASE, k1);
     V us, kk;
     for (int s = 1; s < 7; ++s) {
       TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
@@ -150,14 +151,14 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, La
       for (int p = 0; p < s; ++p) {
         const double a = DP_A[s][p] * h;
         V kp;
-        load_k<NPL, MODEL>(sm, SL::KBASE + p * SL::KSTRIDE, kp);
+        load_k<NPL, MODEL>(km, SL::KBASE + p * SL::KSTRIDE, kp);
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
           us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
           if (MODEL == MODEL_TRAPS) us.t[j] = fmadd(a, kp.t[j], us.t[j]);
         }
       }
       rhs<NPL, MODEL>(c, m, us, kk, aux);
-      store_k<NPL, MODEL>(sm, SL::KBASE + s * SL::KSTRIDE, kk);
+      store_k<NPL, MODEL>(km, SL::KBASE + s * SL::KSTRIDE, kk);
     }
     // us = u_new (stage 7 argument), kk = f(u_new); error = h sum e_j k_j
     V er;
@@ -165,7 +166,7 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, La
     for (int p = 0; p < 7; ++p) {
       const double e = DP_E[p] * h;
       V kp;
-      load_k<NPL, MODEL>(sm, SL::KBASE + p * SL::KSTRIDE, kp);
+      load_k<NPL, MODEL>(km, SL::KBASE + p * SL::KSTRIDE, kp);
       TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
         er.n[j] = fmadd(e, kp.n[j], er.n[j]); er.q[j] = fmadd(e, kp.q[j], er.q[j]);
         if (MODEL == MODEL_TRAPS) er.t[j] = fmadd(e, kp.t[j], er.t[j]);

@@ -57,6 +57,13 @@ TRPL_FN real rcp(real x) {
   return r;
 }
 TRPL_FN real vdiv(real a, real b) { return a / b; }       // IEEE division (cold paths only)
+// Reciprocal with ONE Newton step (~2^-40 or better)
+TRPL_FN real rcp1(real x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
 // Reciprocal to ~2^-23 (the hardware seed alone): for quantities that only steer the step size.
 TRPL_FN real rcp_approx(real x) {
   double r;
@@ -121,6 +128,89 @@ struct LaneMem {
   TRPL_FN void ust(int p, int i, double v) const { reinterpret_cast<double*>(base + p * 32)[i] = v; }
 };
 TRPL_FN void warp_sync() { __syncwarp(); }
+
+// Per-warp scratch in TENSOR MEMORY (sm_100a TMEM, 128 lanes x 512 columns x 32 bit per SM), used
+// as lane-private storage: warp w of a CTA owns TMEM lanes 32*(w%4)..+31, thread l of the warp
+// reads and writes only its own lane, and pair p of the warp's slice is the four 32-bit columns
+// base+4p..+3 of that lane (tcgen05.ld/st .32x32b).  Nothing here is ever an MMA operand: TMEM is
+// simply a second on-chip memory with its own data path (measured 400 B/clk/SM against the
+// 128 B/clk/SM of shared memory, tools/proto/tmem_probe.cu), which takes the lane-private traffic
+// (stage increments, factor blocks) off the shared-memory pipe.  Loads are asynchronous: issue a
+// batch, then wait_ld() before the first use; wait_st() before re-reading what was just stored.
+struct LaneTm {
+  unsigned base;     // (first lane of this warp's quarter << 16) | first column of its slice
+  TRPL_FN void st2(int p, real a, real b) const {
+    asm volatile("{\n .reg .b32 t0,t1,t2,t3;\n mov.b64 {t0,t1}, %1;\n mov.b64 {t2,t3}, %2;\n"
+                 " tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {t0,t1,t2,t3};\n}"
+                 :: "r"(base + 4u * (unsigned)p), "d"(a), "d"(b) : "memory");
+  }
+  TRPL_FN void ld2(int p, real& a, real& b) const {
+    asm volatile("{\n .reg .b32 t0,t1,t2,t3;\n tcgen05.ld.sync.aligned.32x32b.x4.b32 {t0,t1,t2,t3}, [%2];\n"
+                 " mov.b64 %0, {t0,t1};\n mov.b64 %1, {t2,t3};\n}"
+                 : "=d"(a), "=d"(b) : "r"(base + 4u * (unsigned)p) : "memory");
+  }
+  // two / four consecutive pairs per instruction.  A tcgen05.ld/st costs the tensor-memory pipe
+  // about the same whether it moves 4 or 16 columns (measured: ~5.5 clk per instruction per SM), so
+  // everything is laid out to move in .x16 groups: four pairs = 64 bytes per lane.
+  TRPL_FN void st4(int p, const real* v) const {
+    asm volatile("{\n .reg .b32 t0,t1,t2,t3,t4,t5,t6,t7;\n mov.b64 {t0,t1}, %1;\n mov.b64 {t2,t3}, %2;\n"
+                 " mov.b64 {t4,t5}, %3;\n mov.b64 {t6,t7}, %4;\n"
+                 " tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7};\n}"
+                 :: "r"(base + 4u * (unsigned)p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+  }
+  TRPL_FN void ld4(int p, real* v) const {
+    asm volatile("{\n .reg .b32 t0,t1,t2,t3,t4,t5,t6,t7;\n"
+                 " tcgen05.ld.sync.aligned.32x32b.x8.b32 {t0,t1,t2,t3,t4,t5,t6,t7}, [%4];\n"
+                 " mov.b64 %0, {t0,t1};\n mov.b64 %1, {t2,t3};\n mov.b64 %2, {t4,t5};\n mov.b64 %3, {t6,t7};\n}"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "r"(base + 4u * (unsigned)p) : "memory");
+  }
+  TRPL_FN void st8(int p, const real* v) const {
+    asm volatile("{\n .reg .b32 t<16>;\n mov.b64 {t0,t1}, %1;\n mov.b64 {t2,t3}, %2;\n mov.b64 {t4,t5}, %3;\n"
+                 " mov.b64 {t6,t7}, %4;\n mov.b64 {t8,t9}, %5;\n mov.b64 {t10,t11}, %6;\n mov.b64 {t12,t13}, %7;\n"
+                 " mov.b64 {t14,t15}, %8;\n"
+                 " tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15};\n}"
+                 :: "r"(base + 4u * (unsigned)p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]), "d"(v[4]), "d"(v[5]),
+                    "d"(v[6]), "d"(v[7]) : "memory");
+  }
+  TRPL_FN void ld8(int p, real* v) const {
+    asm volatile("{\n .reg .b32 t<16>;\n"
+                 " tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n"
+                 " mov.b64 %0, {t0,t1};\n mov.b64 %1, {t2,t3};\n mov.b64 %2, {t4,t5};\n mov.b64 %3, {t6,t7};\n"
+                 " mov.b64 %4, {t8,t9};\n mov.b64 %5, {t10,t11};\n mov.b64 %6, {t12,t13};\n mov.b64 %7, {t14,t15};\n}"
+                 : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]), "=d"(v[4]), "=d"(v[5]), "=d"(v[6]), "=d"(v[7])
+                 : "r"(base + 4u * (unsigned)p) : "memory");
+  }
+  TRPL_FN void wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+#ifdef TRPL_TM_NO_WAIT_ST
+  TRPL_FN void wait_st() const {}
+#else
+  TRPL_FN void wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+#endif
+};
+// the same interface on shared memory, so that a region can live in either
+TRPL_FN void mem_wait_ld(const LaneMem&) {}
+TRPL_FN void mem_wait_st(const LaneMem&) {}
+TRPL_FN void mem_wait_ld(const LaneTm& t) { t.wait_ld(); }
+TRPL_FN void mem_wait_st(const LaneTm& t) { t.wait_st(); }
+// N consecutive pairs <-> 2N values, in the widest moves the memory has
+template <int N> TRPL_FN void mem_ld_pairs(const LaneMem& m, int p, real* v) {
+  TRPL_UNROLL for (int i = 0; i < N; ++i) m.ld2(p + i, v[2 * i], v[2 * i + 1]);
+}
+template <int N> TRPL_FN void mem_st_pairs(const LaneMem& m, int p, const real* v) {
+  TRPL_UNROLL for (int i = 0; i < N; ++i) m.st2(p + i, v[2 * i], v[2 * i + 1]);
+}
+template <int N> TRPL_FN void mem_ld_pairs(const LaneTm& m, int p, real* v) {
+  constexpr int G = N / 4;
+  TRPL_UNROLL for (int g = 0; g < G; ++g) m.ld8(p + 4 * g, v + 8 * g);
+  if constexpr ((N & 3) >= 2) m.ld4(p + 4 * G, v + 8 * G);
+  if constexpr (N & 1) m.ld2(p + N - 1, v[2 * N - 2], v[2 * N - 1]);
+}
+template <int N> TRPL_FN void mem_st_pairs(const LaneTm& m, int p, const real* v) {
+  constexpr int G = N / 4;
+  TRPL_UNROLL for (int g = 0; g < G; ++g) m.st8(p + 4 * g, v + 8 * g);
+  if constexpr ((N & 3) >= 2) m.st4(p + 4 * G, v + 8 * G);
+  if constexpr (N & 1) m.st2(p + N - 1, v[2 * N - 2], v[2 * N - 1]);
+}
 }  // namespace simt
 
 #else
@@ -182,6 +272,7 @@ inline mask lane_lt(const ivec& l, int k) { return l < k; }
 inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
 template <class A, class B, class C> inline real fmadd(const A& a, const B& b, const C& c) { return fmadd3(real(a), real(b), real(c)); }
 inline real vdiv(const real& a, const real& b) { return a / b; }
+inline real rcp1(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
 inline real rcp_approx(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
 inline real vmax_fast(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] > b.v[i] ? a.v[i] : b.v[i]; return r; }
 inline float ctl_powf(float x, float y) { return powf(x, y); }
@@ -238,5 +329,16 @@ struct LaneMem {
   void ust(int p, int i, double v) { slots[2 * p + (i & 1)].v[i >> 1] = v; }
 };
 inline void warp_sync() {}
+// host stand-in of the tensor-memory slice (see the device half): just another array of pairs
+struct LaneTm {
+  std::vector<real> slots;
+  explicit LaneTm(int n_pairs) : slots(2 * (n_pairs > 0 ? n_pairs : 1)) {}
+  void ld2(int p, real& a, real& b) const { a = slots[2 * p]; b = slots[2 * p + 1]; }
+  void st2(int p, const real& a, const real& b) { slots[2 * p] = a; slots[2 * p + 1] = b; }
+};
+template <class M> inline void mem_wait_ld(const M&) {}
+template <class M> inline void mem_wait_st(const M&) {}
+template <int N, class M> inline void mem_ld_pairs(const M& m, int p, real* v) { for (int i = 0; i < N; ++i) m.ld2(p + i, v[2 * i], v[2 * i + 1]); }
+template <int N, class M> inline void mem_st_pairs(M& m, int p, const real* v) { for (int i = 0; i < N; ++i) m.st2(p + i, v[2 * i], v[2 * i + 1]); }
 }  // namespace simt
 #endif

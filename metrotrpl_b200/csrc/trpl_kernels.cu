@@ -8,6 +8,7 @@
 // (L2-resident, shared by all trajectories) and a handful of result scalars.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -26,7 +27,14 @@ static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch")
 static_assert(sizeof(trpl_solver_opts) == sizeof(SolverOpts), "ABI struct mismatch");
 static_assert(TRPL_NPARAM == trpl::NPARAM, "ABI constant mismatch");
 
-constexpr int WARPS_PER_CTA = 4;
+#ifndef TRPL_WARPS_PER_CTA
+#define TRPL_WARPS_PER_CTA 4
+#endif
+constexpr int WARPS_PER_CTA = TRPL_WARPS_PER_CTA;
+constexpr int CTAS_PER_SM = 8 / WARPS_PER_CTA;     // 8 trajectories per SM (registers)
+#ifndef TRPL_NO_TMEM
+static_assert(WARPS_PER_CTA <= 4, "one warp per tensor-memory lane quarter");
+#endif
 
 struct KernelArgs {
   const double* params;      // [n_sets][16]
@@ -105,12 +113,45 @@ __device__ __forceinline__ void finish_traj(const KernelArgs& a, int traj, int w
   __syncwarp();
 }
 
+// Tensor-memory slice of the calling warp.  One warp of the CTA allocates TM_COLS columns for the
+// CTA (tcgen05.alloc hands out whole columns, all 128 lanes); warp w then owns lanes 32*(w%4)..+31
+// of those columns.  A CTA has at most four warps, so the slices are disjoint.
+template <class SL>
+__device__ __forceinline__ LaneTm tmem_acquire(int warp) {
+  LaneTm tm{0u};
+  if constexpr (SL::TM_COLS > 0) {
+    __shared__ unsigned tm_base_s;
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   :: "r"((unsigned)__cvta_generic_to_shared(&tm_base_s)), "n"(SL::TM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tm.base = tm_base_s + ((unsigned)(32 * (warp & 3)) << 16);
+  }
+  return tm;
+}
+// every warp of the CTA is done with its slice: the allocating warp gives the columns back
+template <class SL>
+__device__ __forceinline__ void tmem_release(int warp, const LaneTm& tm) {
+  if constexpr (SL::TM_COLS > 0) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                   :: "r"(tm.base & 0x0000ffffu), "n"(SL::TM_COLS) : "memory");
+  }
+}
+
 template <int NPL, int MODEL, bool FULL>
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_forward_kernel(const KernelArgs a) {
+  typedef Slots<NPL, MODEL> SL;
   extern __shared__ double2 smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  LaneMem sm{smem + warp * (Slots<NPL, MODEL>::COUNT * 32)};   // COUNT pairs of 16 B per lane
+  TrajMem mem{LaneMem{smem + warp * (SL::COUNT * 32)}, tmem_acquire<SL>(warp)};   // COUNT pairs of 16 B per lane
   const bool allow_defer = a.defer_list != nullptr;
   for (;;) {
     int traj = 0;
@@ -126,21 +167,23 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_forward_kernel(con
     setup_traj(a, traj, warp, in);
     TrajOut out;
     TrajMid mid;
-    if (run_trajectory<NPL, MODEL, FULL>(in, a.opt, sm, out, mid, allow_defer)) {
+    if (run_trajectory<NPL, MODEL, FULL>(in, a.opt, mem, out, mid, allow_defer)) {
       if (lane == 0) a.defer_list[atomicAdd(a.defer_count, 1)] = traj;     // non-stiff: explicit path
       continue;
     }
     finish_traj(a, traj, warp, in, mid, out);
   }
+  tmem_release<SL>(warp, mem.tm);
 }
 
 // second pass over the trajectories the first kernel classified non-stiff
 template <int NPL, int MODEL, bool FULL>
-__global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_explicit_kernel(const KernelArgs a) {
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_explicit_kernel(const KernelArgs a) {
+  typedef Slots<NPL, MODEL> SL;
   extern __shared__ double2 smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  LaneMem sm{smem + warp * (Slots<NPL, MODEL>::COUNT * 32)};
+  TrajMem mem{LaneMem{smem + warp * (SL::COUNT * 32)}, tmem_acquire<SL>(warp)};
   const int n = *a.defer_count;
   for (;;) {
     int q = 0;
@@ -152,10 +195,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, 2) trpl_explicit_kernel(co
     setup_traj(a, traj, warp, in);
     TrajOut out;
     TrajMid mid;
-    run_trajectory_explicit<NPL, MODEL, FULL>(in, a.opt, sm, out, mid);
+    run_trajectory_explicit<NPL, MODEL, FULL>(in, a.opt, mem, out, mid);
     out.status |= ST_EXPLICIT;
     finish_traj(a, traj, warp, in, mid, out);
   }
+  tmem_release<SL>(warp, mem.tm);
 }
 
 // FP64 peak probe: 8 independent FMA chains per thread, no memory traffic.
@@ -223,24 +267,42 @@ namespace {
 
 template <int NPL, int MODEL, bool FULL>
 int launch(trpl_handle* h, KernelArgs a) {
-  // warps per CTA: as many as fit the 227 KB of one CTA (4 for nx <= 128, fewer for the larger grids)
-  const size_t per_warp = Slots<NPL, MODEL>::BYTES;
+  // warps per CTA: at most four (one per tensor-memory lane quarter), fewer if their shared-memory
+  // slices do not fit the 227 KB of one CTA (the larger grids)
+  typedef Slots<NPL, MODEL> SL;
+  const size_t per_warp = SL::BYTES;
   int wpc = WARPS_PER_CTA;
   while (wpc > 1 && (size_t)wpc * per_warp > (size_t)h->prop.sharedMemPerBlockOptin) --wpc;
   if ((size_t)wpc * per_warp > (size_t)h->prop.sharedMemPerBlockOptin)
     return fail("trajectory state does not fit in shared memory");
-  const size_t smem = (size_t)wpc * per_warp;
+  size_t smem = (size_t)wpc * per_warp;
   a.warps_per_cta = wpc;
   auto kern = trpl_forward_kernel<NPL, MODEL, FULL>;
+  // the occupancy calculator assumes the function's current carve-out: ask for the largest one
+  // first, or a small shared-memory request is judged against a small default carve-out
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * wpc, smem));
   if (per_sm < 1) return fail("trajectory kernel does not fit on an SM");
+  // CTAs resident on an SM share its 512 tensor-memory columns (a CTA beyond that would sit in
+  // tcgen05.alloc until another one exits).  The occupancy calculator answers 1 for any kernel
+  // that allocates tensor memory, so residency is computed here: registers and shared memory
+  // (launch bounds), capped by the tensor-memory columns.
+  if (SL::TM_COLS > 0) {
+    const int by_smem = (int)((size_t)h->prop.sharedMemPerMultiprocessor / (smem + 1024 + 16));
+    per_sm = std::min(std::min(CTAS_PER_SM * WARPS_PER_CTA / wpc, by_smem), 512 / SL::TM_COLS);
+    if (per_sm < 1) return fail("trajectory kernel does not fit on an SM");
+  }
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int warps_needed = a.n_traj;
   int grid = h->prop.multiProcessorCount * per_sm;
   const int ctas_needed = (warps_needed + wpc - 1) / wpc;
   if (grid > ctas_needed) grid = ctas_needed;
   if (grid < 1) grid = 1;
+  if (getenv("TRPL_DEBUG"))
+    fprintf(stderr, "[trpl] launch NPL=%d model=%d: %d warps/CTA, %zu B smem/CTA, %d TMEM columns/CTA, %d CTAs/SM, grid %d\n",
+            NPL, MODEL, wpc, smem, SL::TM_COLS, per_sm, grid);
   if (a.scratch) {
     CU(h->d_scratch.reserve((size_t)grid * wpc * a.scratch_stride));
     a.scratch = h->d_scratch.p;
@@ -259,6 +321,7 @@ int launch(trpl_handle* h, KernelArgs a) {
   h->launches += 1;
   if (a.defer_list) {
     auto kern2 = trpl_explicit_kernel<NPL, MODEL, FULL>;
+    CU(cudaFuncSetAttribute(kern2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern2<<<grid, 32 * wpc, smem, h->stream>>>(a);
     CU(cudaGetLastError());

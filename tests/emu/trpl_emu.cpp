@@ -24,7 +24,7 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
   for (int traj = 0; traj < n_traj; ++traj) {
     const int set = traj / n_meas, mi = traj % n_meas;
     const MeasDesc* md = meas + mi;
-    simt::LaneMem sm(Slots<NPL, MODEL>::COUNT);
+    TrajMem sm{simt::LaneMem(Slots<NPL, MODEL>::COUNT), simt::LaneTm(Slots<NPL, MODEL>::TM_COUNT)};
     TrajIn in;
     in.par = params + (size_t)set * TRPL_NPARAM;
     in.md = md;
