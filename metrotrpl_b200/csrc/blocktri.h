@@ -21,6 +21,12 @@
 #include "simt.h"
 #include "model.h"
 
+// Lane exchange of the solves' PCR levels: shuffles (4 x 64 bit per level) or two shared-memory
+// pairs.  Measured on B200 in DESIGN.md section 5.
+#ifndef TRPL_SOLVE_PCR_SHFL
+#define TRPL_SOLVE_PCR_SHFL 0
+#endif
+
 namespace trpl {
 using namespace simt;
 
@@ -116,17 +122,65 @@ TRPL_FN V2 sub_mv_upper(const V2& r, const Blk& m, const V2& v) {
   V2 o; o.x = fmadd(-m.a01, v.y, fmadd(-m.a00, v.x, r.x)); o.y = fmadd(-m.a11, v.y, r.y); return o;
 }
 
-// register-resident part of the factorisation (PCR multipliers of the reduced system)
-struct PcrFac {
+// PCR multipliers of the reduced system (alpha_k, gamma_k of the five levels, final inverse): 44
+// values per lane.  Register-resident (PmRegs), or kept in the trajectory's memories and fetched
+// level by level (PmRun: 4 pairs per level + 2 for the inverse, first TM_PAIRS pairs in `tm`, the
+// rest in `sm`), which takes 88 registers per thread out of the integration loop.
+struct PmRegs {
   Blk al[5], ga[5];
-  Blk binv;
+  Blk binv_;
+  TRPL_FN void put(int k, const Blk& a, const Blk& g) { al[k] = a; ga[k] = g; }
+  TRPL_FN void put_binv(const Blk& b) { binv_ = b; }
+  TRPL_FN void done_storing() const {}
+  struct Level { Blk al, ga; };
+  TRPL_FN Level fetch(int k) const { Level l; l.al = al[k]; l.ga = ga[k]; return l; }
+  TRPL_FN void ready(Level&) const {}
+  TRPL_FN Blk binv() const { return binv_; }
+};
+template <class TM, class SM, int TM_BASE, int SM_BASE, int TM_PAIRS>
+struct PmRun {
+  TM& tm;
+  SM& sm;
+  static constexpr int BINV = 20;        // pair index of the inverse
+  TRPL_FN void put(int k, const Blk& a, const Blk& g) {
+    real v[8];
+    put_blk(v, 0, a); put_blk(v, 2, g);
+    if (4 * k < TM_PAIRS) mem_st_pairs<4>(tm, TM_BASE + 4 * k, v);
+    else mem_st_pairs<4>(sm, SM_BASE + 4 * k - TM_PAIRS, v);
+  }
+  TRPL_FN void put_binv(const Blk& b) {
+    real v[4];
+    put_blk(v, 0, b);
+    if (BINV < TM_PAIRS) mem_st_pairs<2>(tm, TM_BASE + BINV, v);
+    else mem_st_pairs<2>(sm, SM_BASE + BINV - TM_PAIRS, v);
+  }
+  TRPL_FN void done_storing() const { }
+  struct Level { real v[8]; Blk al, ga; bool in_tm; };
+  // issue the loads of level k (asynchronous when it lives in tensor memory)
+  TRPL_FN Level fetch(int k) const {
+    Level l;
+    l.in_tm = 4 * k < TM_PAIRS;
+    if (4 * k < TM_PAIRS) mem_ld_pairs<4>(tm, TM_BASE + 4 * k, l.v);
+    else mem_ld_pairs<4>(sm, SM_BASE + 4 * k - TM_PAIRS, l.v);
+    return l;
+  }
+  TRPL_FN void ready(Level& l) const {
+    if (l.in_tm) mem_wait_ld(tm);
+    l.al = get_blk(l.v, 0); l.ga = get_blk(l.v, 2);
+  }
+  TRPL_FN Blk binv() const {
+    real v[4];
+    if (BINV < TM_PAIRS) { mem_ld_pairs<2>(tm, TM_BASE + BINV, v); mem_wait_ld(tm); }
+    else mem_ld_pairs<2>(sm, SM_BASE + BINV - TM_PAIRS, v);
+    return get_blk(v, 0);
+  }
 };
 
 // Factorise W given by (A, B, C) blocks of this lane's rows.  `fm`/`base`: lane-private factor
 // storage and its first pair; `sm`/`xch`: 12 shared-memory scratch pairs for the lane exchange.
-template <int NPL, class FM>
+template <int NPL, class FM, class PM>
 TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[NPL], FM& fm,
-                       int base, LaneMem& sm, int xch, PcrFac& pf) {
+                       int base, LaneMem& sm, int xch, PM& pf) {
   typedef FacSlots<NPL> S;
   constexpr int NI = NPL - 1;
   Blk ra, rb, rc;
@@ -193,16 +247,16 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
     rb = blk_fma(gamma, ra_dn, blk_fma(alpha, rc_up, rb));
     ra = blk_mul(alpha, ra_up);
     rc = blk_mul(gamma, rc_dn);
-    pf.al[k] = alpha;
-    pf.ga[k] = gamma;
+    pf.put(k, alpha, gamma);
   }
-  pf.binv = blk_inv(rb);
+  pf.put_binv(blk_inv(rb));
+  pf.done_storing();
   warp_sync();
 }
 
 // Solve W x = r in place.  r[j] / x[j] are this lane's NPL block rows; `xch` = 2 scratch pairs.
-template <int NPL, class FM>
-TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch, const PcrFac& pf) {
+template <int NPL, class FM, class PM>
+TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch, const PM& pf) {
   typedef FacSlots<NPL> S;
   constexpr int NI = NPL - 1;
   V2 g[NI > 0 ? NI : 1];
@@ -235,17 +289,24 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch
   }
   TRPL_UNROLL for (int k = 0; k < 5; ++k) {
     const int s = 1 << k;
+    V2 up, dn;
+    typename PM::Level lv = pf.fetch(k);                    // in flight during the lane exchange
+#if TRPL_SOLVE_PCR_SHFL
+    up.x = shfl_up(rr.x, s); up.y = shfl_up(rr.y, s);       // own row where there is no neighbour
+    dn.x = shfl_down(rr.x, s); dn.y = shfl_down(rr.y, s);
+#else
     const int xb = xch + (k & 1);
     sm.st2(xb, rr.x, rr.y);
     warp_sync();
-    V2 up, dn;
     sm.ld2_from(xb, lane_minus(s), up.x, up.y);
     sm.ld2_from(xb, lane_plus(s), dn.x, dn.y);
+#endif
     // two independent chains (multipliers are exact zeros where there is no neighbour)
-    const V2 lo = blk_mv(pf.al[k], up), hi = add_mv(rr, pf.ga[k], dn);
+    pf.ready(lv);
+    const V2 lo = blk_mv(lv.al, up), hi = add_mv(rr, lv.ga, dn);
     rr.x = lo.x + hi.x; rr.y = lo.y + hi.y;
   }
-  const V2 z = blk_mv(pf.binv, rr);
+  const V2 z = blk_mv(pf.binv(), rr);
   r[NPL - 1] = z;
   if constexpr (NI > 0) {
     // spike blocks first, then the arithmetic

@@ -53,6 +53,13 @@ constexpr double RODAS4_GAMMA = 0.25;
 // "Tolerances"): Q is slaved to the densities by dielectric relaxation (sub-picosecond), the
 // stiffly accurate integrator resolves it like an algebraic variable, and the embedded estimate
 // for such components is known to be pessimistic.
+// Tuning switches of the storage layout (measured on B200)
+#ifndef TRPL_PM_REGS
+#define TRPL_PM_REGS 0            // PCR multipliers in registers (1) or in tensor/shared memory (0)
+#endif
+#ifndef TRPL_WARPS_PER_SM
+#define TRPL_WARPS_PER_SM 8       // 8: two CTAs of four warps, 255 registers; 12: one CTA of twelve, 168
+#endif
 #ifndef TRPL_Q_ERR_WEIGHT
 #define TRPL_Q_ERR_WEIGHT 0.03
 #endif
@@ -153,32 +160,55 @@ struct Slots {
   static constexpr int KP = NKS * KSTRIDE;
   static constexpr int FACP = FacSlots<NPL>::COUNT;
   static constexpr int TRP = (MODEL == MODEL_TRAPS) ? 3 * NPL : 0;   // traps: 5 condensation coefficients per node
-#ifdef TRPL_NO_TMEM
-  static constexpr int TM_BUDGET = 0;
+  // PCR multipliers: 5 levels x 4 pairs + the inverse (2 pairs, padded to 4)
+  static constexpr int PMP = 24;
+#if TRPL_PM_REGS
+  static constexpr bool PM_IN_REGS = true;
 #else
-  static constexpr int TM_BUDGET = (KP + FACP <= 64) ? 64 : 128;     // pairs per warp: 2 CTAs (256 columns) or 1 CTA per SM
+  static constexpr bool PM_IN_REGS = false;
 #endif
+  // tensor-memory budget in pairs per warp: 512 columns / (warps per SM / 4 lane quarters) / 4
+#ifdef TRPL_NO_TMEM
+  static constexpr int TM_WANT = 0;
+#elif TRPL_WARPS_PER_SM == 12
+  static constexpr int TM_WANT = 40;
+#else
+  static constexpr int TM_WANT = 64;
+#endif
+  // one CTA per SM (128 pairs) for the grids whose factor blocks alone exceed the two-CTA budget
+  static constexpr int TM_BUDGET = (TM_WANT == 64 && FACP > 64) ? 128 : TM_WANT;
+  // priority: factor blocks, then multipliers (whole levels; the rest stays in shared memory),
+  // then stage increments, then the trap coefficients
   static constexpr bool FAC_IN_TM = FACP <= TM_BUDGET;
-  static constexpr bool K_IN_TM = FAC_IN_TM && KP + FACP <= TM_BUDGET;
-  static constexpr bool TRAP_IN_TM = K_IN_TM && TRP > 0 && KP + FACP + TRP <= TM_BUDGET;
-  // tensor memory: K | FAC | TRAP
+  static constexpr int TM_LEFT1 = TM_BUDGET - (FAC_IN_TM ? FACP : 0);
+  static constexpr int PM_TM_PAIRS = PM_IN_REGS ? 0 : (TM_LEFT1 >= PMP ? PMP : (TM_LEFT1 / 4) * 4);
+  static constexpr int PM_SM_PAIRS = PM_IN_REGS ? 0 : (PM_TM_PAIRS == PMP ? 0 : 22 - PM_TM_PAIRS);
+  static constexpr int TM_LEFT2 = TM_LEFT1 - PM_TM_PAIRS;
+  static constexpr bool K_IN_TM = FAC_IN_TM && KP <= TM_LEFT2;
+  static constexpr int TM_LEFT3 = TM_LEFT2 - (K_IN_TM ? KP : 0);
+  static constexpr bool TRAP_IN_TM = K_IN_TM && TRP > 0 && TRP <= TM_LEFT3;
+  // tensor memory: K | FAC | TRAP | PM   (K first: the explicit path runs its 7 stages from there)
   static constexpr int TM_K = 0;
-  static constexpr int TM_FAC = K_IN_TM ? KP : 0;
+  static constexpr int TM_FAC = K_IN_TM ? (KP + 3) / 4 * 4 : 0;
   static constexpr int TM_TRAP = TM_FAC + (FAC_IN_TM ? FACP : 0);
-  static constexpr int TM_COUNT = TM_TRAP + (TRAP_IN_TM ? TRP : 0);
+  static constexpr int TM_PM = (TM_TRAP + (TRAP_IN_TM ? TRP : 0) + 3) / 4 * 4;
+  static constexpr int TM_COUNT = TM_PM + PM_TM_PAIRS;
   static constexpr int TM_COLS = TM_COUNT == 0 ? 0 : (4 * TM_COUNT <= 32 ? 32 : 4 * TM_COUNT <= 64 ? 64 :
                                   4 * TM_COUNT <= 128 ? 128 : 4 * TM_COUNT <= 256 ? 256 : 512);
-  // shared memory: [K] | [FAC] | [TRAP] | XCH | UNI
+  // shared memory: [K] | [FAC] | [TRAP] | [PM rest] | XCH | UNI
   static constexpr int SM_K = 0;
   static constexpr int SM_FAC = K_IN_TM ? 0 : KP;
   static constexpr int SM_TRAP = SM_FAC + (FAC_IN_TM ? 0 : FACP);
+  static constexpr int SM_PM = SM_TRAP + (TRAP_IN_TM ? 0 : TRP);
   // lane-exchange scratch: 2 pairs for the solves; the factorisation needs 12 (2 x 6, double
   // buffered) and borrows the K region when that lives in shared memory (dead at that point)
-  static constexpr int XCH = SM_TRAP + (TRAP_IN_TM ? 0 : TRP);
+  static constexpr int XCH = SM_PM + PM_SM_PAIRS;
   static constexpr bool XCH_BORROWS_K = !K_IN_TM && KP >= 12;
   static constexpr int XCH_PAIRS = XCH_BORROWS_K ? 2 : 12;
   static constexpr int XCH_FACTOR = XCH_BORROWS_K ? SM_K : XCH;
-  static constexpr int UNI = XCH + XCH_PAIRS;                   // one slot of warp-uniform scalars (Coef)
+  // one slot of warp-uniform scalars (Coef), behind everything else; when the increments live in
+  // shared memory the slice is at least the 7 stages the explicit path keeps from KBASE on
+  static constexpr int UNI = (K_IN_TM || XCH + XCH_PAIRS >= 7 * KSTRIDE) ? XCH + XCH_PAIRS : 7 * KSTRIDE;
   static constexpr int COUNT = UNI + 1;
   static constexpr int BYTES = COUNT * 32 * 16;
   // region bases in whichever memory holds them
@@ -186,12 +216,23 @@ struct Slots {
   static constexpr int FAC = FAC_IN_TM ? TM_FAC : SM_FAC;
   static constexpr int TRAP = TRAP_IN_TM ? TM_TRAP : SM_TRAP;
   // contiguous pairs available from KBASE on (the explicit Runge-Kutta path keeps 7 stages there)
-  static constexpr int KCAP = K_IN_TM ? TM_COUNT : UNI;
+  static constexpr int KCAP = K_IN_TM ? TM_PM : UNI;
 };
 
 struct TrajMem {
   LaneMem sm;
   LaneTm tm;
+};
+// where the PCR multipliers live for this layout (blocktri.h PmRegs / PmRun)
+template <class SL, bool REGS = SL::PM_IN_REGS>
+struct PmChoice {
+  typedef PmRegs type;
+  TRPL_FN static type make(TrajMem&) { return type(); }
+};
+template <class SL>
+struct PmChoice<SL, false> {
+  typedef PmRun<LaneTm, LaneMem, SL::TM_PM, SL::SM_PM, SL::PM_TM_PAIRS> type;
+  TRPL_FN static type make(TrajMem& m) { return type{m.tm, m.sm}; }
 };
 template <class SL> TRPL_FN auto& kmem(TrajMem& m) { if constexpr (SL::K_IN_TM) return m.tm; else return m.sm; }
 template <class SL> TRPL_FN auto& fmem(TrajMem& m) { if constexpr (SL::FAC_IN_TM) return m.tm; else return m.sm; }
@@ -596,7 +637,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
   V cs;           // sum_j c_sj / h K_j of the current stage
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) { cs.n[j] = splat(0.0); cs.q[j] = splat(0.0); }
   TRPL_UNROLL for (int j = 0; j < (MODEL == MODEL_TRAPS ? NPL : 1); ++j) cs.t[j] = splat(0.0);
-  PcrFac pf;
+  typename PmChoice<SL>::type pf = PmChoice<SL>::make(mem);
 
   for (;;) {
     V r;

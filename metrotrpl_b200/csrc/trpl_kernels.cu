@@ -27,14 +27,16 @@ static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch")
 static_assert(sizeof(trpl_solver_opts) == sizeof(SolverOpts), "ABI struct mismatch");
 static_assert(TRPL_NPARAM == trpl::NPARAM, "ABI constant mismatch");
 
+// Residency: TRPL_WARPS_PER_SM trajectories per SM (trajectory.h).  8 = two CTAs of four warps at
+// 255 registers; 12 = one CTA of twelve warps at 168 registers (PCR multipliers in memory).
 #ifndef TRPL_WARPS_PER_CTA
-#define TRPL_WARPS_PER_CTA 4
+#define TRPL_WARPS_PER_CTA (TRPL_WARPS_PER_SM == 12 ? 12 : 4)
 #endif
 constexpr int WARPS_PER_CTA = TRPL_WARPS_PER_CTA;
-constexpr int CTAS_PER_SM = 8 / WARPS_PER_CTA;     // 8 trajectories per SM (registers)
-#ifndef TRPL_NO_TMEM
-static_assert(WARPS_PER_CTA <= 4, "one warp per tensor-memory lane quarter");
-#endif
+constexpr int CTAS_PER_SM = TRPL_WARPS_PER_SM / WARPS_PER_CTA;
+// warps that share a tensor-memory lane quarter stack their slices along the columns
+constexpr int TM_STACK = (WARPS_PER_CTA + 3) / 4;
+constexpr int pow2_cols(int c) { return c == 0 ? 0 : c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 struct KernelArgs {
   const double* params;      // [n_sets][16]
@@ -117,31 +119,36 @@ __device__ __forceinline__ void finish_traj(const KernelArgs& a, int traj, int w
 // CTA (tcgen05.alloc hands out whole columns, all 128 lanes); warp w then owns lanes 32*(w%4)..+31
 // of those columns.  A CTA has at most four warps, so the slices are disjoint.
 template <class SL>
+struct TmCta {
+  static constexpr int COLS = pow2_cols(4 * SL::TM_COUNT * TM_STACK);   // columns one CTA allocates
+  static_assert(4 * SL::TM_COUNT * TM_STACK <= 512, "tensor-memory slices of the CTA exceed 512 columns");
+};
+template <class SL>
 __device__ __forceinline__ LaneTm tmem_acquire(int warp) {
   LaneTm tm{0u};
-  if constexpr (SL::TM_COLS > 0) {
+  if constexpr (SL::TM_COUNT > 0) {
     __shared__ unsigned tm_base_s;
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                   :: "r"((unsigned)__cvta_generic_to_shared(&tm_base_s)), "n"(SL::TM_COLS) : "memory");
+                   :: "r"((unsigned)__cvta_generic_to_shared(&tm_base_s)), "n"(TmCta<SL>::COLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tm.base = tm_base_s + ((unsigned)(32 * (warp & 3)) << 16);
+    tm.base = tm_base_s + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * SL::TM_COUNT);
   }
   return tm;
 }
 // every warp of the CTA is done with its slice: the allocating warp gives the columns back
 template <class SL>
 __device__ __forceinline__ void tmem_release(int warp, const LaneTm& tm) {
-  if constexpr (SL::TM_COLS > 0) {
+  if constexpr (SL::TM_COUNT > 0) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0)
+    if (warp == 0)      // warp 0 sits at column offset 0 of lane quarter 0: its base is the allocation
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                   :: "r"(tm.base & 0x0000ffffu), "n"(SL::TM_COLS) : "memory");
+                   :: "r"(tm.base), "n"(TmCta<SL>::COLS) : "memory");
   }
 }
 
@@ -289,9 +296,9 @@ int launch(trpl_handle* h, KernelArgs a) {
   // tcgen05.alloc until another one exits).  The occupancy calculator answers 1 for any kernel
   // that allocates tensor memory, so residency is computed here: registers and shared memory
   // (launch bounds), capped by the tensor-memory columns.
-  if (SL::TM_COLS > 0) {
+  if (SL::TM_COUNT > 0) {
     const int by_smem = (int)((size_t)h->prop.sharedMemPerMultiprocessor / (smem + 1024 + 16));
-    per_sm = std::min(std::min(CTAS_PER_SM * WARPS_PER_CTA / wpc, by_smem), 512 / SL::TM_COLS);
+    per_sm = std::min(std::min(CTAS_PER_SM * WARPS_PER_CTA / wpc, by_smem), 512 / TmCta<SL>::COLS);
     if (per_sm < 1) return fail("trajectory kernel does not fit on an SM");
   }
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -302,7 +309,7 @@ int launch(trpl_handle* h, KernelArgs a) {
   if (grid < 1) grid = 1;
   if (getenv("TRPL_DEBUG"))
     fprintf(stderr, "[trpl] launch NPL=%d model=%d: %d warps/CTA, %zu B smem/CTA, %d TMEM columns/CTA, %d CTAs/SM, grid %d\n",
-            NPL, MODEL, wpc, smem, SL::TM_COLS, per_sm, grid);
+            NPL, MODEL, wpc, smem, SL::TM_COUNT > 0 ? TmCta<SL>::COLS : 0, per_sm, grid);
   if (a.scratch) {
     CU(h->d_scratch.reserve((size_t)grid * wpc * a.scratch_stride));
     a.scratch = h->d_scratch.p;
