@@ -135,7 +135,9 @@ struct PmRegs {
   struct Level { Blk al, ga; };
   TRPL_FN Level fetch(int k) const { Level l; l.al = al[k]; l.ga = ga[k]; return l; }
   TRPL_FN void ready(Level&) const {}
-  TRPL_FN Blk binv() const { return binv_; }
+  struct Inverse {};
+  TRPL_FN Inverse fetch_binv() const { return Inverse(); }
+  TRPL_FN Blk binv(const Inverse&) const { return binv_; }
 };
 template <class TM, class SM, int TM_BASE, int SM_BASE, int TM_PAIRS>
 struct PmRun {
@@ -168,11 +170,16 @@ struct PmRun {
     if (l.in_tm) mem_wait_ld(tm);
     l.al = get_blk(l.v, 0); l.ga = get_blk(l.v, 2);
   }
-  TRPL_FN Blk binv() const {
-    real v[4];
-    if (BINV < TM_PAIRS) { mem_ld_pairs<2>(tm, TM_BASE + BINV, v); mem_wait_ld(tm); }
-    else mem_ld_pairs<2>(sm, SM_BASE + BINV - TM_PAIRS, v);
-    return get_blk(v, 0);
+  struct Inverse { real v[4]; };
+  TRPL_FN Inverse fetch_binv() const {
+    Inverse i;
+    if (BINV < TM_PAIRS) mem_ld_pairs<2>(tm, TM_BASE + BINV, i.v);
+    else mem_ld_pairs<2>(sm, SM_BASE + BINV - TM_PAIRS, i.v);
+    return i;
+  }
+  TRPL_FN Blk binv(const Inverse& i) const {
+    if (BINV < TM_PAIRS) mem_wait_ld(tm);
+    return get_blk(i.v, 0);
   }
 };
 
@@ -287,10 +294,18 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch
   } else {
     rr = r[0];
   }
+  // Everything the tail of the solve reads (spikes, final inverse) is requested two levels before
+  // it is needed, so that its latency hides behind the last lane exchanges.
+  real f2[2 * (S::RUN2 > 0 ? S::RUN2 : 1)];
+  typename PM::Inverse inv;
   TRPL_UNROLL for (int k = 0; k < 5; ++k) {
     const int s = 1 << k;
     V2 up, dn;
     typename PM::Level lv = pf.fetch(k);                    // in flight during the lane exchange
+    if (k == 3) {
+      if constexpr (NI > 0) mem_ld_pairs<S::RUN2>(fm, base + S::RUN1, f2);
+      inv = pf.fetch_binv();
+    }
 #if TRPL_SOLVE_PCR_SHFL
     up.x = shfl_up(rr.x, s); up.y = shfl_up(rr.y, s);       // own row where there is no neighbour
     dn.x = shfl_down(rr.x, s); dn.y = shfl_down(rr.y, s);
@@ -306,17 +321,12 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch
     const V2 lo = blk_mv(lv.al, up), hi = add_mv(rr, lv.ga, dn);
     rr.x = lo.x + hi.x; rr.y = lo.y + hi.y;
   }
-  const V2 z = blk_mv(pf.binv(), rr);
+  const V2 z = blk_mv(pf.binv(inv), rr);
   r[NPL - 1] = z;
   if constexpr (NI > 0) {
-    // spike blocks first, then the arithmetic
     Blk vs[NI], ws[NI];
-    {
-      real f2[2 * S::RUN2];
-      mem_ld_pairs<S::RUN2>(fm, base + S::RUN1, f2);
-      mem_wait_ld(fm);
-      TRPL_UNROLL for (int j = 0; j < NI; ++j) { vs[j] = get_blk(f2, 2 * j); ws[j] = get_blk(f2, 2 * NI + 2 * j); }
-    }
+    mem_wait_ld(fm);
+    TRPL_UNROLL for (int j = 0; j < NI; ++j) { vs[j] = get_blk(f2, 2 * j); ws[j] = get_blk(f2, 2 * NI + 2 * j); }
     V2 zl; zl.x = shfl_up(z.x, 1); zl.y = shfl_up(z.y, 1);   // lane 0: V is zero there
     TRPL_UNROLL for (int j = 0; j < NI; ++j) r[j] = sub_mv(sub_mv(g[j], vs[j], zl), ws[j], z);
   }

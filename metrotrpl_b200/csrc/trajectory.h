@@ -64,6 +64,11 @@ constexpr double RODAS4_GAMMA = 0.25;
 #define TRPL_Q_ERR_WEIGHT 0.03
 #endif
 constexpr double Q_ERR_WEIGHT = TRPL_Q_ERR_WEIGHT;
+// safety factor of the step-size controller (Hairer's RODAS code uses 0.9; with the predictive controller rejections stay below 1% at 0.95)
+#ifndef TRPL_CTL_SAFETY
+#define TRPL_CTL_SAFETY 0.95f
+#endif
+constexpr float CTL_SAFETY = TRPL_CTL_SAFETY;
 
 enum StatusBits {
   ST_OK = 0,
@@ -810,12 +815,12 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
     //   h_new / h = 0.9 (h / h_acc) (err_old / err^2)^(1/4) = 0.9 (h / h_acc) e2^(-1/4) e2_old^(1/8),
     // and the smaller of the two is taken.
     const float e2f = nonfinite ? 1e20f : (float)fmax(fmin(err2, 1e30), 1e-30);
-    float ifac = fmaxf(1.0f / 6.0f, fminf(5.0f, 0.9f * ctl_powf(e2f, -0.125f)));
+    float ifac = fmaxf(1.0f / 6.0f, fminf(5.0f, CTL_SAFETY * ctl_powf(e2f, -0.125f)));
     h_new = h * (double)ifac;
     if (!nonfinite && err2 <= 1.0) {
       ++n_acc;
       if (!first) {
-        float ifg = 0.9f * (float)(h * ih_acc) * ctl_powf(e2f, -0.25f) * ctl_powf(err2_old, 0.125f);
+        float ifg = CTL_SAFETY * (float)(h * ih_acc) * ctl_powf(e2f, -0.25f) * ctl_powf(err2_old, 0.125f);
         ifg = fmaxf(1.0f / 6.0f, fminf(5.0f, ifg));
         ifac = fminf(ifac, ifg);
         h_new = h * (double)ifac;

@@ -136,7 +136,10 @@ __device__ __forceinline__ LaneTm tmem_acquire(int warp) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tm.base = tm_base_s + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)((warp >> 2) * 4 * SL::TM_COUNT);
+    // broadcast from lane 0: tells ptxas the address is warp-uniform (it then lives in a uniform
+    // register instead of being re-derived from the thread index in front of every access)
+    tm.base = __shfl_sync(0xffffffffu, tm_base_s + ((unsigned)(32 * (warp & 3)) << 16) +
+                                           (unsigned)((warp >> 2) * 4 * SL::TM_COUNT), 0);
   }
   return tm;
 }
@@ -156,7 +159,7 @@ template <int NPL, int MODEL, bool FULL>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_forward_kernel(const KernelArgs a) {
   typedef Slots<NPL, MODEL> SL;
   extern __shared__ double2 smem[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);     // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   TrajMem mem{LaneMem{smem + warp * (SL::COUNT * 32)}, tmem_acquire<SL>(warp)};   // COUNT pairs of 16 B per lane
   const bool allow_defer = a.defer_list != nullptr;
@@ -188,7 +191,7 @@ template <int NPL, int MODEL, bool FULL>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_explicit_kernel(const KernelArgs a) {
   typedef Slots<NPL, MODEL> SL;
   extern __shared__ double2 smem[];
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   TrajMem mem{LaneMem{smem + warp * (SL::COUNT * 32)}, tmem_acquire<SL>(warp)};
   const int n = *a.defer_count;
