@@ -2,10 +2,12 @@
 //
 // Execution model: persistent warps.  The grid is (SM count x 2) CTAs of 4 warps; every warp
 // repeatedly claims the next (parameter set, measurement) trajectory from a global counter and
-// integrates it start to finish (trajectory.h) using only its registers and its private slice of
-// shared memory.  There is no __syncthreads anywhere on the path, no inter-warp communication,
-// and the only global traffic per trajectory is its 16 parameters, the measurement arrays
-// (L2-resident, shared by all trajectories) and a handful of result scalars.
+// integrates it start to finish (trajectory.h) using only its registers, its private slice of
+// tensor memory (factor blocks, PCR multipliers: lane-private data) and its private slice of shared
+// memory (stage increments, lane exchange).  The only __syncthreads are the two that bracket the
+// CTA's tensor-memory allocation, there is no inter-warp communication, and the only global
+// traffic per trajectory is its 16 parameters, the measurement arrays (L2-resident, shared by all
+// trajectories), its step log and a handful of result scalars.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
