@@ -57,6 +57,9 @@ constexpr double RODAS4_GAMMA = 0.25;
 #ifndef TRPL_PM_REGS
 #define TRPL_PM_REGS 0            // PCR multipliers in registers (1) or in tensor/shared memory (0)
 #endif
+#ifndef TRPL_UNROLL_STAGES
+#define TRPL_UNROLL_STAGES 0      // stages 2..6 as straight-line code instead of the state machine
+#endif
 #ifndef TRPL_WARPS_PER_SM
 #define TRPL_WARPS_PER_SM 8       // 8: two CTAs of four warps, 255 registers; 12: one CTA of twelve, 168
 #endif
@@ -562,6 +565,39 @@ TRPL_FN void stage_combine(TrajMem& mem, double ih, const Vec<NPL, MODEL>& u, co
 //   PH_RETRY     step rejected: same u, same f(u) (kept in shared memory), new h
 enum Phase { PH_ACCEPTED = 0, PH_STAGE = 1, PH_RETRY = 2 };
 
+// K = W^{-1} r with the factorisation of this step (traps: occupancy condensed out, see the
+// factorisation in run_trajectory)
+template <int NPL, int MODEL, class PF>
+TRPL_FN void stage_solve(TrajMem& mem, PF& pf, const Vec<NPL, MODEL>& r, Vec<NPL, MODEL>& kk) {
+  typedef Slots<NPL, MODEL> SL;
+  LaneMem& sm = mem.sm;
+  if (MODEL != MODEL_TRAPS) kk.t[0] = splat(0.0);
+  V2 b[NPL];
+  if (MODEL == MODEL_TRAPS) {
+    real w[NPL], gn[NPL], fnt[NPL], fqt[NPL], fqtn[NPL];
+    real tr[6 * NPL];
+    mem_wait_st(trmem<SL>(mem));
+    mem_ld_pairs<3 * NPL>(trmem<SL>(mem), SL::TRAP, tr);
+    mem_wait_ld(trmem<SL>(mem));
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+      gn[j] = tr[6 * j + 1]; fnt[j] = tr[6 * j + 2]; fqt[j] = tr[6 * j + 3]; fqtn[j] = tr[6 * j + 4];
+      w[j] = tr[6 * j + 0] * r.t[j];                        // idt * r_T
+    }
+    const real w_next = shfl_down(w[0], 1);
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
+      const real wn = (j == NPL - 1) ? w_next : w[j + 1];
+      b[j].x = fmadd(fnt[j], w[j], r.n[j]);
+      b[j].y = fmadd(fqt[j], w[j], fmadd(fqtn[j], wn, r.q[j]));
+    }
+    bt_solve<NPL>(b, fmem<SL>(mem), SL::FAC, sm, SL::XCH, pf);
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) kk.t[j] = fmadd(gn[j], b[j].x, w[j]);
+  } else {
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) { b[j].x = r.n[j]; b[j].y = r.q[j]; }
+    bt_solve<NPL>(b, fmem<SL>(mem), SL::FAC, sm, SL::XCH, pf);
+  }
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) { kk.n[j] = b[j].x; kk.q[j] = b[j].y; }
+}
+
 template <int NPL, int MODEL>
 TRPL_FN bool is_nonstiff(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u, double tend);   // explicit.h
 
@@ -731,34 +767,29 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
 
     // ---- K_s = W^{-1} r ----
     V kk;
-    if (MODEL != MODEL_TRAPS) kk.t[0] = splat(0.0);
-    {
-      V2 b[NPL];
-      if (MODEL == MODEL_TRAPS) {
-        real w[NPL], gn[NPL], fnt[NPL], fqt[NPL], fqtn[NPL];
-        real tr[6 * NPL];
-        mem_wait_st(trmem<SL>(mem));
-        mem_ld_pairs<3 * NPL>(trmem<SL>(mem), SL::TRAP, tr);
-        mem_wait_ld(trmem<SL>(mem));
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          gn[j] = tr[6 * j + 1]; fnt[j] = tr[6 * j + 2]; fqt[j] = tr[6 * j + 3]; fqtn[j] = tr[6 * j + 4];
-          w[j] = tr[6 * j + 0] * r.t[j];                        // idt * r_T
-        }
-        const real w_next = shfl_down(w[0], 1);
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-          const real wn = (j == NPL - 1) ? w_next : w[j + 1];
-          b[j].x = fmadd(fnt[j], w[j], r.n[j]);
-          b[j].y = fmadd(fqt[j], w[j], fmadd(fqtn[j], wn, r.q[j]));
-        }
-        bt_solve<NPL>(b, fmem<SL>(mem), SL::FAC, sm, SL::XCH, pf);
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) kk.t[j] = fmadd(gn[j], b[j].x, w[j]);
-      } else {
-        TRPL_UNROLL for (int j = 0; j < NPL; ++j) { b[j].x = r.n[j]; b[j].y = r.q[j]; }
-        bt_solve<NPL>(b, fmem<SL>(mem), SL::FAC, sm, SL::XCH, pf);
-      }
-      TRPL_UNROLL for (int j = 0; j < NPL; ++j) { kk.n[j] = b[j].x; kk.q[j] = b[j].y; }
-    }
+    stage_solve<NPL, MODEL>(mem, pf, r, kk);
 
+#if TRPL_UNROLL_STAGES
+    // Stages 2..6 as straight-line code (stage index known at compile time): the scheduler sees one
+    // basic block per step and can move the older-increment loads and FMAs of the next
+    // combination into the stalls of the current solve.
+#define TRPL_STAGE(S)                                                                         \
+    {                                                                                         \
+      store_k<NPL, MODEL>(kmem<SL>(mem), SL::KBASE + (S - 1) * SL::KSTRIDE, kk);              \
+      stage_combine<S, NPL, MODEL>(mem, ih, u, kk, us, cs);                                   \
+      RhsAux<NPL> aux2;                                                                       \
+      V r2;                                                                                   \
+      rhs<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, us, r2, aux2);                              \
+      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {                                             \
+        r2.n[j] = r2.n[j] + cs.n[j]; r2.q[j] = r2.q[j] + cs.q[j];                             \
+        if (MODEL == MODEL_TRAPS) r2.t[j] = r2.t[j] + cs.t[j];                                \
+      }                                                                                       \
+      stage_solve<NPL, MODEL>(mem, pf, r2, kk);                                               \
+    }
+    TRPL_STAGE(1) TRPL_STAGE(2) TRPL_STAGE(3) TRPL_STAGE(4) TRPL_STAGE(5)
+#undef TRPL_STAGE
+    s = 5;
+#endif
     if (s < 5) {
       // ---- keep K_s, build the next stage argument and c-combination ----
       store_k<NPL, MODEL>(kmem<SL>(mem), SL::KBASE + s * SL::KSTRIDE, kk);
