@@ -66,20 +66,49 @@ def simulate(e_data, P, X, param_info, sim_params, init_params, sim_flags, logge
     if not sim_flags["log_y"]:
         raise NotImplementedError("the likelihood kernel compares log10 signals (log_y = 1)")
     sigmas = sim_flags["current_sigma"]
-    if evaluator is None:
-        from .trial_move_evaluation import PathCache, eval_trial_moves
-        cache = PathCache(sf, device=comm.local_rank)
-
-        def evaluator(states):
-            return eval_trial_moves(states, np.ones(len(states)), sigmas, sf, cache=cache).logll
     n = len(X)
     lo, hi = comm.shard(n)
     local = np.zeros(hi - lo)
-    for b0 in range(lo, hi, block):
-        b1 = min(b0 + block, hi)
-        if logger is not None:
-            logger.info(f"Rank {comm.rank}: samples {b0}..{b1} of {n}")
-        local[b0 - lo:b1 - lo] = evaluator(X[b0:b1])
+    blocks = [(b0, min(b0 + block, hi)) for b0 in range(lo, hi, block)]
+    if evaluator is None:
+        # Two contexts (two streams, two sets of device buffers) take the blocks in turn: block
+        # k+1 is uploaded and launched while block k still runs, so its CTAs fill the SMs that
+        # block k's last trajectories leave idle and the copies hide behind the kernels.
+        from . import _capi
+        from .forward_solver import get_context
+        from .trial_move_evaluation import PathCache
+        dev = get_context(comm.local_rank).device
+        caches = [PathCache(sf, device=dev), PathCache(sf, ctx=_capi.Context(dev))]
+        pending = [None, None]
+
+        def collect(k):
+            b0, b1 = pending[k]
+            per, _, _, _ = caches[k].ctx.download()
+            ll = per[:, :, 0].sum(axis=1)
+            local[b0 - lo:b1 - lo] = np.where(np.isnan(ll), -np.inf, ll)
+            pending[k] = None
+
+        for i, (b0, b1) in enumerate(blocks):
+            k = i % 2
+            if pending[k] is not None:
+                collect(k)
+            if logger is not None:
+                logger.info(f"Rank {comm.rank}: samples {b0}..{b1} of {n}")
+            c = caches[k]
+            params, aux = c.pack(X[b0:b1], sigmas, np.ones((b1 - b0, 3)))
+            c.ctx.set_problem_if_needed(c.prob)
+            c.ctx.upload(params, aux)
+            c.ctx.run_resident(c.opts())
+            pending[k] = (b0, b1)
+        for k in ((len(blocks)) % 2, (len(blocks) + 1) % 2):       # oldest first
+            if pending[k] is not None:
+                collect(k)
+        caches[1].ctx.close()
+    else:
+        for b0, b1 in blocks:
+            if logger is not None:
+                logger.info(f"Rank {comm.rank}: samples {b0}..{b1} of {n}")
+            local[b0 - lo:b1 - lo] = evaluator(X[b0:b1])
     full = comm.allgather_rows(local[:, None], n)[:, 0] if comm.world > 1 else local
     P[:] += full
     return P

@@ -37,7 +37,9 @@ class BatchLikelihood:
 class PathCache:
     """Packs shared_fields once and keeps the problem resident on the device."""
 
-    def __init__(self, shared_fields, device=None):
+    def __init__(self, shared_fields, device=None, ctx=None):
+        """ctx: a private _capi.Context (own stream and device buffers) instead of the process-wide
+        one of `device`; two caches on two contexts let consecutive launches overlap."""
         sf = shared_fields
         if any(m == "pa" for m in sf["_sim_info"]["meas_types"]):
             raise NotImplementedError("'pa' toy measurements are not simulations; not on the CUDA path")
@@ -47,7 +49,7 @@ class PathCache:
                                        ini_mode=sf.get("ini_mode", "density"),
                                        irf_convolution=sf.get("irf_convolution", None),
                                        irf_tables=sf.get("_IRF_tables", None))
-        self.ctx = get_context(device)
+        self.ctx = ctx if ctx is not None else get_context(device)
         self.ctx.set_problem(self.prob)
         self.n_meas = self.prob.n_meas
         idx = sf["_param_indexes"]
