@@ -16,22 +16,6 @@
 #pragma once
 #include "simt.h"
 
-// Tuning switches (measured on B200): recompute neighbour-lane quantities
-// from shuffles of the raw state instead of shuffling derived values.  Shorter dependency chain,
-// but the extra live values cost more than they save in the 255-register right-hand side.
-#ifndef TRPL_RHS_RAW_SHFL
-#define TRPL_RHS_RAW_SHFL 0
-#endif
-#ifndef TRPL_RHS_FOLDED
-#define TRPL_RHS_FOLDED 1
-#endif
-#ifndef TRPL_RHS_RCP1
-#define TRPL_RHS_RCP1 0
-#endif
-#ifndef TRPL_JAC_RAW_SHFL
-#define TRPL_JAC_RAW_SHFL 1
-#endif
-
 namespace trpl {
 using namespace simt;
 
@@ -176,26 +160,6 @@ TRPL_FN void holes(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>&
 template <int NPL, int MODEL>
 TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u,
                  Vec<NPL, MODEL>& f, RhsAux<NPL>& aux) {
-#if TRPL_RHS_RAW_SHFL
-  // Every cross-lane value is a shuffle of the RAW state, issued up front (one shuffle latency per
-  // evaluation instead of three dependent ones): the neighbour quantities derived from them
-  // (hole density of the next lane's first node, current through my left face) are recomputed
-  // locally with the very same operations the owning lane performs, so they agree bit for bit.
-  real ql0 = shfl_up(u.q[NPL - 1], 1);            // running charge left of my first node
-  ql0 = sel(m.first_lane, 0.0, ql0);
-  const real n_prev = shfl_up(u.n[NPL - 1], 1);
-  const real n_next = shfl_down(u.n[0], 1);
-  const real q_next = shfl_down(u.q[0], 1);
-  real P[NPL];
-  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    const real ql = (j == 0) ? ql0 : u.q[j - 1];
-    P[j] = u.n[j] + c.d0 + (u.q[j] - ql);
-    if (MODEL == MODEL_TRAPS) P[j] = P[j] + u.t[j];
-    aux.p[j] = P[j];
-  }
-  real p_next = n_next + c.d0 + (q_next - u.q[NPL - 1]);
-  if (MODEL == MODEL_TRAPS) p_next = p_next + shfl_down(u.t[0], 1);
-#else
   // left running charge of my first node comes from my left neighbour
   real ql0 = shfl_up(u.q[NPL - 1], 1);
   ql0 = sel(m.first_lane, 0.0, ql0);
@@ -208,17 +172,12 @@ TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u
   }
   const real n_next = shfl_down(u.n[0], 1);
   const real p_next = shfl_down(P[0], 1);
-#endif
 
   // node-local recombination, and the surface term of whichever contact this lane owns
   real np_ex[NPL], loss[NPL];
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
     np_ex[j] = fmadd(u.n[j], P[j], -c.n0p0);
-#if TRPL_RHS_RCP1
-    const real inv = rcp1(fmadd(c.taun, P[j], c.taup * u.n[j]));
-#else
     const real inv = rcp(fmadd(c.taun, P[j], c.taup * u.n[j]));
-#endif
     const real rate = fmadd(c.cn, u.n[j], fmadd(c.cp, P[j], c.ks)) + inv;
     loss[j] = rate * np_ex[j];
   }
@@ -232,7 +191,6 @@ TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u
     bx = sel(m.last_node[j], np_ex[j], bx);
     has_last = mor(has_last, m.last_node[j]);
   }
-#if TRPL_RHS_FOLDED
   // currents carry the 1/dx of the divergence (coefficients pre-multiplied in make_coef)
   const real svel = sel(has_last, c.sbx, c.sfx);
   const real surf = svel * bx * rcp(bn + bp);       // forward_solver.py:346-347, times 1/dx
@@ -248,11 +206,7 @@ TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u
     jp[j] = sel(m.inner_face[j], b, -a);
   }
   if (MODEL != MODEL_TRAPS) f.t[0] = splat(0.0);
-#if TRPL_RHS_RAW_SHFL
-  real jl0 = fmadd((n_prev + u.n[0]) * c.anl, ql0, c.dnx * (u.n[0] - n_prev));
-#else
   real jl0 = shfl_up(jn[NPL - 1], 1);
-#endif
   jl0 = sel(m.first_lane, surf, jl0);                                   // forward_solver.py:349
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
     const real jl = (j == 0) ? jl0 : jn[j - 1];
@@ -268,47 +222,6 @@ TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u
     f.q[j] = fq;
   }
 }
-#else
-  const real svel = sel(has_last, c.sb, c.sf);
-  const real surf = svel * bx * rcp(bn + bp);       // forward_solver.py:346-347
-
-  // right-face currents of my nodes
-  real jn[NPL], jsum[NPL];
-  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    const real nn = (j == NPL - 1) ? n_next : u.n[j + 1];
-    const real pn = (j == NPL - 1) ? p_next : P[j + 1];
-    const real e = c.ld * u.q[j];
-    real a = fmadd(c.an * (u.n[j] + nn), e, c.dn * (nn - u.n[j]));      // forward_solver.py:356-357
-    real b = fmadd(c.ap * (P[j] + pn), e, -(c.dp * (pn - P[j])));       // forward_solver.py:358-359
-    // back contact: Jn = -S, Jp = +S (sum exactly zero); padding: no current
-    a = sel(m.inner_face[j], a, sel(m.last_node[j], -surf, 0.0));
-    jn[j] = a;
-    jsum[j] = sel(m.inner_face[j], a + b, 0.0);
-  }
-  if (MODEL != MODEL_TRAPS) f.t[0] = splat(0.0);
-#if TRPL_RHS_RAW_SHFL
-  // electron current through my left face = right-face current of the previous lane's last node
-  // (an interior face whenever my first node is a real node; irrelevant otherwise)
-  real jl0 = fmadd(c.an * (n_prev + u.n[0]), c.ld * ql0, c.dn * (u.n[0] - n_prev));
-#else
-  real jl0 = shfl_up(jn[NPL - 1], 1);
-#endif
-  jl0 = sel(m.first_lane, surf, jl0);                                   // forward_solver.py:349
-  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    const real jl = (j == 0) ? jl0 : jn[j - 1];
-    real fn = fmadd(c.ix, jn[j] - jl, -loss[j]);                        // forward_solver.py:369
-    real fq = -(c.ix * jsum[j]);                                        // forward_solver.py:363 (/ (Lambda dx))
-    if (MODEL == MODEL_TRAPS) {
-      const real capture = c.kc * u.n[j] * (c.nt - u.t[j]);             // forward_solver.py:410
-      const real release = u.t[j] * c.itaue;                            // forward_solver.py:411
-      fn = fn + (release - capture);
-      f.t[j] = sel(m.real_node[j], capture - release, 0.0);
-    }
-    f.n[j] = sel(m.real_node[j], fn, 0.0);
-    f.q[j] = fq;
-  }
-}
-#endif
 
 // 2x2 block, row-major {a00, a01, a10, a11}
 struct Blk { real a00, a01, a10, a11; };
@@ -337,13 +250,9 @@ TRPL_FN void jacobian(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODE
   }
   const real n_prev = shfl_up(u.n[NPL - 1], 1);
   const real n_next = shfl_down(u.n[0], 1);
-#if TRPL_JAC_RAW_SHFL
   // hole density of the next lane's first node, recomputed from raw-state shuffles (see rhs)
   real p_next = n_next + c.d0 + (shfl_down(u.q[0], 1) - u.q[NPL - 1]);
   if (MODEL == MODEL_TRAPS) p_next = p_next + shfl_down(u.t[0], 1);
-#else
-  const real p_next = shfl_down(P[0], 1);
-#endif
 
   // contact term partials (one lane each, same trick as in rhs)
   real bn = u.n[0], bp = P[0];

@@ -57,13 +57,6 @@ TRPL_FN real rcp(real x) {
   return r;
 }
 TRPL_FN real vdiv(real a, real b) { return a / b; }       // IEEE division (cold paths only)
-// Reciprocal with ONE Newton step (~2^-40 or better)
-TRPL_FN real rcp1(real x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  const double e = fma(-x, r, 1.0);
-  return fma(r, e, r);
-}
 // Reciprocal to ~2^-23 (the hardware seed alone): for quantities that only steer the step size.
 TRPL_FN real rcp_approx(real x) {
   double r;
@@ -181,11 +174,7 @@ struct LaneTm {
                  : "r"(base + 4u * (unsigned)p) : "memory");
   }
   TRPL_FN void wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-#ifdef TRPL_TM_NO_WAIT_ST
-  TRPL_FN void wait_st() const {}
-#else
   TRPL_FN void wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-#endif
 };
 // the same interface on shared memory, so that a region can live in either
 TRPL_FN void mem_wait_ld(const LaneMem&) {}
@@ -272,7 +261,6 @@ inline mask lane_lt(const ivec& l, int k) { return l < k; }
 inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
 template <class A, class B, class C> inline real fmadd(const A& a, const B& b, const C& c) { return fmadd3(real(a), real(b), real(c)); }
 inline real vdiv(const real& a, const real& b) { return a / b; }
-inline real rcp1(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
 inline real rcp_approx(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
 inline real vmax_fast(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] > b.v[i] ? a.v[i] : b.v[i]; return r; }
 inline float ctl_powf(float x, float y) { return powf(x, y); }

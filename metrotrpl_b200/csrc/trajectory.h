@@ -57,9 +57,6 @@ constexpr double RODAS4_GAMMA = 0.25;
 #ifndef TRPL_PM_REGS
 #define TRPL_PM_REGS 0            // PCR multipliers in registers (1) or in tensor/shared memory (0)
 #endif
-#ifndef TRPL_UNROLL_STAGES
-#define TRPL_UNROLL_STAGES 0      // stages 2..6 as straight-line code instead of the state machine
-#endif
 #ifndef TRPL_WARPS_PER_SM
 #define TRPL_WARPS_PER_SM 8       // 8: two CTAs of four warps, 255 registers; 12: one CTA of twelve, 168
 #endif
@@ -769,27 +766,6 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
     V kk;
     stage_solve<NPL, MODEL>(mem, pf, r, kk);
 
-#if TRPL_UNROLL_STAGES
-    // Stages 2..6 as straight-line code (stage index known at compile time): the scheduler sees one
-    // basic block per step and can move the older-increment loads and FMAs of the next
-    // combination into the stalls of the current solve.
-#define TRPL_STAGE(S)                                                                         \
-    {                                                                                         \
-      store_k<NPL, MODEL>(kmem<SL>(mem), SL::KBASE + (S - 1) * SL::KSTRIDE, kk);              \
-      stage_combine<S, NPL, MODEL>(mem, ih, u, kk, us, cs);                                   \
-      RhsAux<NPL> aux2;                                                                       \
-      V r2;                                                                                   \
-      rhs<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, us, r2, aux2);                              \
-      TRPL_UNROLL for (int j = 0; j < NPL; ++j) {                                             \
-        r2.n[j] = r2.n[j] + cs.n[j]; r2.q[j] = r2.q[j] + cs.q[j];                             \
-        if (MODEL == MODEL_TRAPS) r2.t[j] = r2.t[j] + cs.t[j];                                \
-      }                                                                                       \
-      stage_solve<NPL, MODEL>(mem, pf, r2, kk);                                               \
-    }
-    TRPL_STAGE(1) TRPL_STAGE(2) TRPL_STAGE(3) TRPL_STAGE(4) TRPL_STAGE(5)
-#undef TRPL_STAGE
-    s = 5;
-#endif
     if (s < 5) {
       // ---- keep K_s, build the next stage argument and c-combination ----
       store_k<NPL, MODEL>(kmem<SL>(mem), SL::KBASE + s * SL::KSTRIDE, kk);
