@@ -116,3 +116,32 @@ def test_dense_sampling_on_gpu_against_oracle():
         want, _ = orc.state_loglik(X[i], sim_info, ini, e_data[0], e_data[1], e_data[2], idx, units,
                                    {"TRPL": sigma}, rtol=1e-10, atol=1e-16)
         assert abs(P[i] / want - 1) < 1e-5
+
+
+def test_dense_sampling_pipeline_equals_block_by_block():
+    """simulate() alternates its blocks between two contexts (launches overlap); the result must be
+    what one context gives block by block, bit for bit, whatever the block size."""
+    tmp = tempfile.mkdtemp()
+    sim_info, ini, e_data, MCMC, param_info = small_problem(tmp)
+    names = param_info["names"]
+    rng = np.random.default_rng(5)
+    base = np.array([GUESS[n] for n in names], dtype=float)
+    X = np.repeat(base[None, :], 37, axis=0)
+    X[:, names.index("tauN")] = 10 ** rng.uniform(2, 3, 37)
+    X[:, names.index("p0")] = 10 ** rng.uniform(15, 16, 37)
+    flags = {"log_y": 1, "model": "std", "ini_mode": "density", "rtol": 1e-7, "current_sigma": {"TRPL": 0.05}}
+    outs = []
+    for block in (5, 16, 64):
+        P = np.zeros(37)
+        ds.simulate(e_data, P, X, param_info, dict(sim_info), ini, flags, block=block)
+        outs.append(P)
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
+    from metrotrpl_b200.trial_move_evaluation import eval_trial_moves
+    idx = {n: i for i, n in enumerate(names)}
+    units = np.array([UNITS.get(n, 1) for n in names], dtype=float)
+    sf = {"_sim_info": sim_info, "_init_params": ini, "_times": e_data[0], "_vals": e_data[1],
+          "_uncs": e_data[2], "_param_indexes": idx, "units": units, "model": "std",
+          "ini_mode": "density", "rtol": 1e-7, "atol": None}
+    ref = eval_trial_moves(X, np.ones(37), {"TRPL": 0.05}, sf).logll
+    np.testing.assert_array_equal(outs[0], ref)

@@ -150,3 +150,25 @@ def test_self_convergence_at_full_size(ctx):
 def test_no_device_no_fallback():
     with pytest.raises(_capi.TrplError):
         _capi.Context(99)
+
+
+def test_results_do_not_depend_on_what_ran_before(ctx):
+    """Tensor memory and shared memory are never cleared between trajectories, launches or
+    problems: every value read must have been written by the same trajectory.  Run the staub batch,
+    then problems with other nodes-per-lane instantiations and the traps model (other layouts of
+    the same memories), then the staub batch again: bit-identical results."""
+    g, prob, params, aux = pc.staub_problem()
+    opts = _capi.make_opts(RTOL=1e-7)
+    ctx.set_problem(prob)
+    first = ctx.loglik_batch(params, aux, opts, want_curves=True)
+    assert pc.check_edges(lambda *a: _backend(ctx, *a))
+    pc.check_traps_irf(lambda *a: _backend(ctx, *a))
+    ctx.set_problem(prob)
+    again = ctx.loglik_batch(params, aux, opts, want_curves=True)
+    for a, b in zip(first, again):
+        np.testing.assert_array_equal(a, b)
+
+
+def _backend(ctx, prob, params, aux, opts, want_curves):
+    ctx.set_problem(prob)
+    return ctx.loglik_batch(params, aux, opts, want_curves=want_curves)
