@@ -156,7 +156,7 @@ struct PmRun {
     if (BINV < TM_PAIRS) mem_st_pairs<2>(tm, TM_BASE + BINV, v);
     else mem_st_pairs<2>(sm, SM_BASE + BINV - TM_PAIRS, v);
   }
-  TRPL_FN void done_storing() const { }
+  TRPL_FN void done_storing() const { if (TM_PAIRS > 0) mem_wait_st(tm); }
   struct Level { real v[8]; Blk al, ga; bool in_tm; };
   // issue the loads of level k (asynchronous when it lives in tensor memory)
   TRPL_FN Level fetch(int k) const {
@@ -258,6 +258,7 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
   }
   pf.put_binv(blk_inv(rb));
   pf.done_storing();
+  mem_wait_st(fm);          // one fence per step: everything the six solves read has landed
   warp_sync();
 }
 
@@ -274,8 +275,7 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch
     Blk az, cz;
     {
       real f1[2 * S::RUN1];
-      mem_wait_st(fm);
-      mem_ld_pairs<S::RUN1>(fm, base, f1);
+      mem_ld_pairs<S::RUN1>(fm, base, f1);          // stores were fenced once, at the end of bt_factor
       mem_wait_ld(fm);
       TRPL_UNROLL for (int j = 0; j < NI; ++j) {
         dinv[j] = get_blk(f1, S::DINV + 2 * j);
