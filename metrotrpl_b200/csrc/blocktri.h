@@ -7,16 +7,18 @@
 //      are eliminated sequentially in registers (block Thomas) against the two neighbouring
 //      interface unknowns, which produces the spike blocks V, W (fill-in columns);
 //   2. the 32 interface rows (one per lane, z_l = u at the lane's last node) form a reduced
-//      block-tridiagonal system that is solved by parallel cyclic reduction with shuffles:
-//      5 levels, strides 1,2,4,8,16;
+//      block-tridiagonal system that is solved by parallel cyclic reduction: 5 levels, strides
+//      1,2,4,8,16, neighbour rows exchanged through shared memory;
 //   3. interiors are recovered as x = g - V z_{l-1} - W z_l.
 // The factorisation is done once per step; each Rosenbrock stage then costs one `solve`.
 // No pivoting: W is a shifted M-matrix-like operator and the prototype
 // (tools/proto/proto_test3.py) shows <=3e-11 relative error against a pivoted dense solve over the
 // whole prior box, step sizes 1e-6..1e3 ns.
 //
-// Storage: interior factors and spikes live in the per-warp shared-memory slots
-// (slot-major, conflict-free); the PCR multipliers stay in registers.
+// Storage: the interior factors, spikes and interface blocks (FacSlots: two runs of consecutive
+// pairs) and the PCR multipliers (PmRun: one run per level) are lane-private and live in the
+// warp's tensor-memory slice (or shared memory, whatever `FM`/`PM` are); only the PCR lane exchange
+// goes through shared memory.
 #pragma once
 #include "simt.h"
 #include "model.h"
