@@ -41,9 +41,10 @@ RTOL = 1e-7   # the reference's default RTOL (forward_solver.py:18)
 
 # Algorithmic FP64 flops of one integrator step per space node, 'std' model, 4 nodes per lane
 # (FMA = 2, division = 1); the breakdown is derived in DESIGN.md section 5:
-#   6 right-hand sides x 32 + Jacobian 72 + factorisation 184 + 6 solves x 52.5
-#   + stage combinations / error norm 128 + readout 8
-FLOPS_PER_NODE_STEP = 6 * 32 + 72 + 184 + 6 * 52.5 + 128 + 8   # = 899
+#   6 right-hand sides x 32 + Jacobian 38 (reuses the stage-1 right-hand side's recombination terms
+#   and flux factors) + factorisation 184 + 6 solves x 52.5 + stage combinations / error norm 114
+#   + readout 8
+FLOPS_PER_NODE_STEP = 6 * 32 + 38 + 184 + 6 * 52.5 + 114 + 8   # = 851
 
 
 def workload_inputs():

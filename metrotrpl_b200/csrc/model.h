@@ -142,6 +142,15 @@ struct Vec {
 template <int NPL>
 struct RhsAux {
   real p[NPL];     // hole density
+  // node-local recombination terms and neighbour values, reused by the Jacobian when it is
+  // evaluated at the same state (stage 1 of every step)
+  real npx[NPL];   // N P - n0 p0
+  real inv[NPL];   // 1 / (tauN P + tauP N)
+  real rate[NPL];  // Cn N + Cp P + ks + inv
+  real ql0;        // running charge left of this lane's first node
+  real n_next, p_next;   // first node of the next lane
+  real bn, bp, bx, isum; // the contact node this lane owns: N, P, N P - n0 p0, 1 / (N + P)
+  real snl[NPL], spl[NPL];   // (N_i + N_{i+1}) anl and (P_i + P_{i+1}) apl of the right face: d(flux)/dQ
 };
 
 // hole density from the state: P_i = N_i [+ Ntrap_i] + (p0 - n0) + Q_{i+1} - Q_i
@@ -172,6 +181,7 @@ TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u
   }
   const real n_next = shfl_down(u.n[0], 1);
   const real p_next = shfl_down(P[0], 1);
+  aux.ql0 = ql0; aux.n_next = n_next; aux.p_next = p_next;
 
   // node-local recombination, and the surface term of whichever contact this lane owns
   real np_ex[NPL], loss[NPL];
@@ -180,6 +190,7 @@ TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u
     const real inv = rcp(fmadd(c.taun, P[j], c.taup * u.n[j]));
     const real rate = fmadd(c.cn, u.n[j], fmadd(c.cp, P[j], c.ks)) + inv;
     loss[j] = rate * np_ex[j];
+    aux.npx[j] = np_ex[j]; aux.inv[j] = inv; aux.rate[j] = rate;
   }
   // one division serves both contacts: lane 0 evaluates the front (node 0), the lane holding node
   // L-1 the back.  NPL is chosen minimal by the host so these are different lanes.
@@ -193,13 +204,17 @@ TRPL_FN void rhs(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u
   }
   // currents carry the 1/dx of the divergence (coefficients pre-multiplied in make_coef)
   const real svel = sel(has_last, c.sbx, c.sfx);
-  const real surf = svel * bx * rcp(bn + bp);       // forward_solver.py:346-347, times 1/dx
+  const real isum = rcp(bn + bp);
+  const real surf = svel * bx * isum;               // forward_solver.py:346-347, times 1/dx
+  aux.bn = bn; aux.bp = bp; aux.bx = bx; aux.isum = isum;
   real jn[NPL], jp[NPL];
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
     const real nn = (j == NPL - 1) ? n_next : u.n[j + 1];
     const real pn = (j == NPL - 1) ? p_next : P[j + 1];
-    real a = fmadd((u.n[j] + nn) * c.anl, u.q[j], c.dnx * (nn - u.n[j]));      // forward_solver.py:356-357
-    real b = fmadd((P[j] + pn) * c.apl, u.q[j], -(c.dpx * (pn - P[j])));       // forward_solver.py:358-359
+    const real snl = (u.n[j] + nn) * c.anl, spl = (P[j] + pn) * c.apl;
+    aux.snl[j] = snl; aux.spl[j] = spl;
+    real a = fmadd(snl, u.q[j], c.dnx * (nn - u.n[j]));                        // forward_solver.py:356-357
+    real b = fmadd(spl, u.q[j], -(c.dpx * (pn - P[j])));                       // forward_solver.py:358-359
     // back contact: Jn = -S, Jp = +S (sum exactly zero); padding: no current
     a = sel(m.inner_face[j], a, sel(m.last_node[j], -surf, 0.0));
     jn[j] = a;
@@ -237,90 +252,72 @@ struct JacTraps {
   real ft_t[NPL];   // d fT / d Ntrap
 };
 
+// `aux` is what rhs() left behind for the SAME state u (the Jacobian is only ever evaluated right
+// after f(u), at stage 1 of a step): hole densities, recombination terms, contact terms, neighbour
+// values and the d(flux)/dQ factors are not recomputed.  Every flux partial carries the 1/dx of the
+// divergence (coefficients pre-multiplied in make_coef), like the fluxes in rhs().
 template <int NPL, int MODEL>
-TRPL_FN void jacobian(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u,
+TRPL_FN void jacobian(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODEL>& u, const RhsAux<NPL>& aux,
                       Blk (&A)[NPL], Blk (&B)[NPL], Blk (&C)[NPL], JacTraps<NPL>& jt) {
-  real ql0 = shfl_up(u.q[NPL - 1], 1);
-  ql0 = sel(m.first_lane, 0.0, ql0);
-  real P[NPL];
-  TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    const real ql = (j == 0) ? ql0 : u.q[j - 1];
-    P[j] = u.n[j] + c.d0 + (u.q[j] - ql);
-    if (MODEL == MODEL_TRAPS) P[j] = P[j] + u.t[j];
-  }
   const real n_prev = shfl_up(u.n[NPL - 1], 1);
-  const real n_next = shfl_down(u.n[0], 1);
-  // hole density of the next lane's first node, recomputed from raw-state shuffles (see rhs)
-  real p_next = n_next + c.d0 + (shfl_down(u.q[0], 1) - u.q[NPL - 1]);
-  if (MODEL == MODEL_TRAPS) p_next = p_next + shfl_down(u.t[0], 1);
 
   // contact term partials (one lane each, same trick as in rhs)
-  real bn = u.n[0], bp = P[0];
   mask has_last = mconst(false);
+  TRPL_UNROLL for (int j = 0; j < NPL; ++j) has_last = mor(has_last, m.last_node[j]);
+  const real svel = sel(has_last, c.sbx, c.sfx);
+  const real common = aux.bx * aux.isum * aux.isum;
+  const real s_n = svel * (aux.bp * aux.isum - common);   // dS/dN at fixed P
+  const real s_p = svel * (aux.bn * aux.isum - common);   // dS/dP at fixed N
+
+  // interior form of the right-face partials of every node (the left face of node j is the right
+  // face of node j-1; the face left of this lane's first node is formed from the shuffled values)
+  real r_ni[NPL], r_nn[NPL], p_pi[NPL], p_pn[NPL];
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    bn = sel(m.last_node[j], u.n[j], bn);
-    bp = sel(m.last_node[j], P[j], bp);
-    has_last = mor(has_last, m.last_node[j]);
+    r_ni[j] = fmadd(c.anl, u.q[j], -c.dnx);         // d jnR / d N_i
+    r_nn[j] = fmadd(c.anl, u.q[j], c.dnx);          // d jnR / d N_{i+1}
+    p_pi[j] = fmadd(c.apl, u.q[j], c.dpx);          // d jpR / d P_i
+    p_pn[j] = fmadd(c.apl, u.q[j], -c.dpx);         // d jpR / d P_{i+1}
   }
-  const real svel = sel(has_last, c.sb, c.sf);
-  const real isum = rcp(bn + bp);
-  const real bx = fmadd(bn, bp, -c.n0p0);
-  const real common = bx * isum * isum;
-  const real s_n = svel * (bp * isum - common);   // dS/dN at fixed P
-  const real s_p = svel * (bn * isum - common);   // dS/dP at fixed N
+  const real l0_nm = fmadd(c.anl, aux.ql0, -c.dnx), l0_ni = fmadd(c.anl, aux.ql0, c.dnx);
+  const real l0_q = (n_prev + u.n[0]) * c.anl;
 
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    const real nj = u.n[j], pj = P[j];
-    const real ql = (j == 0) ? ql0 : u.q[j - 1];
-    const real nm = (j == 0) ? n_prev : u.n[j - 1];
-    const real nn = (j == NPL - 1) ? n_next : u.n[j + 1];
-    const real pn = (j == NPL - 1) ? p_next : P[j + 1];
+    const real nj = u.n[j], pj = aux.p[j];
     // recombination partials
-    const real npx = fmadd(nj, pj, -c.n0p0);
-    const real inv = rcp(fmadd(c.taun, pj, c.taup * nj));
-    const real rate = fmadd(c.cn, nj, fmadd(c.cp, pj, c.ks)) + inv;
-    const real inv2 = inv * inv;
-    const real r_n = fmadd(c.cn - c.taup * inv2, npx, rate * pj);
-    const real r_p = fmadd(c.cp - c.taun * inv2, npx, rate * nj);
-    // right face (between i and i+1), interior form
-    const real er = c.ld * u.q[j];
-    real jr_ni = fmadd(c.an, er, -c.dn);            // d jnR / d N_i
-    real jr_nn = fmadd(c.an, er, c.dn);             // d jnR / d N_{i+1}
-    real jr_q = c.an * (nj + nn) * c.ld;            // d jnR / d Q_{i+1}
-    real jr_pi = splat(0.0);                        // d jnR / d P_i (only through the back contact)
-    real jp_pi = fmadd(c.ap, er, c.dp);             // d jpR / d P_i
-    real jp_pn = fmadd(c.ap, er, -c.dp);            // d jpR / d P_{i+1}
-    real jp_q = c.ap * (pj + pn) * c.ld;            // d jpR / d Q_{i+1} (explicit field)
-    // back contact replaces the right face of node L-1: jnR = -S(N_i, P_i)
-    jr_ni = sel(m.inner_face[j], jr_ni, sel(m.last_node[j], -s_n, 0.0));
-    jr_pi = sel(m.last_node[j], -s_p, jr_pi);
-    jr_nn = sel(m.inner_face[j], jr_nn, 0.0);
-    jr_q = sel(m.inner_face[j], jr_q, 0.0);
-    // left face (between i-1 and i)
-    const real el = c.ld * ql;
-    real jl_nm = fmadd(c.an, el, -c.dn);            // d jnL / d N_{i-1}
-    real jl_ni = fmadd(c.an, el, c.dn);             // d jnL / d N_i
-    real jl_q = c.an * (nm + nj) * c.ld;            // d jnL / d Q_i
+    const real inv2 = aux.inv[j] * aux.inv[j];
+    const real r_n = fmadd(c.cn - c.taup * inv2, aux.npx[j], aux.rate[j] * pj);
+    const real r_p = fmadd(c.cp - c.taun * inv2, aux.npx[j], aux.rate[j] * nj);
+    // right face (between i and i+1); the back contact replaces it at node L-1: jnR = -S(N_i, P_i)
+    const real jr_ni = sel(m.inner_face[j], r_ni[j], sel(m.last_node[j], -s_n, 0.0));
+    const real jr_pi = sel(m.last_node[j], -s_p, 0.0);      // d jnR / d P_i (only through the back contact)
+    const real jr_nn = sel(m.inner_face[j], r_nn[j], 0.0);
+    const real jr_q = sel(m.inner_face[j], aux.snl[j], 0.0); // d jnR / d Q_{i+1}
+    const real jp_pi = p_pi[j], jp_pn = p_pn[j];
+    const real jp_q = aux.spl[j];                           // d jpR / d Q_{i+1} (explicit field)
+    // left face (between i-1 and i); front contact: jnL = +S(N_0, P_0)
+    real jl_nm = (j == 0) ? l0_nm : r_ni[j > 0 ? j - 1 : 0];    // d jnL / d N_{i-1}
+    real jl_ni = (j == 0) ? l0_ni : r_nn[j > 0 ? j - 1 : 0];    // d jnL / d N_i
+    real jl_q = (j == 0) ? l0_q : aux.snl[j > 0 ? j - 1 : 0];   // d jnL / d Q_i
     real jl_pi = splat(0.0);
-    if (j == 0) {                                   // front contact: jnL = +S(N_0, P_0)
+    if (j == 0) {
       jl_nm = sel(m.first_lane, 0.0, jl_nm);
       jl_q = sel(m.first_lane, 0.0, jl_q);
       jl_ni = sel(m.first_lane, s_n, jl_ni);
       jl_pi = sel(m.first_lane, s_p, jl_pi);
     }
     // chain coefficient of P_i in fN_i
-    const real c_p = fmadd(c.ix, jr_pi - jl_pi, -r_p);
-    real b00 = fmadd(c.ix, jr_ni - jl_ni, -r_n) + c_p;
-    real b01 = fmadd(c.ix, jr_q, c_p);
-    real a00 = -(c.ix * jl_nm);
-    real a01 = -fmadd(c.ix, jl_q, c_p);
-    real c00 = c.ix * jr_nn;
-    // fQ_{i+1} = -ix (jnR + jpR) on interior faces, identically zero otherwise
-    real b10 = -(c.ix * (jr_ni + jp_pi));
-    real b11 = -(c.ix * (jr_q + jp_pi - jp_pn + jp_q));
-    real a11 = c.ix * jp_pi;
-    real c10 = -(c.ix * (jr_nn + jp_pn));
-    real c11 = -(c.ix * jp_pn);
+    const real c_p = (jr_pi - jl_pi) - r_p;
+    real b00 = ((jr_ni - jl_ni) - r_n) + c_p;
+    real b01 = jr_q + c_p;
+    real a00 = -jl_nm;
+    real a01 = -(jl_q + c_p);
+    real c00 = jr_nn;
+    // fQ_{i+1} = -(jnR + jpR) on interior faces, identically zero otherwise
+    real b10 = -(jr_ni + jp_pi);
+    real b11 = -((jr_q + jp_q) + (jp_pi - jp_pn));
+    real a11 = jp_pi;
+    real c10 = -(jr_nn + jp_pn);
+    real c11 = -jp_pn;
     b10 = sel(m.inner_face[j], b10, 0.0);
     b11 = sel(m.inner_face[j], b11, 0.0);
     a11 = sel(m.inner_face[j], a11, 0.0);
@@ -332,8 +329,8 @@ TRPL_FN void jacobian(const Coef& c, const NodeMask<NPL>& m, const Vec<NPL, MODE
       b00 = b00 - cap_n;
       // Ntrap enters fN directly (release - capture) and through P_i (+1)
       jt.fn_t[j] = sel(m.real_node[j], (c.itaue - cap_t) + c_p, 0.0);
-      jt.fq_t[j] = sel(m.inner_face[j], -(c.ix * jp_pi), 0.0);
-      jt.fq_tn[j] = sel(m.inner_face[j], -(c.ix * jp_pn), 0.0);
+      jt.fq_t[j] = sel(m.inner_face[j], -jp_pi, 0.0);
+      jt.fq_tn[j] = sel(m.inner_face[j], -jp_pn, 0.0);
       jt.ft_n[j] = sel(m.real_node[j], cap_n, 0.0);
       jt.ft_t[j] = sel(m.real_node[j], cap_t - c.itaue, 0.0);
     }

@@ -497,9 +497,12 @@ TRPL_FN void combine_term(const Vec<NPL, MODEL>& kp, double ih, Vec<NPL, MODEL>&
   constexpr double a = Rodas4::A[S][P];
   const double cc = Rodas4::C[S][P] * ih;
   TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-    us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
+    if constexpr (S != 5) {       // stage 6's argument is built from stage 5's (stage_combine)
+      us.n[j] = fmadd(a, kp.n[j], us.n[j]); us.q[j] = fmadd(a, kp.q[j], us.q[j]);
+      if (MODEL == MODEL_TRAPS) us.t[j] = fmadd(a, kp.t[j], us.t[j]);
+    }
     cs.n[j] = fmadd(cc, kp.n[j], cs.n[j]); cs.q[j] = fmadd(cc, kp.q[j], cs.q[j]);
-    if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kp.t[j], us.t[j]); cs.t[j] = fmadd(cc, kp.t[j], cs.t[j]); }
+    if (MODEL == MODEL_TRAPS) cs.t[j] = fmadd(cc, kp.t[j], cs.t[j]);
   }
 }
 template <int S, int NPL, int MODEL>
@@ -520,9 +523,17 @@ TRPL_FN void stage_combine(TrajMem& mem, double ih, const Vec<NPL, MODEL>& u, co
     constexpr double a = Rodas4::A[S][S - 1];
     const double cc = Rodas4::C[S][S - 1] * ih;
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      us.n[j] = fmadd(a, kk.n[j], u.n[j]); us.q[j] = fmadd(a, kk.q[j], u.q[j]);
+      if constexpr (S == 5) {
+        // row 6 of A is row 5 plus e_5: the argument of stage 6 is the argument of stage 5 (still
+        // in `us`) plus K_5
+        us.n[j] = us.n[j] + kk.n[j]; us.q[j] = us.q[j] + kk.q[j];
+        if (MODEL == MODEL_TRAPS) us.t[j] = us.t[j] + kk.t[j];
+      } else {
+        us.n[j] = fmadd(a, kk.n[j], u.n[j]); us.q[j] = fmadd(a, kk.q[j], u.q[j]);
+        if (MODEL == MODEL_TRAPS) us.t[j] = fmadd(a, kk.t[j], u.t[j]);
+      }
       cs.n[j] = cc * kk.n[j]; cs.q[j] = cc * kk.q[j];
-      if (MODEL == MODEL_TRAPS) { us.t[j] = fmadd(a, kk.t[j], u.t[j]); cs.t[j] = cc * kk.t[j]; }
+      if (MODEL == MODEL_TRAPS) cs.t[j] = cc * kk.t[j];
     }
   }
   if constexpr (S >= 2) {
@@ -679,10 +690,10 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
 
   for (;;) {
     V r;
+    RhsAux<NPL> aux;                // of the latest right-hand side; the Jacobian reuses it at stage 1
     {
       // PH_RETRY re-evaluates f(u) (us == u): rejections are rare (~0.5% of steps) and this keeps
       // f(u) out of shared memory
-      RhsAux<NPL> aux;
       const Coef cr = fetch_coef(sm, SL::UNI);
       rhs<NPL, MODEL>(cr, m, us, r, aux);
       if (phase == PH_ACCEPTED) {
@@ -725,7 +736,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
         // W = 1/(gamma h) I - J, factorised
         Blk A[NPL], B[NPL], C[NPL];
         JacTraps<NPL> jt;
-        jacobian<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, u, A, B, C, jt);
+        jacobian<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, u, aux, A, B, C, jt);
         TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
           A[j] = blk_neg(A[j]); C[j] = blk_neg(C[j]);
           B[j].a00 = gi - B[j].a00; B[j].a01 = -B[j].a01; B[j].a10 = -B[j].a10; B[j].a11 = gi - B[j].a11;
