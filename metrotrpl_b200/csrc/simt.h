@@ -305,24 +305,27 @@ inline ivec lane_plus(int d) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i +
 inline ivec to_int_floor(const real& x) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = (int)floor(x.v[i]); return r; }
 inline real to_real(const ivec& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (double)a.v[i]; return r; }
 
+// every access is bounds-checked (std::vector::at): the pair indices are the same compile-time
+// layout constants the device build uses, so the CPU test tier doubles as the bounds check of the
+// shared-memory and tensor-memory slices (compute-sanitizer is not available on the GPU pool)
 struct LaneMem {
   std::vector<real> slots;     // 2 per pair
   explicit LaneMem(int n_pairs) : slots(2 * n_pairs) {}
-  void ld2(int p, real& a, real& b) const { a = slots[2 * p]; b = slots[2 * p + 1]; }
-  void st2(int p, const real& a, const real& b) { slots[2 * p] = a; slots[2 * p + 1] = b; }
+  void ld2(int p, real& a, real& b) const { a = slots.at(2 * p); b = slots.at(2 * p + 1); }
+  void st2(int p, const real& a, const real& b) { slots.at(2 * p) = a; slots.at(2 * p + 1) = b; }
   void ld2_from(int p, const ivec& src, real& a, real& b) const {
-    for (int i = 0; i < 32; ++i) { a.v[i] = slots[2 * p].v[src.v[i]]; b.v[i] = slots[2 * p + 1].v[src.v[i]]; }
+    for (int i = 0; i < 32; ++i) { a.v[i] = slots.at(2 * p).v[src.v[i] & 31]; b.v[i] = slots.at(2 * p + 1).v[src.v[i] & 31]; }
   }
-  double uld(int p, int i) const { return slots[2 * p + (i & 1)].v[i >> 1]; }
-  void ust(int p, int i, double v) { slots[2 * p + (i & 1)].v[i >> 1] = v; }
+  double uld(int p, int i) const { return slots.at(2 * p + (i & 1)).v[i >> 1]; }
+  void ust(int p, int i, double v) { slots.at(2 * p + (i & 1)).v[i >> 1] = v; }
 };
 inline void warp_sync() {}
 // host stand-in of the tensor-memory slice (see the device half): just another array of pairs
 struct LaneTm {
   std::vector<real> slots;
-  explicit LaneTm(int n_pairs) : slots(2 * (n_pairs > 0 ? n_pairs : 1)) {}
-  void ld2(int p, real& a, real& b) const { a = slots[2 * p]; b = slots[2 * p + 1]; }
-  void st2(int p, const real& a, const real& b) { slots[2 * p] = a; slots[2 * p + 1] = b; }
+  explicit LaneTm(int n_pairs) : slots(2 * n_pairs) {}
+  void ld2(int p, real& a, real& b) const { a = slots.at(2 * p); b = slots.at(2 * p + 1); }
+  void st2(int p, const real& a, const real& b) { slots.at(2 * p) = a; slots.at(2 * p + 1) = b; }
 };
 template <class M> inline void mem_wait_ld(const M&) {}
 template <class M> inline void mem_wait_st(const M&) {}
