@@ -192,12 +192,19 @@ struct Slots {
   static constexpr bool K_IN_TM = FAC_IN_TM && KP <= TM_LEFT2;
   static constexpr int TM_LEFT3 = TM_LEFT2 - (K_IN_TM ? KP : 0);
   static constexpr bool TRAP_IN_TM = K_IN_TM && TRP > 0 && TRP <= TM_LEFT3;
-  // tensor memory: K | FAC | TRAP | PM   (K first: the explicit path runs its 7 stages from there)
+  // tensor memory: K | FAC | TRAP | PM | first increments   (K first: the explicit path runs its 7
+  // stages from there)
   static constexpr int TM_K = 0;
   static constexpr int TM_FAC = K_IN_TM ? (KP + 3) / 4 * 4 : 0;
   static constexpr int TM_TRAP = TM_FAC + (FAC_IN_TM ? FACP : 0);
   static constexpr int TM_PM = (TM_TRAP + (TRAP_IN_TM ? TRP : 0) + 3) / 4 * 4;
-  static constexpr int TM_COUNT = TM_PM + PM_TM_PAIRS;
+  // When the increments as a whole stay in shared memory, whatever tensor memory is left takes the
+  // first K_TM_STAGES of them: K_1 is read back by four later stages, K_2 by three, K_5 by none.
+  static constexpr int TM_KS = (TM_PM + PM_TM_PAIRS + 3) / 4 * 4;
+  static constexpr int K_TM_ROOM = (!K_IN_TM && FAC_IN_TM && KSTRIDE % 4 == 0 && TM_BUDGET > TM_KS)
+                                       ? (TM_BUDGET - TM_KS) / KSTRIDE : 0;
+  static constexpr int K_TM_STAGES = K_TM_ROOM > NKS - 1 ? NKS - 1 : K_TM_ROOM;
+  static constexpr int TM_COUNT = K_TM_STAGES > 0 ? TM_KS + K_TM_STAGES * KSTRIDE : TM_PM + PM_TM_PAIRS;
   static constexpr int TM_COLS = TM_COUNT == 0 ? 0 : (4 * TM_COUNT <= 32 ? 32 : 4 * TM_COUNT <= 64 ? 64 :
                                   4 * TM_COUNT <= 128 ? 128 : 4 * TM_COUNT <= 256 ? 256 : 512);
   // shared memory: [K] | [FAC] | [TRAP] | [PM rest] | XCH | UNI
@@ -269,6 +276,31 @@ TRPL_FN void unpack_k(const KRun<NPL, MODEL>& r, Vec<NPL, MODEL>& k) {
   } else {
     k.t[0] = splat(0.0);
   }
+}
+// increment of stage `st` (0-based) of the Rosenbrock step: tensor memory for the first
+// K_TM_STAGES stages when the K region is split, the K region's memory otherwise
+template <int NPL, int MODEL>
+TRPL_FN void store_stage(TrajMem& mem, int st, const Vec<NPL, MODEL>& k) {
+  typedef Slots<NPL, MODEL> SL;
+  if (SL::K_TM_STAGES > 0 && st < SL::K_TM_STAGES) store_k<NPL, MODEL>(mem.tm, SL::TM_KS + st * SL::KSTRIDE, k);
+  else store_k<NPL, MODEL>(kmem<SL>(mem), SL::KBASE + st * SL::KSTRIDE, k);
+}
+template <int ST, int NPL, int MODEL>
+TRPL_FN void load_stage_nowait(TrajMem& mem, KRun<NPL, MODEL>& r) {
+  typedef Slots<NPL, MODEL> SL;
+  if constexpr (ST < SL::K_TM_STAGES) load_k_nowait<NPL, MODEL>(mem.tm, SL::TM_KS + ST * SL::KSTRIDE, r);
+  else load_k_nowait<NPL, MODEL>(kmem<SL>(mem), SL::KBASE + ST * SL::KSTRIDE, r);
+}
+template <int ST, int NPL, int MODEL>
+TRPL_FN void wait_stage(TrajMem& mem) {
+  typedef Slots<NPL, MODEL> SL;
+  if constexpr (ST < SL::K_TM_STAGES) mem_wait_ld(mem.tm); else mem_wait_ld(kmem<SL>(mem));
+}
+template <int NPL, int MODEL>
+TRPL_FN void fence_stage_stores(TrajMem& mem) {
+  typedef Slots<NPL, MODEL> SL;
+  if constexpr (SL::K_TM_STAGES > 0) mem_wait_st(mem.tm);
+  mem_wait_st(kmem<SL>(mem));
 }
 template <int NPL, int MODEL, class M>
 TRPL_FN void load_k(const M& km, int kb, Vec<NPL, MODEL>& k) {
@@ -509,14 +541,13 @@ template <int S, int NPL, int MODEL>
 TRPL_FN void stage_combine(TrajMem& mem, double ih, const Vec<NPL, MODEL>& u, const Vec<NPL, MODEL>& kk,
                            Vec<NPL, MODEL>& us, Vec<NPL, MODEL>& cs) {
   typedef Slots<NPL, MODEL> SL;
-  auto& km = kmem<SL>(mem);
   // Older increments come back from their memory through two buffers: the load of term p+1 is in
   // flight while term p is consumed.
   KRun<NPL, MODEL> ka, kb;
   Vec<NPL, MODEL> kp;
   if constexpr (S >= 2) {
-    mem_wait_st(km);
-    load_k_nowait<NPL, MODEL>(km, SL::KBASE + 0 * SL::KSTRIDE, ka);
+    fence_stage_stores<NPL, MODEL>(mem);
+    load_stage_nowait<0, NPL, MODEL>(mem, ka);
   }
   {
     // the newest increment is still in registers
@@ -537,32 +568,32 @@ TRPL_FN void stage_combine(TrajMem& mem, double ih, const Vec<NPL, MODEL>& u, co
     }
   }
   if constexpr (S >= 2) {
-    mem_wait_ld(km);
-    if constexpr (S >= 3) load_k_nowait<NPL, MODEL>(km, SL::KBASE + 1 * SL::KSTRIDE, kb);
+    wait_stage<0, NPL, MODEL>(mem);
+    if constexpr (S >= 3) load_stage_nowait<1, NPL, MODEL>(mem, kb);
     unpack_k<NPL, MODEL>(ka, kp);
     combine_term<S, 0, NPL, MODEL>(kp, ih, us, cs);
   }
   if constexpr (S >= 3) {
-    mem_wait_ld(km);
-    if constexpr (S >= 4) load_k_nowait<NPL, MODEL>(km, SL::KBASE + 2 * SL::KSTRIDE, ka);
+    wait_stage<1, NPL, MODEL>(mem);
+    if constexpr (S >= 4) load_stage_nowait<2, NPL, MODEL>(mem, ka);
     unpack_k<NPL, MODEL>(kb, kp);
     combine_term<S, 1, NPL, MODEL>(kp, ih, us, cs);
   }
   if constexpr (S >= 4) {
-    mem_wait_ld(km);
-    if constexpr (S >= 5) load_k_nowait<NPL, MODEL>(km, SL::KBASE + 3 * SL::KSTRIDE, kb);
+    wait_stage<2, NPL, MODEL>(mem);
+    if constexpr (S >= 5) load_stage_nowait<3, NPL, MODEL>(mem, kb);
     unpack_k<NPL, MODEL>(ka, kp);
     combine_term<S, 2, NPL, MODEL>(kp, ih, us, cs);
   }
   if constexpr (S >= 5) {
-    mem_wait_ld(km);
+    wait_stage<3, NPL, MODEL>(mem);
     unpack_k<NPL, MODEL>(kb, kp);
     combine_term<S, 3, NPL, MODEL>(kp, ih, us, cs);
   }
   // Row 6 of A is row 5 plus e_5, so the new state is (argument of stage 6) + K_6.  K_1..K_5 are
   // dead once this combination is formed: park the stage-6 argument in K_1's slot instead of
   // rebuilding it from five increments at the end of the step.
-  if constexpr (S == 5) store_k<NPL, MODEL>(km, SL::KBASE, us);
+  if constexpr (S == 5) store_stage<NPL, MODEL>(mem, 0, us);
 }
 // ---- the trajectory -------------------------------------------------------------------------
 // Control flow is a small state machine so that the right-hand side, the readout/emit block and the
@@ -779,7 +810,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
 
     if (s < 5) {
       // ---- keep K_s, build the next stage argument and c-combination ----
-      store_k<NPL, MODEL>(kmem<SL>(mem), SL::KBASE + s * SL::KSTRIDE, kk);
+      if (s < 4) store_stage<NPL, MODEL>(mem, s, kk);     // K_5 is consumed from registers only
       ++s;
       switch (s) {
         case 1: stage_combine<1, NPL, MODEL>(mem, ih, u, kk, us, cs); break;
@@ -794,7 +825,13 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
 
     // ---- stage 6 done: u_new = u + sum_j m_j K_j = (stage-6 argument, parked by stage_combine<5>)
     // + K_6; the error estimate is K_6 ----
-    load_k<NPL, MODEL>(kmem<SL>(mem), SL::KBASE, us);
+    {
+      KRun<NPL, MODEL> parked;
+      fence_stage_stores<NPL, MODEL>(mem);
+      load_stage_nowait<0, NPL, MODEL>(mem, parked);
+      wait_stage<0, NPL, MODEL>(mem);
+      unpack_k<NPL, MODEL>(parked, us);
+    }
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
       us.n[j] = us.n[j] + kk.n[j]; us.q[j] = us.q[j] + kk.q[j];
       if (MODEL == MODEL_TRAPS) us.t[j] = us.t[j] + kk.t[j];
