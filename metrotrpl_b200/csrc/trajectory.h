@@ -57,9 +57,6 @@ constexpr double RODAS4_GAMMA = 0.25;
 #ifndef TRPL_PM_REGS
 #define TRPL_PM_REGS 0            // PCR multipliers in registers (1) or in tensor/shared memory (0)
 #endif
-#ifndef TRPL_WARPS_PER_SM
-#define TRPL_WARPS_PER_SM 8       // 8: two CTAs of four warps, 255 registers; 12: one CTA of twelve, 168
-#endif
 #ifndef TRPL_Q_ERR_WEIGHT
 #define TRPL_Q_ERR_WEIGHT 0.03
 #endif
@@ -172,11 +169,9 @@ struct Slots {
 #else
   static constexpr bool PM_IN_REGS = false;
 #endif
-  // tensor-memory budget in pairs per warp: 512 columns / (warps per SM / 4 lane quarters) / 4
+  // tensor-memory budget in pairs per warp: 512 columns / 2 CTAs per SM / 4 columns per pair
 #ifdef TRPL_NO_TMEM
   static constexpr int TM_WANT = 0;
-#elif TRPL_WARPS_PER_SM == 12
-  static constexpr int TM_WANT = 40;
 #else
   static constexpr int TM_WANT = 64;
 #endif

@@ -29,15 +29,11 @@ static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch")
 static_assert(sizeof(trpl_solver_opts) == sizeof(SolverOpts), "ABI struct mismatch");
 static_assert(TRPL_NPARAM == trpl::NPARAM, "ABI constant mismatch");
 
-// Residency: TRPL_WARPS_PER_SM trajectories per SM (trajectory.h).  8 = two CTAs of four warps at
-// 255 registers; 12 = one CTA of twelve warps at 168 registers (PCR multipliers in memory).
-#ifndef TRPL_WARPS_PER_CTA
-#define TRPL_WARPS_PER_CTA (TRPL_WARPS_PER_SM == 12 ? 12 : 4)
-#endif
-constexpr int WARPS_PER_CTA = TRPL_WARPS_PER_CTA;
-constexpr int CTAS_PER_SM = TRPL_WARPS_PER_SM / WARPS_PER_CTA;
-// warps that share a tensor-memory lane quarter stack their slices along the columns
-constexpr int TM_STACK = (WARPS_PER_CTA + 3) / 4;
+// Residency: 8 trajectories per SM - two CTAs of four warps at 255 registers per thread.  (Twelve
+// per SM at 168 registers, with the tensor-memory slices of a 12-warp CTA stacked along the
+// columns, was built and measured: no gain)
+constexpr int WARPS_PER_CTA = 4;                  // one warp per tensor-memory lane quarter
+constexpr int CTAS_PER_SM = 2;
 constexpr int pow2_cols(int c) { return c == 0 ? 0 : c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 struct KernelArgs {
@@ -122,8 +118,8 @@ __device__ __forceinline__ void finish_traj(const KernelArgs& a, int traj, int w
 // of those columns.  A CTA has at most four warps, so the slices are disjoint.
 template <class SL>
 struct TmCta {
-  static constexpr int COLS = pow2_cols(4 * SL::TM_COUNT * TM_STACK);   // columns one CTA allocates
-  static_assert(4 * SL::TM_COUNT * TM_STACK <= 512, "tensor-memory slices of the CTA exceed 512 columns");
+  static constexpr int COLS = pow2_cols(4 * SL::TM_COUNT);   // columns one CTA allocates
+  static_assert(4 * SL::TM_COUNT <= 512, "tensor-memory slice exceeds 512 columns");
 };
 template <class SL>
 __device__ __forceinline__ LaneTm tmem_acquire(int warp) {
@@ -140,8 +136,7 @@ __device__ __forceinline__ LaneTm tmem_acquire(int warp) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // broadcast from lane 0: tells ptxas the address is warp-uniform (it then lives in a uniform
     // register instead of being re-derived from the thread index in front of every access)
-    tm.base = __shfl_sync(0xffffffffu, tm_base_s + ((unsigned)(32 * (warp & 3)) << 16) +
-                                           (unsigned)((warp >> 2) * 4 * SL::TM_COUNT), 0);
+    tm.base = __shfl_sync(0xffffffffu, tm_base_s + ((unsigned)(32 * warp) << 16), 0);
   }
   return tm;
 }
@@ -151,7 +146,7 @@ __device__ __forceinline__ void tmem_release(int warp, const LaneTm& tm) {
   if constexpr (SL::TM_COUNT > 0) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0)      // warp 0 sits at column offset 0 of lane quarter 0: its base is the allocation
+    if (warp == 0)      // warp 0 owns lane quarter 0: its base is the allocation
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                    :: "r"(tm.base), "n"(TmCta<SL>::COLS) : "memory");
   }
