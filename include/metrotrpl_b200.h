@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TRPL_ABI_VERSION 2
+#define TRPL_ABI_VERSION 3
 #define TRPL_NPARAM 16  /* doubles per parameter set, model units (nm, ns, V) */
 #define TRPL_NAUX 6     /* doubles per trajectory, see below */
 #define TRPL_NTEMP 3    /* likelihoods are returned for three temperatures per trajectory */
@@ -144,6 +144,28 @@ int trpl_flush_l2(trpl_handle* h);
 
 /* Dependent-free DFMA stream on every SM: measured FP64 peak for the roofline denominator. */
 int trpl_fp64_peak_probe(trpl_handle* h, int32_t iters, double* tflops, float* ms);
+
+/* Host side of one Metropolis iteration: the proposals of ALL chains and their acceptance draws,
+ * consuming a PCG64 stream (NumPy's default_rng) in exactly the order of the reference's serial
+ * loop - for each chain in turn one draw per parameter and attempt (trial_move_generation.py:54-96,
+ * retried up to max_tries times under hard bounds, checks of :4-52), then the chain's acceptance
+ * draw (metropolis.py:118-127).  No device work.
+ *   cur, moves        [n_chains][n_par] current states and box half-widths in the sampler's scale
+ *                     (log10 of the parameters with do_log set); proposals come back in that scale
+ *   do_log, active    [n_par] flags; lo, hi [n_par] prior bounds (linear units)
+ *   idx_*             parameter indices of p0/n0 and tauN/tauP, or -1 when absent
+ *   pcg_state/pcg_inc the generator's 128-bit state and increment as {high, low} 64-bit words
+ *   proposals [n_chains][n_par], u [n_chains], n_draws = doubles consumed (advance the generator
+ *   by this), n_failed [n_chains] failed attempts, fail_masks [n_chains][TRPL_MAX_LOGGED_FAILS]
+ *   checks failed by each of the first failed attempts: bit i = parameter i out of bounds,
+ *   bit 30 = p0 <= n0, bit 31 = tauN and tauP more than two decades apart.  n_par <= 30. */
+#define TRPL_MAX_LOGGED_FAILS 8
+int trpl_make_trial_moves(int32_t n_chains, int32_t n_par, const double* cur, const double* moves,
+                          const uint8_t* do_log, const uint8_t* active, const double* lo,
+                          const double* hi, int32_t idx_p0, int32_t idx_n0, int32_t idx_taun,
+                          int32_t idx_taup, int32_t hard_bounds, int32_t max_tries,
+                          const uint64_t pcg_state[2], const uint64_t pcg_inc[2], double* proposals,
+                          double* u, int64_t* n_draws, int32_t* n_failed, uint32_t* fail_masks);
 
 #ifdef __cplusplus
 }

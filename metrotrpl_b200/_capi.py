@@ -12,6 +12,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
+ABI_VERSION = 3
 NPARAM = 16
 NAUX = 6
 NTEMP = 3
@@ -240,6 +241,10 @@ def load_library() -> C.CDLL:
     lib.trpl_last_kernel_ms.argtypes = [H, C.POINTER(C.c_float)]
     lib.trpl_launch_count.argtypes = [H]
     lib.trpl_launch_count.restype = C.c_int64
+    u8p, u64p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    lib.trpl_make_trial_moves.argtypes = [C.c_int32, C.c_int32, dp, dp, u8p, u8p, dp, dp, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_int32, C.c_int32, C.c_int32, u64p, u64p, dp, dp,
+                                          C.POINTER(C.c_int64), ip, u32p]
     lib.trpl_synchronize.argtypes = [H]
     lib.trpl_timer_begin.argtypes = [H]
     lib.trpl_timer_end.argtypes = [H, C.POINTER(C.c_float)]
@@ -257,7 +262,7 @@ class Context:
 
     def __init__(self, device: int = 0):
         self.lib = load_library()
-        if self.lib.trpl_abi_version() != 2:
+        if self.lib.trpl_abi_version() != ABI_VERSION:
             raise TrplError("ABI version mismatch")
         self.h = C.c_void_p()
         self._check(self.lib.trpl_create(int(device), C.byref(self.h)))

@@ -20,6 +20,7 @@
 #include "../../include/metrotrpl_b200.h"
 #include "trajectory.h"
 #include "explicit.h"
+#include "proposals.h"
 
 namespace {
 
@@ -674,6 +675,21 @@ int trpl_flush_l2(trpl_handle* h) {
   CU(h->d_flush.reserve(bytes));
   CU(cudaMemsetAsync(h->d_flush.p, 1, bytes, h->stream));
   return 0;
+}
+
+int trpl_make_trial_moves(int32_t n_chains, int32_t n_par, const double* cur, const double* moves,
+                          const uint8_t* do_log, const uint8_t* active, const double* lo, const double* hi,
+                          int32_t idx_p0, int32_t idx_n0, int32_t idx_taun, int32_t idx_taup,
+                          int32_t hard_bounds, int32_t max_tries, const uint64_t pcg_state[2],
+                          const uint64_t pcg_inc[2], double* proposals, double* u, int64_t* n_draws,
+                          int32_t* n_failed, uint32_t* fail_masks) {
+  if (n_chains < 1 || n_par < 1 || n_par > 30) return fail("trpl_make_trial_moves: 1..30 parameters");
+  if (!cur || !moves || !do_log || !active || !lo || !hi || !pcg_state || !pcg_inc || !proposals || !u ||
+      !n_draws || !n_failed || !fail_masks || max_tries < 1)
+    return fail("trpl_make_trial_moves: bad arguments");
+  return trpl_host::make_trial_moves(n_chains, n_par, cur, moves, do_log, active, lo, hi, idx_p0, idx_n0,
+                                     idx_taun, idx_taup, hard_bounds, max_tries, pcg_state, pcg_inc,
+                                     proposals, u, n_draws, n_failed, fail_masks, TRPL_MAX_LOGGED_FAILS);
 }
 
 int trpl_fp64_peak_probe(trpl_handle* h, int32_t iters, double* tflops, float* ms_out) {

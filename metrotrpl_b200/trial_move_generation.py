@@ -91,7 +91,83 @@ def _approve_rows(new_states, shared_fields):
     return ok
 
 
-def make_trial_moves(current_states, trial_moves, shared_fields, RNG, logger=None):
+MAX_LOGGED_FAILS = 8       # include/metrotrpl_b200.h TRPL_MAX_LOGGED_FAILS
+_native = {"lib": None, "tried": False}
+
+
+def _native_lib():
+    """The C entry point trpl_make_trial_moves of the CUDA library (host code), or None."""
+    if not _native["tried"]:
+        _native["tried"] = True
+        try:
+            from . import _capi
+            _native["lib"] = _capi.load_library()
+        except Exception:
+            _native["lib"] = None
+    return _native["lib"]
+
+
+def _make_trial_moves_native(lib, cur, trial_moves, shared_fields, RNG, logger):
+    """All chains in one C call (csrc/proposals.h): same generator stream, same arithmetic."""
+    import ctypes as C
+    n_chains, n_par = cur.shape
+    order = shared_fields["names"]
+    idx = shared_fields["_param_indexes"]
+    prior = shared_fields["prior_dist"]
+    do_log = np.ascontiguousarray(shared_fields["do_log"], dtype=np.uint8)
+    active = np.ascontiguousarray(shared_fields["active"], dtype=np.uint8)
+    lo = np.array([prior[n][0] for n in order], dtype=np.float64)
+    hi = np.array([prior[n][1] for n in order], dtype=np.float64)
+    st = RNG.bit_generator.state["state"]
+    mask64 = (1 << 64) - 1
+    pcg_state = (C.c_uint64 * 2)(st["state"] >> 64, st["state"] & mask64)
+    pcg_inc = (C.c_uint64 * 2)(st["inc"] >> 64, st["inc"] & mask64)
+    dl = np.asarray(shared_fields["do_log"], dtype=bool)
+    cur = np.ascontiguousarray(np.where(dl[None, :], np.log10(cur), cur), dtype=np.float64)
+    moves = np.ascontiguousarray(np.broadcast_to(trial_moves, cur.shape), dtype=np.float64)
+    proposals = np.empty_like(cur)
+    u = np.empty(n_chains)
+    n_failed = np.zeros(n_chains, dtype=np.int32)
+    masks = np.zeros((n_chains, MAX_LOGGED_FAILS), dtype=np.uint32)
+    n_draws = C.c_int64(0)
+    dp = C.POINTER(C.c_double)
+    rc = lib.trpl_make_trial_moves(
+        n_chains, n_par, cur.ctypes.data_as(dp), moves.ctypes.data_as(dp),
+        do_log.ctypes.data_as(C.POINTER(C.c_uint8)), active.ctypes.data_as(C.POINTER(C.c_uint8)),
+        lo.ctypes.data_as(dp), hi.ctypes.data_as(dp),
+        idx["p0"] if "p0" in order and "n0" in order else -1, idx["n0"] if "p0" in order and "n0" in order else -1,
+        idx["tauN"] if "tauN" in order and "tauP" in order else -1,
+        idx["tauP"] if "tauN" in order and "tauP" in order else -1,
+        1 if shared_fields.get("hard_bounds", 0) else 0, MAX_PROPOSALS, pcg_state, pcg_inc,
+        proposals.ctypes.data_as(dp), u.ctypes.data_as(dp), C.byref(n_draws),
+        n_failed.ctypes.data_as(C.POINTER(C.c_int32)), masks.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if rc != 0:
+        raise RuntimeError(lib.trpl_last_error().decode())
+    RNG.bit_generator.advance(n_draws.value)
+    proposals = np.where(dl[None, :], 10 ** proposals, proposals)
+    if logger is not None and n_failed.any():
+        # The reference warns once per failed attempt ("Failed checks: [...]"); with hundreds of hot
+        # chains that is the most expensive thing the host does in an iteration.  One line per
+        # iteration with the same information, counted per check.
+        counts = {}
+        logged = 0
+        for m in np.nonzero(n_failed)[0]:
+            for k in range(min(int(n_failed[m]), MAX_LOGGED_FAILS)):
+                bits = int(masks[m, k])
+                logged += 1
+                for i in range(n_par):
+                    if bits >> i & 1:
+                        counts[f"{order[i]}_size"] = counts.get(f"{order[i]}_size", 0) + 1
+                if bits >> 30 & 1:
+                    counts["p0_greater"] = counts.get("p0_greater", 0) + 1
+                if bits >> 31 & 1:
+                    counts["tn_tp_close"] = counts.get("tn_tp_close", 0) + 1
+        logger.warning(f"Failed checks: {int(n_failed.sum())} attempts of {int((n_failed > 0).sum())} chains "
+                       f"rejected; per check (first {MAX_LOGGED_FAILS} attempts of a chain): {counts}")
+    return proposals, u
+
+
+def make_trial_moves(current_states, trial_moves, shared_fields, RNG, logger=None, native=True):
     """All chains' proposals and acceptance draws of one iteration.
 
     Consumes the generator exactly as the reference's serial loop does (metropolis.py:118-127):
@@ -104,10 +180,14 @@ def make_trial_moves(current_states, trial_moves, shared_fields, RNG, logger=Non
     """
     cur = np.asarray(current_states, dtype=float)
     n_chains, n_par = cur.shape
-    proposals = np.empty_like(cur)
-    u = np.empty(n_chains)
     bitgen = RNG.bit_generator
     can_batch = shared_fields.get("do_mu_constraint", None) is None and hasattr(bitgen, "advance")
+    if native and can_batch and n_par <= 30 and bitgen.state.get("bit_generator") == "PCG64":
+        lib = _native_lib()
+        if lib is not None and hasattr(lib, "trpl_make_trial_moves"):
+            return _make_trial_moves_native(lib, cur, trial_moves, shared_fields, RNG, logger)
+    proposals = np.empty_like(cur)
+    u = np.empty(n_chains)
     do_log = np.asarray(shared_fields["do_log"], dtype=bool)
     hard = bool(shared_fields.get("hard_bounds", 0))
     m = 0

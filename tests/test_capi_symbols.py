@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 14
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.trpl_abi_version() == 2
+    assert lib.trpl_abi_version() == _capi.ABI_VERSION
 
 
 def test_struct_layouts():
