@@ -116,15 +116,10 @@ def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, sha
         logratio = np.where(np.isnan(logratio), -np.inf, logratio)
         with np.errstate(over="ignore"):
             accepted = u < np.exp(logratio)
-        for m in range(n_chains):
-            if accepted[m]:
-                logll[m, k] = new_ll[m]
-                states[m, :, k] = proposals[m]
-                accept[m, k] = 1
-                cur_ladder[m] = new_ladder[m]
-            else:
-                logll[m, k] = logll[m, k - 1]
-                states[m, :, k] = states[m, :, k - 1]
+        logll[:, k] = np.where(accepted, new_ll, logll[:, k - 1])
+        states[:, :, k] = np.where(accepted[:, None], proposals, states[:, :, k - 1])
+        accept[accepted, k] = 1
+        cur_ladder[accepted] = new_ladder[accepted]
         if shared_fields["do_parallel_tempering"] and k % shared_fields["temper_freq"] == 0:
             for _ in range(n_chains - 1):
                 i = RNG.integers(0, n_chains - 1)
