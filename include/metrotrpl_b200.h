@@ -8,6 +8,8 @@
  *   trial_move_evaluation.py:9-28   eval_trial_move(state, unique_fields, shared_fields, logger)
  *   trial_move_evaluation.py:30-166 one_sim_likelihood(...)             -> trpl_loglik_batch
  *   Dense_Sample/dense_sampling.py:42-196 simulate(...) inner loops      -> trpl_loglik_batch
+ *   trial_move_generation.py:54-96 make_trial_move + metropolis.py:118-127 draw order
+ *                                                                       -> trpl_make_trial_moves
  *
  * with whole batches of parameter sets per call instead of one state at a time.
  * Plain pointers and sizes only; all arrays are C-contiguous float64 / int32 HOST arrays unless a
