@@ -17,5 +17,5 @@ PY
 done
 $TR --nproc-per-node 8 --master-port 29611 tools/run_dense_example.py --points 1000000 2> gpurun_out/dense_n8.err | tail -1 | tee gpurun_out/dense_n8.log
 $TR --nproc-per-node 2 --master-port 29612 tools/run_dense_example.py --points 65536 2> gpurun_out/dense_n2.err | tail -1 | tee gpurun_out/dense_n2.log
-$TR --nproc-per-node 8 --master-port 29613 tools/run_pt_example.py --iters 31 2> gpurun_out/pt_n8.err | tail -1 | tee gpurun_out/pt_n8.log
-$TR --nproc-per-node 2 --master-port 29614 tools/run_pt_example.py --iters 31 2> gpurun_out/pt_n2.err | tail -1 | tee gpurun_out/pt_n2.log
+$TR --nproc-per-node 8 --master-port 29613 tools/run_pt_example.py --iters 201 2> gpurun_out/pt_n8.err | tail -1 | tee gpurun_out/pt_n8.log
+$TR --nproc-per-node 2 --master-port 29614 tools/run_pt_example.py --iters 201 2> gpurun_out/pt_n2.err | tail -1 | tee gpurun_out/pt_n2.log
