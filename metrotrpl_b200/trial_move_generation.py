@@ -15,7 +15,8 @@ def approve_move(new_state, shared_fields):
     idx = shared_fields["_param_indexes"]
     do_log = shared_fields["do_log"]
     failed = []
-    linear = np.where(do_log, 10 ** new_state, new_state)
+    with np.errstate(over="ignore"):        # both branches of the where() are evaluated
+        linear = np.where(do_log, 10 ** new_state, new_state)
     for i, name in enumerate(order):
         if not shared_fields["active"][i]:
             continue

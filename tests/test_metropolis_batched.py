@@ -270,3 +270,60 @@ def test_native_proposals_equal_the_python_mirror_bit_for_bit():
     # serial path writes
     assert len(ma) == 5
     assert sum(int(m.split()[2]) for m in ma) == len(mb)
+
+
+def _approve_fields(do_log, active):
+    names = ["tauP", "tauN", "somethingelse"]
+    prior = {"tauP": (0.1, np.inf), "tauN": (0.1, np.inf), "somethingelse": (-np.inf, np.inf)}
+    return {"do_log": np.array(do_log, dtype=bool), "active": np.array(active, dtype=bool),
+            "prior_dist": prior, "_param_indexes": {n: i for i, n in enumerate(names)}, "names": names,
+            "hard_bounds": 1}
+
+
+def _native_failed_names(state_in_sampler_scale, sf):
+    """The checks the C implementation reports for one fixed state (move size zero: every attempt
+    proposes the state itself)."""
+    from metrotrpl_b200 import trial_move_generation as tmg
+    import logging
+    msgs = []
+
+    class H(logging.Handler):
+        def emit(self, record):
+            msgs.append(record.getMessage())
+    log = logging.getLogger("approve_native")
+    log.setLevel(logging.WARNING)
+    log.handlers = [H()]
+    dl = sf["do_log"]
+    lin = np.where(dl, 10 ** np.asarray(state_in_sampler_scale, dtype=float), state_in_sampler_scale)
+    rng = np.random.default_rng(0)
+    tmg.make_trial_moves(lin[None, :], np.zeros((1, 3)), sf, rng, log)
+    if not msgs:
+        return []
+    counts = eval(msgs[0].split("per check (first 8 attempts of a chain): ")[1])
+    return sorted(counts)
+
+
+def test_approve_move_reference_cases_python_and_native():
+    """Tests/test_approve_move.py:15-80 (tauN/tauP within two decades, size limits, inactive
+    parameters, parameters that are not log-scaled) - on the Python mirror and on the checks inside
+    trpl_make_trial_moves."""
+    for do_log, scale in (([1, 1, 1], np.log10), ([0, 0, 1], lambda x: np.array(x, dtype=float))):
+        sf = _approve_fields(do_log, [1, 1, 1])
+
+        def st(v):
+            v = np.array(v, dtype=float)
+            out = scale(v)
+            if do_log == [0, 0, 1]:
+                out[2] = np.log10(v[2])
+            return out
+        cases = [([511, 511e2, 1], []), ([511, 511e2 + 1, 1], ["tn_tp_close"]), ([0.11, 0.11, 1], []),
+                 ([0.1, 0.11, 1], ["tauP_size"]), ([0.11, 0.1, 1], ["tauN_size"])]
+        for vals, want in cases:
+            got = approve_move(st(vals), sf)
+            assert sorted(got) == want, (vals, got)
+            if do_log == [1, 1, 1]:
+                # the native path receives log-scaled states: same arithmetic, same verdicts
+                assert _native_failed_names(st(vals), sf) == want, vals
+    sf = _approve_fields([1, 1, 1], [0, 0, 1])
+    assert approve_move(np.log10([0.11, 0.1, 1]), sf) == []
+    assert _native_failed_names(np.log10([0.11, 0.1, 1]), sf) == []
