@@ -88,22 +88,24 @@ def simulate(e_data, P, X, param_info, sim_params, init_params, sim_flags, logge
             local[b0 - lo:b1 - lo] = np.where(np.isnan(ll), -np.inf, ll)
             pending[k] = None
 
-        for i, (b0, b1) in enumerate(blocks):
-            k = i % 2
-            if pending[k] is not None:
-                collect(k)
-            if logger is not None:
-                logger.info(f"Rank {comm.rank}: samples {b0}..{b1} of {n}")
-            c = caches[k]
-            params, aux = c.pack(X[b0:b1], sigmas, np.ones((b1 - b0, 3)))
-            c.ctx.set_problem_if_needed(c.prob)
-            c.ctx.upload(params, aux)
-            c.ctx.run_resident(c.opts())
-            pending[k] = (b0, b1)
-        for k in ((len(blocks)) % 2, (len(blocks) + 1) % 2):       # oldest first
-            if pending[k] is not None:
-                collect(k)
-        caches[1].ctx.close()
+        try:
+            for i, (b0, b1) in enumerate(blocks):
+                k = i % 2
+                if pending[k] is not None:
+                    collect(k)
+                if logger is not None:
+                    logger.info(f"Rank {comm.rank}: samples {b0}..{b1} of {n}")
+                c = caches[k]
+                params, aux = c.pack(X[b0:b1], sigmas, np.ones((b1 - b0, 3)))
+                c.ctx.set_problem_if_needed(c.prob)
+                c.ctx.upload(params, aux)
+                c.ctx.run_resident(c.opts())
+                pending[k] = (b0, b1)
+            for k in ((len(blocks)) % 2, (len(blocks) + 1) % 2):       # oldest first
+                if pending[k] is not None:
+                    collect(k)
+        finally:
+            caches[1].ctx.close()                                      # the private second context
     else:
         for b0, b1 in blocks:
             if logger is not None:

@@ -299,7 +299,8 @@ def _native_failed_names(state_in_sampler_scale, sf):
     tmg.make_trial_moves(lin[None, :], np.zeros((1, 3)), sf, rng, log)
     if not msgs:
         return []
-    counts = eval(msgs[0].split("per check (first 8 attempts of a chain): ")[1])
+    import ast
+    counts = ast.literal_eval(msgs[0].split("per check (first 8 attempts of a chain): ")[1])
     return sorted(counts)
 
 
