@@ -144,6 +144,14 @@ int trpl_timer_end(trpl_handle* h, float* ms);
 /* Write a 256 MiB scratch buffer on the library's stream (evicts the 126 MB L2 between steps). */
 int trpl_flush_l2(trpl_handle* h);
 
+/* Queue order of the next launches: order[q] = index (set * n_meas + meas) of the q-th trajectory
+ * the persistent warps claim.  Any permutation of [0, n_traj) is valid and none changes a result;
+ * longest first shortens the tail of a launch (a Metropolis driver passes the step counts of the
+ * previous iteration's proposals, sorted descending).  Applies to launches with exactly n_traj
+ * trajectories until replaced; n_traj = 0 or order = NULL restores the built-in order
+ * (measurement-major, statically most expensive curves first).  trpl_set_problem clears it. */
+int trpl_set_queue_order(trpl_handle* h, int32_t n_traj, const int32_t* order);
+
 /* Dependent-free DFMA stream on every SM: measured FP64 peak for the roofline denominator. */
 int trpl_fp64_peak_probe(trpl_handle* h, int32_t iters, double* tflops, float* ms);
 

@@ -245,6 +245,7 @@ def load_library() -> C.CDLL:
     lib.trpl_make_trial_moves.argtypes = [C.c_int32, C.c_int32, dp, dp, u8p, u8p, dp, dp, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, u64p, u64p, dp, dp,
                                           C.POINTER(C.c_int64), ip, u32p]
+    lib.trpl_set_queue_order.argtypes = [H, C.c_int32, ip]
     lib.trpl_synchronize.argtypes = [H]
     lib.trpl_timer_begin.argtypes = [H]
     lib.trpl_timer_end.argtypes = [H, C.POINTER(C.c_float)]
@@ -304,6 +305,15 @@ class Context:
     def set_problem_if_needed(self, prob: PackedProblem):
         if self.problem is not prob:
             self.set_problem(prob)
+
+    def set_queue_order(self, order=None):
+        """Order in which the persistent warps claim trajectories (index = set * n_meas + meas) in the
+        next launches of exactly len(order) trajectories; None restores the built-in order."""
+        if order is None:
+            self._check(self.lib.trpl_set_queue_order(self.h, 0, None))
+            return
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        self._check(self.lib.trpl_set_queue_order(self.h, int(order.size), _ptr(order, C.c_int32)))
 
     def set_ladder(self, temps):
         temps = np.ascontiguousarray(temps, dtype=np.float64)

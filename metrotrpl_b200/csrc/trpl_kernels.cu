@@ -57,6 +57,7 @@ struct KernelArgs {
   int n_ladder;
   int* counter;              // work queue head
   const int* meas_order;     // [n_meas] measurement indices, most expensive first
+  const int* queue;          // [n_traj] explicit queue order (trpl_set_queue_order) or null
   double* hist;              // per-warp step histories, 3 * HIST_CAP doubles each
   int* defer_list;           // trajectories handed to the explicit path
   int* defer_count;
@@ -168,9 +169,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_forward_
     if (traj >= a.n_traj) break;
     // queue order is measurement-major with the (statically) most expensive curves first, so that
     // the tail of the launch is made of the cheapest trajectories; results are indexed [set][meas]
-    const int n_sets_q = a.n_traj / a.n_meas;
-    const int qm = traj / n_sets_q;
-    traj = (traj - qm * n_sets_q) * a.n_meas + a.meas_order[qm];
+    if (a.queue) {
+      traj = a.queue[traj];
+    } else {
+      const int n_sets_q = a.n_traj / a.n_meas;
+      const int qm = traj / n_sets_q;
+      traj = (traj - qm * n_sets_q) * a.n_meas + a.meas_order[qm];
+    }
     TrajIn in;
     setup_traj(a, traj, warp, in);
     TrajOut out;
@@ -264,7 +269,8 @@ struct trpl_handle {
   size_t max_nrs = 0, max_nt = 0;
   int irf_rows_needed = 0;
   DevBuf<double> d_params, d_aux, d_logll, d_curves;
-  DevBuf<int> d_status, d_nsteps, d_counter, d_order, d_defer;
+  DevBuf<int> d_status, d_nsteps, d_counter, d_order, d_defer, d_queue;
+  int queue_n = 0;           // trajectories the explicit queue order is for (0: none)
   int n_sets = 0;
   bool curves_valid = false;
   float last_ms = 0.f;
@@ -488,6 +494,7 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
     }
   }
   h->model = model; h->n_meas = n_meas; h->n_times_total = n_times_total; h->max_nx = max_nx;
+  h->queue_n = 0;
   h->all_full = true;
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) h->all_full = false;
   return 0;
@@ -501,6 +508,23 @@ int trpl_set_irf(trpl_handle* h, int32_t n_rows_total, const double* moments) {
   CU(cudaMemcpyAsync(h->d_irf.p, moments, sizeof(double) * 3 * n_rows_total, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   h->have_irf = true;
+  return 0;
+}
+
+int trpl_set_queue_order(trpl_handle* h, int32_t n_traj, const int32_t* order) {
+  if (!h) return fail("null handle");
+  if (n_traj <= 0 || !order) { h->queue_n = 0; return 0; }
+  std::vector<char> seen(n_traj, 0);
+  for (int i = 0; i < n_traj; ++i) {
+    const int t = order[i];
+    if (t < 0 || t >= n_traj || seen[t]) return fail("trpl_set_queue_order: order is not a permutation of [0, n_traj)");
+    seen[t] = 1;
+  }
+  CU(cudaSetDevice(h->device));
+  CU(h->d_queue.reserve(n_traj));
+  CU(cudaMemcpyAsync(h->d_queue.p, order, sizeof(int) * n_traj, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->queue_n = n_traj;
   return 0;
 }
 
@@ -589,6 +613,7 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
   }
   a.counter = h->d_counter.p;
   a.meas_order = h->d_order.p;
+  a.queue = (h->queue_n > 0 && h->queue_n == h->n_sets * h->n_meas) ? h->d_queue.p : nullptr;
   a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;
   memcpy(&a.opt, opts, sizeof(SolverOpts));
   if (h->model == TRPL_MODEL_STD) return launch_npl<MODEL_STD>(h, a);

@@ -54,6 +54,7 @@ class CudaEvaluator:
         self.ladder = np.asarray(shared_fields["_T"], dtype=np.float64)
         self.cache.ctx.set_ladder(self.ladder)
         self.flags = self.cache.flags | _capi.OPT_LADDER
+        self._cost = None       # integrator steps of the previous call's trajectories
 
     def __call__(self, states, sigmas):
         """states [n, n_params], sigmas: list of {meas_type: sigma}.  Returns [n, n_T]."""
@@ -63,7 +64,15 @@ class CudaEvaluator:
         opts = _capi.make_opts(sf.get("rtol", None), sf.get("atol", None), flags=self.flags)
         ctx = self.cache.ctx
         ctx.set_problem_if_needed(self.cache.prob)
-        ctx.loglik_batch(params, aux, opts, want_curves=False)
+        # Longest first: a chain's proposal costs about what its previous proposal cost, and an
+        # iteration is only as fast as its last trajectory (a few hundred trajectories are one or
+        # two waves of the GPU).  The order never changes a result.
+        if self._cost is not None and self._cost.size == n * self.cache.n_meas:
+            ctx.set_queue_order(np.argsort(-self._cost, kind="stable"))
+        else:
+            ctx.set_queue_order(None)
+        _, _, nsteps, _ = ctx.loglik_batch(params, aux, opts, want_curves=False)
+        self._cost = nsteps.sum(axis=-1).ravel()
         lad = ctx.download_ladder(n)
         tot = lad.sum(axis=1)
         return np.where(np.isnan(tot), -np.inf, tot)

@@ -172,3 +172,27 @@ def test_results_do_not_depend_on_what_ran_before(ctx):
 def _backend(ctx, prob, params, aux, opts, want_curves):
     ctx.set_problem(prob)
     return ctx.loglik_batch(params, aux, opts, want_curves=want_curves)
+
+
+def test_queue_order_never_changes_a_result(ctx):
+    """trpl_set_queue_order: any permutation of the trajectory queue gives bit-identical results
+    (every trajectory is self-contained); a non-permutation is rejected."""
+    g, prob, params, aux = pc.staub_problem()
+    opts = _capi.make_opts(RTOL=1e-7)
+    ctx.set_problem(prob)
+    ctx.set_queue_order(None)
+    base = ctx.loglik_batch(params, aux, opts, want_curves=True)
+    n_traj = params.shape[0] * 6
+    rng = np.random.default_rng(3)
+    for order in (rng.permutation(n_traj), np.arange(n_traj)[::-1]):
+        ctx.set_queue_order(order)
+        got = ctx.loglik_batch(params, aux, opts, want_curves=True)
+        for a, b in zip(base, got):
+            np.testing.assert_array_equal(a, b)
+    with pytest.raises(_capi.TrplError):
+        ctx.set_queue_order(np.zeros(n_traj, dtype=np.int32))
+    # an order for another batch size is ignored, not misapplied
+    ctx.set_queue_order(np.arange(12))
+    got = ctx.loglik_batch(params, aux, opts, want_curves=True)
+    np.testing.assert_array_equal(base[0], got[0])
+    ctx.set_queue_order(None)
