@@ -98,7 +98,9 @@ class PathCache:
                 aux[:, m, _capi.A_SCALE_SHIFT] = np.log10(states[:, self.s_idx[m]])
         mtypes = sf["_sim_info"]["meas_types"]
         if isinstance(sigmas, dict):
-            sig = np.array([[sigmas[t] for t in mtypes]] * n_sets, dtype=np.float64)
+            sig = np.broadcast_to(np.array([sigmas[t] for t in mtypes], dtype=np.float64), (n_sets, self.n_meas))
+        elif len(sigmas) > 0 and all(s is sigmas[0] for s in sigmas):
+            sig = np.broadcast_to(np.array([sigmas[0][t] for t in mtypes], dtype=np.float64), (n_sets, self.n_meas))
         else:
             sig = np.array([[s[t] for t in mtypes] for s in sigmas], dtype=np.float64)
         temps = np.asarray(temps, dtype=np.float64).reshape(n_sets, 3)
