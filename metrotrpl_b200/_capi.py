@@ -37,7 +37,7 @@ OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD, OPT_LADDER, OPT_NO_EXPLICIT = 1, 2, 4, 8
 # of its hmax-limited steps, so a tolerance-proportional integrator must not honour it literally.
 # See DESIGN.md "Tolerances".
 DEFAULT_RTOL = 1e-7
-ATOL_CEILING = 1e-20
+ATOL_CEILING = 1e-30
 DEFAULT_MAX_STEPS = 200000
 
 

@@ -104,6 +104,12 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, Tr
   const double tend = in.times[md.n_t - 1];
   V u;
   initial_state<NPL, MODEL>(in, c, m, u);
+  double ex_floor;
+  {
+    real dn_max = splat(0.0);
+    TRPL_UNROLL for (int j = 0; j < NPL; ++j) dn_max = vmax(dn_max, sel(m.real_node[j], vabs(u.n[j] - c.n0), 0.0));
+    ex_floor = EXCESS_RANGE * uni(warp_max(dn_max));
+  }
   Emitter em;
   emitter_init(em);
   int n_acc = 0, n_rej = 0;
@@ -177,12 +183,14 @@ TRPL_FN void run_trajectory_explicit(const TrajIn& in, const SolverOpts& opt, Tr
     real pold[NPL];
     holes<NPL, MODEL>(c, m, u, pold);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      const real iscn = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(us.n[j])), opt.atol));
+      // same scales as the Rosenbrock path (trajectory.h): excess density for N, carrier density for Q
+      const real mx = vmax(vmax(vabs(u.n[j] - c.n0), vabs(us.n[j] - c.n0)), ex_floor);
+      const real iscn = rcp(fmadd(opt.rtol, mx, opt.atol));
       const real iscq = rcp(fmadd(opt.rtol, vmax(vabs(u.n[j]), vabs(pold[j])), opt.atol));
       const real en = er.n[j] * iscn, eq = er.q[j] * iscq;
       real e2 = fmadd(en, en, eq * eq);
       if (MODEL == MODEL_TRAPS) {
-        const real isct = rcp(fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(us.t[j]), vabs(u.n[j]))), opt.atol));
+        const real isct = rcp(fmadd(opt.rtol, vmax(vabs(u.t[j]), vmax(vabs(us.t[j]), mx)), opt.atol));
         const real et = er.t[j] * isct;
         e2 = fmadd(et, et, e2);
       }

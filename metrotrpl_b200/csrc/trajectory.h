@@ -61,6 +61,12 @@ constexpr double RODAS4_GAMMA = 0.25;
 #define TRPL_Q_ERR_WEIGHT 0.03
 #endif
 constexpr double Q_ERR_WEIGHT = TRPL_Q_ERR_WEIGHT;
+// The density error is controlled relative to the excess carrier density down to EXCESS_RANGE
+// times its initial peak (12 decades of dynamic range; below that the scale stays at the floor).
+#ifndef TRPL_EXCESS_RANGE
+#define TRPL_EXCESS_RANGE 1e-12
+#endif
+constexpr double EXCESS_RANGE = TRPL_EXCESS_RANGE;
 // safety factor of the step-size controller (Hairer's RODAS code uses 0.9; with the predictive controller rejections stay below 1% at 0.95)
 #ifndef TRPL_CTL_SAFETY
 #define TRPL_CTL_SAFETY 0.95f
@@ -659,8 +665,10 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
 
   // ---- initial condition (forward_solver.py:100-122) ----
   V u;
+  double ex_floor = 0.0;            // error-control floor of the excess density (EXCESS_RANGE x initial peak)
   {
     real rho_run = splat(0.0);
+    real dn_max = splat(0.0);
     real qloc[NPL];
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
       const ivec i = iadd(node0, j);
@@ -676,6 +684,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
         const real x = fmadd(idx, step, x0);
         dn = (fluence * alpha) * vexp(-(alpha * x));
       }
+      dn_max = vmax(dn_max, sel(m.real_node[j], vabs(dn), 0.0));
       const real n = dn + c.n0, p = dn + c.p0;
       const real rho = (p - c.p0) - (n - c.n0);                  // forward_solver.py:28-29
       rho_run = rho_run + sel(m.real_node[j], rho, 0.0);
@@ -685,6 +694,7 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
     }
     if (MODEL != MODEL_TRAPS) u.t[0] = splat(0.0);
     // Gauss's law: running net charge = in-lane running sum + exclusive warp scan of lane totals
+    ex_floor = EXCESS_RANGE * uni(warp_max(dn_max));
     const real incl = warp_scan_incl(rho_run);
     const real excl = incl - rho_run;
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) u.q[j] = sel(m.real_node[j], qloc[j] + excl, 0.0);
@@ -835,20 +845,23 @@ TRPL_FN bool run_trajectory(const TrajIn& in, const SolverOpts& opt, TrajMem& me
     // seed and the max() has no NaN bookkeeping (non-finite states are caught by `bad`)
     real esum = splat(0.0);
     mask bad = mconst(false);
-    // scale of the charge components: the larger carrier density at the old state.  (The cheaper
-    // bound N + |p0 - n0| over-estimates the holes where space charge depletes them, under-weights
-    // the charge error there and let one of 24576 benchmark trajectories slip to 1.6e-5.)
     real pold[NPL];
-    holes<NPL, MODEL>(fetch_coef(sm, SL::UNI), m, u, pold);
+    const Coef ce = fetch_coef(sm, SL::UNI);
+    holes<NPL, MODEL>(ce, m, u, pold);
     TRPL_UNROLL for (int j = 0; j < NPL; ++j) {
-      const real mx = vmax_fast(vabs(u.n[j]), vabs(us.n[j]));
+      // The density error is measured relative to the EXCESS density N - n0 (floored at ex_floor):
+      // the signal is n0 dP + p0 dN + dN dP, so once the excess has fallen below the dark density a
+      // scale rtol |N| would stop controlling the only thing the readout sees.
+      // The charge keeps the larger carrier density at the old state as its scale (the cheaper bound
+      // N + |p0 - n0| let one of 24576 benchmark trajectories slip to 1.6e-5).
+      const real mx = vmax_fast(vmax_fast(vabs(u.n[j] - ce.n0), vabs(us.n[j] - ce.n0)), ex_floor);
       const real mq = vmax_fast(vabs(u.n[j]), vabs(pold[j]));
       const real iscn = rcp_approx(fmadd(opt.rtol, mx, opt.atol));
       const real iscq = rcp_approx(fmadd(opt.rtol, mq, opt.atol));
       const real en = kk.n[j] * iscn, eq = kk.q[j] * (iscq * Q_ERR_WEIGHT);
       real e2 = fmadd(en, en, eq * eq);
       if (MODEL == MODEL_TRAPS) {
-        const real isct = rcp_approx(fmadd(opt.rtol, vmax_fast(vabs(u.t[j]), vmax_fast(vabs(us.t[j]), vabs(u.n[j]))), opt.atol));
+        const real isct = rcp_approx(fmadd(opt.rtol, vmax_fast(vabs(u.t[j]), vmax_fast(vabs(us.t[j]), mx)), opt.atol));
         const real et = kk.t[j] * isct;
         e2 = fmadd(et, et, e2);
       }

@@ -126,7 +126,12 @@ def bayes(N, P, init_params, sim_params, e_data, sim_flags, param_info, logger=N
     min_X = np.array([param_info["prior_dist"][n][0] if act[n] else param_info["init_guess"][n] for n in names])
     max_X = np.array([param_info["prior_dist"][n][1] if act[n] else param_info["init_guess"][n] for n in names])
     do_log = np.array([param_info["do_log"][n] for n in names])
+    comm = comm or Comm()
     N, P, X = make_grid(N, P, min_X, max_X, do_log, sim_flags)
+    # The grid comes from the unseeded global np.random (as in the reference, which never shards):
+    # every rank would draw its own.  Rank 0's grid is the grid; the others receive it, so the
+    # likelihood slices that simulate() gathers belong to the X that is returned and exported.
+    X = comm.broadcast_array(X)
     if logger is not None:
         logger.info(f"Initializing {len(X)} random samples")
     param_info["trial_move"] = np.array([param_info["trial_move"][p] for p in names], dtype=float)

@@ -62,6 +62,14 @@ class Comm:
         parts = [recv[r][:counts[r][1] - counts[r][0]].cpu().numpy() for r in range(self.world)]
         return np.concatenate(parts, axis=0)
 
+    def broadcast_array(self, x, src=0):
+        """Rank `src`'s float64 array on every rank (same shape everywhere)."""
+        if self.dist is None:
+            return x
+        t = self.torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(self._dev())
+        self.dist.broadcast(t, src=src)
+        return t.cpu().numpy()
+
     def max(self, x: float) -> float:
         if self.dist is None:
             return x

@@ -69,6 +69,12 @@ class PathCache:
                     out[m] = idx[name]
             return out
 
+        if sf.get("ini_mode", "density") != "fluence" and (sf.get("fittable_fluences", None) is not None
+                                                             or sf.get("fittable_absps", None) is not None):
+            # trial_move_evaluation.py:44,51 multiplies iniPar[0] / iniPar[1] whatever the mode; with a
+            # density profile those are the first two nodes' densities, not a fluence or an absorption
+            # coefficient.  That is not reproduced; it is refused.
+            raise ValueError("fittable_fluences / fittable_absps need ini_mode == 'fluence'")
         self.f_idx = group_index(sf.get("fittable_fluences", None), "_f")
         self.a_idx = group_index(sf.get("fittable_absps", None), "_a")
         self.s_idx = group_index(sf.get("scale_factor", None), "_s")

@@ -92,6 +92,18 @@ def _approve_rows(new_states, shared_fields):
     return ok
 
 
+def _advance_keeping_buffer(bitgen, n):
+    """PCG64.advance() clears the generator's buffered half-word (`has_uint32` / `uinteger`).  The
+    reference never advances: a pending 32-bit half left by an `integers()` swap draw
+    (metropolis.py:71) is consumed by the next one, so the buffer is carried across the jump."""
+    before = bitgen.state
+    bitgen.advance(n)
+    after = bitgen.state
+    after["has_uint32"] = before["has_uint32"]
+    after["uinteger"] = before["uinteger"]
+    bitgen.state = after
+
+
 MAX_LOGGED_FAILS = 8       # include/metrotrpl_b200.h TRPL_MAX_LOGGED_FAILS
 _native = {"lib": None, "tried": False}
 
@@ -144,7 +156,7 @@ def _make_trial_moves_native(lib, cur, trial_moves, shared_fields, RNG, logger):
         n_failed.ctypes.data_as(C.POINTER(C.c_int32)), masks.ctypes.data_as(C.POINTER(C.c_uint32)))
     if rc != 0:
         raise RuntimeError(lib.trpl_last_error().decode())
-    RNG.bit_generator.advance(n_draws.value)
+    _advance_keeping_buffer(RNG.bit_generator, n_draws.value)
     proposals = np.where(dl[None, :], 10 ** proposals, proposals)
     if logger is not None and n_failed.any():
         # The reference warns once per failed attempt ("Failed checks: [...]"); with hundreds of hot
@@ -211,7 +223,7 @@ def make_trial_moves(current_states, trial_moves, shared_fields, RNG, logger=Non
         if m < n_chains:
             # chain m needs retries: rewind to just before its first attempt and replay serially
             bitgen.state = state0
-            bitgen.advance(n_ok * (n_par + 1))
+            _advance_keeping_buffer(bitgen, n_ok * (n_par + 1))
             proposals[m] = make_trial_move(cur[m], trial_moves[m], shared_fields, RNG, logger)
             u[m] = RNG.random()
             m += 1

@@ -3,34 +3,46 @@
 
     backend(prob, params, aux, opts, want_curves) -> (logll[n_sets,n_meas,3], status, nsteps, curves)
 
-Tolerances (stated here once, asserted below):
-  CURVE_TOL_DEFAULT = 1e-4   relative, per time step, against the reference run at its default
-                             tolerances, wherever the reference is converged to 5e-5 itself
-                             (all points of the clean states, top three decades of the others)
-  CURVE_TOL_TIGHT   = 1e-5   relative, per time step, against the reference run at rtol=1e-10 /
-                             atol=1e-14, in the top three decades of every curve (all 17 states)
-  CURVE_TOL_CLEAN   = 1e-6   the same on the states whose reference is converged everywhere
-  LOGLL_TOL         = 1e-6   relative, log-likelihood against the converged reference likelihood
-  LOGLL_TOL_DEFAULT = 1e-5   relative, against the reference's own default-tolerance eval_trial_move
-                             (its solver error alone is up to 4.5e-6 on these states)
+What "the truth" is.  The reference's LSODA run is not converged once a curve
+has decayed a few decades (its default atol = 1e-10 nm^-3 exceeds the densities; tightening it to
+1e-14 still leaves errors of atol / excess density, and beyond that SciPy's LSODA stalls - measured,
+see DESIGN.md).  Every fixture state is therefore checked against THREE routes that share no time
+integrator:
+  (A) the integrator under test at rtol = 1e-9 (CPU) / 1e-10 (GPU): self-convergence;
+  (B) the reference's algorithm (SciPy LSODA on the bit-exact right-hand side) at rtol 1e-10 /
+      atol 1e-14, inside the part of the curve where that run can be accurate (top three decades);
+  (C) the linear-regime asymptote: at low injection the reference's equations are linear and every
+      curve ends as exp(-lambda t) with lambda an eigenvalue of the reference's Jacobian at
+      equilibrium (oracle/excess_model.decay_rates, LAPACK, no time stepping at all).
+Tolerances (stated here once, asserted below; RANGE = 14 decades below each curve's first point,
+the dynamic range the error control covers - trajectory.h EXCESS_RANGE plus the initial transient):
+  CURVE_TOL         = 1e-5   relative per time step, run under test vs route (A), every point of
+                             every state within RANGE  (north star: <= 1e-4)
+  CURVE_TOL_LSODA   = 1e-5   route (A) vs route (B), top three decades of every curve
+  RATE_TOL          = 2e-6   log-slope of a deep single-exponential tail vs route (C)
+  CURVE_TOL_DEFAULT = 1e-4   vs the reference at its DEFAULT tolerances, every point within RANGE,
+                             up to that run's own distance from route (A) (triangle inequality; no mask)
+  LOGLL_TOL         = 1e-6   relative, every state whose converged log-likelihood is > -1e4
+                             (north star: <= 1e-6), at three temperatures
 """
 import os
 
 import numpy as np
 
 from metrotrpl_b200 import _capi
+from oracle import excess_model as exm
 from oracle import trpl_oracle as orc
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-CURVE_TOL_DEFAULT = 1e-4
-CURVE_TOL_TIGHT = 1e-5
+CURVE_TOL = 1e-5
+CURVE_TOL_LSODA = 1e-5
 CURVE_TOL_CLEAN = 1e-6
+RATE_TOL = 2e-6
+CURVE_TOL_DEFAULT = 1e-4
 LOGLL_TOL = 1e-6
-LOGLL_TOL_DEFAULT = 1e-5
-# states of staub6.npz whose reference curves are converged (default vs tight <= 1e-4) over the
-# whole time window; the others decay by >9 decades and the reference itself is not reproducible
-CLEAN_STATES = [0, 1, 3, 5, 8, 12, 16]
+RANGE_DECADES = 14.0
+LOGLL_FLOOR = -1e4          # states below this are certain rejections: decision parity only
 
 
 def staub_problem():
@@ -46,58 +58,143 @@ def staub_problem():
     return g, prob, params, aux
 
 
-def check_staub(backend, rtol=1e-7):
+def real3_problem():
+    """configs[0] on the reference's real data (tools/make_golden.py gen_real3)."""
+    g = np.load(os.path.join(GOLDEN, "staub_real3.npz"))
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    n_t = g["n_t"]
+    times = [g["t"][m, :n_t[m]] for m in range(3)]
+    vals = [g["vals"][m, :n_t[m]] for m in range(3)]
+    uncs = [g["uncs"][m, :n_t[m]] for m in range(3)]
+    sim = {"lengths": list(g["lengths"]), "nx": [int(g["nx"])] * 3, "meas_types": ["TRPL"] * 3, "num_meas": 3}
+    prob = _capi.pack_problem(sim, g["ini"], times, vals, uncs)
+    params = _capi.pack_params(g["states"], idx, g["units"])
+    aux = _capi.default_aux(params.shape[0], 3, [float(g["sigma"])] * 3, temps=tuple(g["temps"]))
+    return g, prob, params, aux, times, vals, uncs
+
+
+def _model_args(state, units, idx, length, nx):
+    s = np.asarray(state, dtype=float) * units
+    lam = orc.Q_C / (s[idx["eps"]] * orc.EPS0)
+    return (nx, length / nx, s[idx["n0"]], s[idx["p0"]], s[idx["mu_n"]], s[idx["mu_p"]], s[idx["ks"]],
+            s[idx["Cn"]], s[idx["Cp"]], s[idx["Sf"]], s[idx["Sb"]], s[idx["tauN"]], s[idx["tauP"]], lam,
+            s[idx["Tm"]])
+
+
+def check_against_converged(backend, g, prob, params, aux, times, vals, uncs, rtol=1e-7, tight_rtol=1e-9,
+                            pl_lsoda_tight=None, pl_default=None, min_tails=3):
+    """Every state of a fixture against the three truth routes of the module docstring."""
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    nS, nM = params.shape[0], len(times)
+    sigma = float(g["sigma"])
+    ll, status, nsteps, curves = backend(prob, params, aux, _capi.make_opts(RTOL=rtol), True)
+    _, _, ns_t, curves_t = backend(prob, params, aux, _capi.make_opts(RTOL=tight_rtol), True)
+    off = np.concatenate([[0], np.cumsum([len(t) for t in times])])
+    cur = [[curves[s, off[m]:off[m + 1]] for m in range(nM)] for s in range(nS)]
+    tru = [[curves_t[s, off[m]:off[m + 1]] for m in range(nM)] for s in range(nS)]
+    rep = {"rtol": rtol, "truth_rtol": tight_rtol}
+    worst = {"curve": 0.0, "lsoda": 0.0, "default_excess": 0.0, "rate": 0.0}
+    ref_default_dev = np.zeros(nS)
+    n_tails = 0
+    for s in range(nS):
+        for m in range(nM):
+            T, c = tru[s][m], cur[s][m]
+            with np.errstate(all="ignore"):
+                in_range = T >= 10.0 ** (-RANGE_DECADES) * T[0]
+                e = np.where(in_range, np.abs(c / T - 1), 0.0)
+            worst["curve"] = max(worst["curve"], float(e.max()))
+            assert e.max() <= CURVE_TOL * max(1.0, rtol / 1e-7), (s, m, e.max())
+            if pl_lsoda_tight is not None:
+                B = pl_lsoda_tight[s][m][:len(T)]
+                top = B >= 1e-3 * B[0]
+                eb = np.abs(T[top] / B[top] - 1).max()
+                worst["lsoda"] = max(worst["lsoda"], float(eb))
+                assert eb <= CURVE_TOL_LSODA, (s, m, eb)
+            if pl_default is not None:
+                D = pl_default[s][m][:len(T)]
+                with np.errstate(all="ignore"):
+                    ok = in_range & (D > 0)
+                    # log ratios, so that the triangle inequality is exact however far the
+                    # reference's own run has drifted (it reaches the min_y floor decades early)
+                    d_ref = np.where(ok, np.abs(np.log(D) - np.log(T)), 0.0)  # the reference's own solver error
+                    d_us = np.where(ok, np.abs(np.log(c) - np.log(D)), 0.0)
+                ref_default_dev[s] = max(ref_default_dev[s], float(d_ref.max()))
+                excess = float((d_us - d_ref).max())
+                worst["default_excess"] = max(worst["default_excess"], excess)
+                assert excess <= CURVE_TOL_DEFAULT, (s, m, excess)
+            # route (C): a deep, single-exponential tail decays at an eigenvalue of the reference's
+            # Jacobian at equilibrium
+            t = times[m]
+            with np.errstate(all="ignore"):
+                k = np.where((T < 1e-8 * T[0]) & (T > 1e-12 * T[0]))[0]
+            if len(k) >= 6:
+                h = len(k) // 2
+                def slope(i, j, y=T):
+                    return -(np.log(y[j]) - np.log(y[i])) / (t[j] - t[i])
+                s1, s2 = slope(k[0], k[h]), slope(k[h], k[-1])
+                if abs(s1 / s2 - 1) <= 2e-7:              # one mode left
+                    rates = exm.decay_rates(*_model_args(g["states"][s], g["units"], idx,
+                                                         float(g["lengths"][m]), int(g["nx"])))
+                    sl_t, sl_c = slope(k[0], k[-1]), slope(k[0], k[-1], c)
+                    dev_t = np.abs(sl_t / rates - 1).min()
+                    dev_c = np.abs(sl_c / rates - 1).min()
+                    worst["rate"] = max(worst["rate"], float(dev_t), float(dev_c))
+                    assert dev_t <= RATE_TOL and dev_c <= RATE_TOL, (s, m, sl_t, sl_c, dev_t, dev_c)
+                    n_tails += 1
+    assert n_tails >= min_tails, n_tails
+    rep["max_curve_err_vs_converged_within_range"] = worst["curve"]
+    rep["max_converged_vs_lsoda_tight_top3decades"] = worst["lsoda"]
+    rep["max_excess_over_reference_default_error"] = worst["default_excess"]
+    rep["deep_tails_checked_against_jacobian_eigenvalues"] = n_tails
+    rep["max_decay_rate_rel_err"] = worst["rate"]
+    # log-likelihood: every state above LOGLL_FLOOR, three temperatures, against the likelihood of
+    # the converged curves (the oracle's restatement of one_sim_likelihood, pinned to the reference)
+    rows = []
+    worst_ll = 0.0
+    for s in range(nS):
+        conv = [sum(orc.curve_loglik(tru[s][m], times[m], times[m], vals[m], uncs[m], sigma, T=float(temp))
+                    for m in range(nM)) for temp in g["temps"]]
+        ours = [ll[s, :, k].sum() for k in range(3)]
+        if conv[0] > LOGLL_FLOOR:
+            rel = max(abs(ours[k] / conv[k] - 1) for k in range(3))
+            ref_rel = abs(float(g["logll"][s]) / conv[0] - 1)
+            rows.append((s, float(conv[0]), float(ours[0]), float(rel), float(g["logll"][s]), float(ref_rel),
+                         float(ref_default_dev[s])))
+            worst_ll = max(worst_ll, rel)
+            assert rel <= LOGLL_TOL * max(1.0, rtol / 1e-7), (s, conv, ours, rel)
+            assert np.all((status[s] & ~_capi.ST_FLOORED) == 0)
+        else:
+            # certain rejection for everybody: only the decision is compared
+            assert ours[0] < 0.999 * LOGLL_FLOOR, (s, conv[0], ours[0])
+            assert float(g["logll"][s]) < 0.5 * LOGLL_FLOOR, (s, g["logll"][s])
+    rep["logll_rows_[state,converged,ours,rel,reference_default,ref_rel,ref_curve_dev]"] = rows
+    rep["max_logll_rel_vs_converged"] = worst_ll
+    rep["states_above_floor"] = len(rows)
+    rep["mean_steps"] = float(nsteps[..., 0].mean())
+    rep["mean_rejected"] = float(nsteps[..., 1].mean())
+    rep["mean_steps_truth_run"] = float(ns_t[..., 0].mean())
+    return rep
+
+
+def check_staub(backend, rtol=1e-7, tight_rtol=1e-9):
+    """The six-curve staub example (Inputs/mcmc0.txt grid and initial conditions), 17 states."""
     g, prob, params, aux = staub_problem()
     t = g["t"]
-    nS = params.shape[0]
-    ll, status, nsteps, curves = backend(prob, params, aux, _capi.make_opts(RTOL=rtol), True)
-    cur = curves.reshape(nS, 6, len(t))
-    T, D = g["pl_tight"], g["pl_default"]
-    report = {}
-    # (1) every state, top three decades, against the converged reference
-    win = T >= 1e-3 * T[:, :, :1]
-    with np.errstate(all="ignore"):
-        e_tight = np.where(win, np.abs(cur / T - 1), 0.0)
-    report["max_err_vs_tight_top3decades"] = float(e_tight.max())
-    assert e_tight.max() <= CURVE_TOL_TIGHT, e_tight.max()
-    # (2) clean states, every time step
-    e_clean = np.abs(cur[CLEAN_STATES] / T[CLEAN_STATES] - 1)
-    report["max_err_vs_tight_clean"] = float(e_clean.max())
-    assert e_clean.max() <= CURVE_TOL_CLEAN * max(1.0, rtol / 1e-7), e_clean.max()
-    # (3) against the default-tolerance reference wherever that reference is itself converged
-    with np.errstate(all="ignore"):
-        clean = np.zeros(T.shape, dtype=bool)
-        clean[CLEAN_STATES] = True
-        ref_ok = (np.abs(D / T - 1) <= 5e-5) & (win | clean)
-    assert ref_ok.mean() > 0.5
-    with np.errstate(all="ignore"):
-        e_def = np.where(ref_ok, np.abs(cur / D - 1), 0.0)
-    report["max_err_vs_default_where_ref_converged"] = float(e_def.max())
-    report["frac_points_ref_converged"] = float(ref_ok.mean())
-    assert e_def.max() <= CURVE_TOL_DEFAULT, e_def.max()
-    # every clean-state point of the default reference qualifies
-    assert ref_ok[CLEAN_STATES].mean() > 0.99
-    # (4) log-likelihood, three temperatures
-    worst_t, worst_d = 0.0, 0.0
-    for s in CLEAN_STATES:
-        for k, temp in enumerate(g["temps"]):
-            ll_conv = sum(orc.curve_loglik(T[s, m], t, t, g["vals"][m], g["uncs"][m], float(g["sigma"]),
-                                           T=float(temp)) for m in range(6))
-            ours = ll[s, :, k].sum()
-            worst_t = max(worst_t, abs(ours / ll_conv - 1))
-            worst_d = max(worst_d, abs(ours / g["logll_T"][s, k] - 1))
-    report["max_logll_rel_vs_converged_ref"] = worst_t
-    report["max_logll_rel_vs_default_ref"] = worst_d
-    assert worst_t <= LOGLL_TOL * max(1.0, rtol / 1e-7), worst_t
-    assert worst_d <= LOGLL_TOL_DEFAULT, worst_d
-    # (5) the hopeless proposals are hopeless for both (decision parity): reference logll < -5000
-    hopeless = [s for s in range(nS) if s not in CLEAN_STATES and g["logll"][s] < -5000]
-    for s in hopeless:
-        assert ll[s, :, 0].sum() < -5000
-    assert np.all((status[CLEAN_STATES] & ~_capi.ST_FLOORED) == 0)
-    report["mean_steps"] = float(nsteps[..., 0].mean())
-    report["mean_rejected"] = float(nsteps[..., 1].mean())
-    return report
+    return check_against_converged(backend, g, prob, params, aux, [t] * 6, list(g["vals"]), list(g["uncs"]),
+                                   rtol=rtol, tight_rtol=tight_rtol, pl_lsoda_tight=g["pl_tight"],
+                                   pl_default=g["pl_default"], min_tails=8)
+
+
+def check_real3(backend, rtol=1e-7, tight_rtol=1e-9):
+    """configs[0] on the reference's real measurement (values and uncertainties of
+    Inputs/real_staub_aug_corr_renoised.csv), 17 states."""
+    g, prob, params, aux, times, vals, uncs = real3_problem()
+    n_t = g["n_t"]
+    D = [[g["pl_default"][s, m, :n_t[m]] for m in range(3)] for s in range(params.shape[0])]
+    return check_against_converged(backend, g, prob, params, aux, times, vals, uncs, rtol=rtol,
+                                   tight_rtol=tight_rtol, pl_default=D, min_tails=3)
 
 
 def _known_units():
@@ -400,3 +497,135 @@ def check_hmax_option(backend):
     T = g["pl_tight"][0].reshape(-1)
     np.testing.assert_allclose(c1[0], T, rtol=5e-7)
     return {"free_steps": n0[0, :, 0].tolist(), "capped_steps": n1[0, :, 0].tolist()}
+
+
+def check_reference_unit_cases(backend):
+    """Parameter sets of the reference's remaining unit tests, replayed through the backend:
+      Tests/test_forward_solver.py:40-327  test_solver_nothing / LI_SRH / LI_rad / LI_auger
+      Tests/test_metropolis.py:199-380     test_solve_depletion / test_solve_traps / test_solve_iniPar
+      Tests/test_eval_trial_move.py:210-279 test_run_iter_scale
+    The reference's own assertions on N, P are `assert_almost_equal` at 7 decimals on densities of
+    1e-11 nm^-3, which any output passes; here each case is held to the closed form its docstring
+    names, through the signal the path returns (a radiative probe ks = 1e-20 cm^3/s where the
+    reference's parameter set has no readout at all)."""
+    names = ["n0", "p0", "mu_n", "mu_p", "ks", "Cn", "Cp", "Sf", "Sb", "tauN", "tauP", "eps", "Tm", "m"]
+    uc = {"n0": 1e-21, "p0": 1e-21, "mu_n": 1e5, "mu_p": 1e5, "ks": 1e12, "Cn": 1e33, "Cp": 1e33,
+          "Sf": 1e-2, "Sb": 1e-2}
+    units = np.array([uc.get(n, 1) for n in names], dtype=float)
+    idx = {n: i for i, n in enumerate(names)}
+    nx, L = 100, 1000.0
+    t = np.linspace(0, 10, 101)
+    sim = {"lengths": [L], "nx": [nx], "meas_types": ["TRPL"], "num_meas": 1}
+    opts = _capi.make_opts(RTOL=1e-9, flags=_capi.OPT_NO_LIKELIHOOD)
+    aux1 = _capi.default_aux(1, 1, [1.0])
+    N0 = 1e10 * 1e-21
+    base = {"n0": 0, "p0": 0, "mu_n": 0, "mu_p": 0, "ks": 0, "Sf": 0, "Sb": 0, "Cn": 0, "Cp": 0,
+            "tauN": 1e99, "tauP": 1e99, "eps": 10, "Tm": 300, "m": 0}
+    out = {}
+
+    def pl_of(guess, ini=None, tt=t, model="std", extra_names=(), extra_units=(), min_y=None, meas="TRPL",
+              ini_mode="density", length=L):
+        nm = names + list(extra_names)
+        un = np.concatenate([units, np.array(extra_units, dtype=float)]) if extra_names else units
+        ix = {n: i for i, n in enumerate(nm)}
+        st = np.array([[guess[n] for n in nm]], dtype=float)
+        sm = {"lengths": [length], "nx": [nx], "meas_types": [meas], "num_meas": 1}
+        prob = _capi.pack_problem(sm, [1e10 * np.ones(nx) if ini is None else ini], [tt], None, None, model=model,
+                                  ini_mode=ini_mode, min_y=min_y)
+        _, s, ns, cur = backend(prob, _capi.pack_params(st, ix, un, model=model), aux1, opts, True)
+        return cur[0], s[0], ns[0]
+
+    probe = 1e-20 * 1e12                  # ks of the radiative probe in model units
+    # test_solver_nothing (:40-84): no process at all; ks = 0 means no PL: the curve is min_y throughout
+    cur, s, _ = pl_of(base)
+    assert np.all(cur == np.finfo(float).tiny)
+    cur, s, _ = pl_of(dict(base, ks=1e-20))
+    np.testing.assert_allclose(cur, probe * N0 ** 2 * L * 1e23 * np.ones_like(t), rtol=1e-9)
+    # test_solver_LI_SRH (:140-185): tauN = 1, tauP = 1e99, n0 = p0 = 0.  With N = P the SRH rate is
+    # N P / (tauN P + tauP N) = N / (1 + 1e99): nothing decays
+    cur, s, _ = pl_of(dict(base, ks=1e-20, tauN=1.0))
+    np.testing.assert_allclose(cur, probe * N0 ** 2 * L * 1e23 * np.ones_like(t), rtol=1e-9)
+    # test_solver_LI_rad (:235-285): p0 = 1 cm^-3, ks = 1e-11, tauN = tauP = 1:
+    # dN/dt = -N/2 - ks N^2 (p0 is 1e-10 of N0)  ->  N = N0 e^{-t/2} / (1 + 2 ks N0 (1 - e^{-t/2}))
+    ks = 1e-11 * 1e12
+    cur, s, _ = pl_of(dict(base, p0=1.0, ks=1e-11, tauN=1.0, tauP=1.0))
+    Nt = N0 * np.exp(-t / 2) / (1 + 2 * ks * N0 * (1 - np.exp(-t / 2)))
+    np.testing.assert_allclose(cur, ks * Nt ** 2 * L * 1e23, rtol=1e-7)
+    # test_solver_LI_auger (:287-327): p0 = 10 cm^-3, Cp = 1e-29: the Auger term is 1e-29 of the SRH one
+    cur, s, _ = pl_of(dict(base, p0=10.0, Cp=1e-29, ks=1e-20, tauN=1.0, tauP=1.0))
+    np.testing.assert_allclose(cur, probe * (N0 * np.exp(-t / 2)) ** 2 * L * 1e23, rtol=1e-7)
+    # test_solve_traps (Tests/test_metropolis.py:270-327): null trap parameters == 'std'; known final density
+    t100 = np.linspace(0, 100, 1001)
+    tg = dict(base, ks=1e-11, eps=1, kC=0, Nt=0, tauE=1e99)
+    ini20 = 1e20 * np.ones(nx)
+    cur_t, s, _ = pl_of(tg, ini=ini20, tt=t100, model="traps", extra_names=("kC", "Nt", "tauE"),
+                        extra_units=(1e12, 1e-21, 1.0))
+    cur_s, s, _ = pl_of(tg | {"m": 0}, ini=ini20, tt=t100)
+    out_dN = 0.0009900990095719482                                  # the reference test's constant
+    expected = ks * out_dN ** 2 * L * 1e23
+    assert abs(cur_t[-1] / expected - 1) < 1e-7                     # reference: 7 decimals of the ratio
+    np.testing.assert_allclose(cur_t, cur_s, rtol=1e-9)
+    out["traps_final_rel"] = float(cur_t[-1] / expected - 1)
+    # test_solve_depletion (:199-268): Grid.min_y truncates the curve (PL and TRTS)
+    dg = dict(base, mu_n=1, mu_p=1, ks=2e-10, eps=1)
+    ini18 = 1e18 * np.ones(nx)
+    full, s, _ = pl_of(dg, ini=ini18, tt=t100)
+    assert len(full) == len(t100) and np.all(full > 0)
+    PL0 = 2e-10 * 1e12 * (1e18 * 1e-21) ** 2 * L * 1e23
+    np.testing.assert_allclose(full[0], PL0, rtol=1e-12)
+    cut, s, _ = pl_of(dg, ini=ini18, tt=t100, min_y=[PL0 * 1e-2])
+    assert cut.min() >= PL0 * 1e-2 and np.all(cut[-10:] == PL0 * 1e-2)
+    first = int(np.argmax(full < PL0 * 1e-2))
+    np.testing.assert_allclose(cut[:first], full[:first], rtol=1e-9)
+    assert np.all(cut[first:] == PL0 * 1e-2) and (s & _capi.ST_FLOORED)
+    TR0 = orc.Q_C * (2 * 1e5) * (1e18 * 1e-21) * L * 1e9
+    tr_full, s, _ = pl_of(dg, ini=ini18, tt=t100, meas="TRTS", min_y=[TR0 * 1e-10])
+    assert len(tr_full) == len(t100) and tr_full.min() > TR0 * 1e-10
+    np.testing.assert_allclose(tr_full[0], TR0, rtol=1e-12)
+    tr_cut, s, _ = pl_of(dg, ini=ini18, tt=t100, meas="TRTS", min_y=[TR0 * 1e-1])
+    assert tr_cut.min() >= TR0 * 1e-1 and np.all(tr_cut[-10:] == TR0 * 1e-1)
+    # test_solve_iniPar (:329-380): [fluence, alpha] (two values, no direction) == the explicit profile
+    xs = np.linspace(L / nx / 2, L - L / nx / 2, nx)
+    prof = 1e15 * 6e4 * np.exp(-6e4 * xs * 1e-7)
+    ig = dict(base, ks=1e-11, eps=1)
+    by_vals, s, _ = pl_of(ig, ini=prof, tt=t100)
+    by_par, s, _ = pl_of(ig, ini=np.array([1e15, 6e4]), tt=t100, ini_mode="fluence")
+    np.testing.assert_allclose(by_par, by_vals, rtol=1e-9)
+    # test_run_iter_scale (Tests/test_eval_trial_move.py:210-279): scale factors with constraint
+    # groups, through the product's PathCache.pack (group lookup) where the backend is the library
+    out["scale"] = check_scale_groups(backend)
+    return out
+
+
+def check_scale_groups(backend):
+    """test_run_iter_scale: `_s0`, `_s1` chosen per constraint group ((0,2,4), (1,3,5)) so that both
+    curves match the flat measurement: the likelihood is ~0 (reference: 0 to 0 decimals)."""
+    from metrotrpl_b200.utils import search_c_grps
+    names = ["n0", "p0", "mu_n", "mu_p", "ks", "Cn", "Cp", "Tm", "Sf", "Sb", "tauN", "tauP", "eps", "_s0", "_s1"]
+    uc = {"n0": 1e-21, "p0": 1e-21, "mu_n": 1e5, "mu_p": 1e5, "ks": 1e12, "Sf": 1e-2, "Sb": 1e-2}
+    units = np.array([uc.get(n, 1) for n in names], dtype=float)
+    idx = {n: i for i, n in enumerate(names)}
+    guess = {"n0": 0, "p0": 0, "mu_n": 0, "mu_p": 0, "ks": 1e-20, "Sf": 0, "Sb": 0, "Cn": 0, "Cp": 0, "Tm": 300,
+             "tauN": 1e99, "tauP": 1e99, "eps": 10, "_s0": 2e-17 ** -1, "_s1": 2e-15 ** -1}
+    state = np.array([[guess[n] for n in names]], dtype=float)
+    t = np.linspace(0, 100, 1001)
+    sim = {"lengths": [2000, 2000], "nx": [128, 128], "meas_types": ["TRPL", "TRPL"], "num_meas": 2}
+    ini = np.array([1e15 * np.ones(128), 1e16 * np.ones(128)])
+    vals = [np.ones(1001) * 23] * 2
+    uncs = [np.ones(1001) * 1e-99] * 2
+    spec = (0.02, [0, 1, 2, 3, 4, 5], [(0, 2, 4), (1, 3, 5)])
+    prob = _capi.pack_problem(sim, ini, [t, t], vals, uncs)
+    params = _capi.pack_params(state, idx, units)
+    aux = _capi.default_aux(1, 2, [1.0, 1.0])
+    for m in range(2):
+        aux[0, m, _capi.A_SCALE_SHIFT] = np.log10(state[0, idx[f"_s{search_c_grps(spec[2], m)}"]])
+    ll, st, ns, cur = backend(prob, params, aux, _capi.make_opts(RTOL=1e-5, ATOL=1e-8), True)
+    total = ll[0, :, 0].sum()
+    np.testing.assert_almost_equal(total, 0, decimal=0)             # the reference's criterion
+    sf = {"units": units, "model": "std", "hmax": 4, "rtol": 1e-10, "atol": 1e-18}
+    want, _ = orc.state_loglik(state[0], sim, ini, [t, t], vals, uncs, idx, units, {"TRPL": 1.0},
+                               rtol=1e-10, atol=1e-18,
+                               scale_shifts=[aux[0, m, _capi.A_SCALE_SHIFT] for m in range(2)])
+    ll9, _, _, _ = backend(prob, params, aux, _capi.make_opts(RTOL=1e-9), False)
+    assert abs(ll9[0, :, 0].sum() - want) <= 1e-6 * abs(want) + 1e-9, (ll9[0, :, 0].sum(), want)
+    return {"logll_rtol_1e-5": float(total), "logll_rtol_1e-9": float(ll9[0, :, 0].sum()), "oracle": float(want)}

@@ -19,8 +19,16 @@ def test_staub_fixture_rtol_1e7():
     print(rep)
 
 
+def test_real_staub_data_three_curves():
+    print(pc.check_real3(backend, rtol=1e-7))
+
+
 def test_known_answers_of_reference_tests():
     print(pc.check_known_answers(backend))
+
+
+def test_reference_unit_test_parameter_sets():
+    print(pc.check_reference_unit_cases(backend))
 
 
 def test_closed_forms():

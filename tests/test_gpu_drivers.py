@@ -145,3 +145,49 @@ def test_dense_sampling_pipeline_equals_block_by_block():
           "ini_mode": "density", "rtol": 1e-7, "atol": None}
     ref = eval_trial_moves(X, np.ones(37), {"TRPL": 0.05}, sf).logll
     np.testing.assert_array_equal(outs[0], ref)
+
+
+def test_scale_fluence_and_absorption_factors_against_the_oracle():
+    """`_s#`, `_f#`, `_a#` (trial_move_evaluation.py:38-60) end to end through PathCache and the
+    kernel, fluence mode, with constraint groups; the oracle gets the factors applied to a fresh copy
+    of the initial condition (the reference multiplies _init_params in place, so its factor
+    compounds from call to call - documented deviation)."""
+    from metrotrpl_b200.trial_move_evaluation import eval_trial_moves
+    names = list(NAMES) + ["_s0", "_s1", "_f0", "_f2", "_a1"]
+    units = np.array([UNITS.get(n, 1) for n in names], dtype=float)
+    idx = {n: i for i, n in enumerate(names)}
+    t = np.linspace(0, 60, 61)
+    sim = {"lengths": [311.0, 500.0, 311.0], "nx": [64, 64, 64], "meas_types": ["TRPL"] * 3, "num_meas": 3}
+    inis = [np.array([2e12, 6e4, 1.0]), np.array([6e12, 5e4, -1.0]), np.array([2e13, 6e4, 1.0])]
+    rng = np.random.default_rng(3)
+    vals = [17.0 - 0.02 * t + 0.01 * rng.standard_normal(61) for _ in range(3)]
+    uncs = [np.full(61, 0.03)] * 3
+    sf = {"_sim_info": sim, "_init_params": [i.copy() for i in inis], "_times": [t] * 3, "_vals": vals,
+          "_uncs": uncs, "_param_indexes": idx, "units": units, "model": "std", "ini_mode": "fluence",
+          "rtol": 1e-8, "atol": None, "hmax": 4,
+          "scale_factor": (0.02, [0, 1, 2], [(0, 2)]),            # meas 0, 2 share _s0; meas 1 has _s1
+          "fittable_fluences": (0.02, [0, 2], None),              # _f0, _f2
+          "fittable_absps": (0.02, [1], None)}                    # _a1
+    base = np.array([GUESS[n] for n in NAMES] + [3.0, 0.4, 1.7, 0.6, 1.3], dtype=float)
+    other = base.copy()
+    other[idx["_s0"]], other[idx["_f2"]], other[idx["_a1"]] = 0.7, 2.5, 0.8
+    states = np.stack([base, other])
+    res = eval_trial_moves(states, np.ones(2), {"TRPL": 1.0}, sf, want_curves=True)
+    res2 = eval_trial_moves(states, np.ones(2), {"TRPL": 1.0}, sf, want_curves=True)
+    np.testing.assert_array_equal(res.per_meas, res2.per_meas)    # no compounding across calls
+    for k, st in enumerate(states):
+        for m in range(3):
+            ini = inis[m].copy()
+            if m in (0, 2):
+                ini[0] *= st[idx[f"_f{m}"]]
+            if m == 1:
+                ini[1] *= st[idx["_a1"]]
+            shift = np.log10(st[idx["_s0"]] if m in (0, 2) else st[idx["_s1"]])
+            g = orc.Grid(sim["lengths"][m], 64, t, 4)
+            ref = orc.simulate(ini, g, st, idx, units=units, ini_mode="fluence", RTOL=1e-10, ATOL=1e-16)
+            np.testing.assert_allclose(res.curves[k, 61 * m:61 * (m + 1)], ref, rtol=2e-6)
+            want = orc.curve_loglik(ref, t, t, vals[m], uncs[m], 1.0, scale_shift=shift)
+            assert abs(res.per_meas[k, m, 0] - want) <= 2e-6 * abs(want), (k, m, res.per_meas[k, m, 0], want)
+    sf_d = dict(sf, ini_mode="density", _init_params=[np.full(64, 1e16)] * 3)
+    with pytest.raises(ValueError, match="fluence"):
+        eval_trial_moves(states, np.ones(2), {"TRPL": 1.0}, sf_d)

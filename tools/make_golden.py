@@ -279,8 +279,49 @@ def gen_traps_irf(seed=11):
                         pl_tight=pl_tight, vals=np.array(vals), uncs=np.array(uncs), logll=logll)
 
 
+def gen_real3():
+    """configs[0] on the reference's real data: Inputs/real_staub_input.csv (three injection levels,
+    311 nm film) against Inputs/real_staub_aug_corr_renoised.csv, both read by the reference's own
+    bayes_io.get_data / get_initpoints with mcmc0.txt's flags (time cutoff 0..2000 ns, log10 of the
+    measurement and its uncertainty), parameter set list = the staub6 fixture's 17 states.  (The
+    six-curve measurement file mcmc0.txt names, staub_MAPI_threepower_twothick_withauger.csv, is
+    not part of the reference tree; this three-curve set is the real data it ships.)"""
+    import bayes_io as ref_io
+    g6 = np.load(os.path.join(OUT, "staub6.npz"))
+    states = g6["states"]
+    ic_flags = {"time_cutoff": [0, 2000], "select_obs_sets": None, "noise_level": None}
+    times, vals, uncs = ref_io.get_data(os.path.join(REF, "Inputs", "real_staub_aug_corr_renoised.csv"),
+                                        ic_flags, {"log_y": 1})
+    ini = ref_io.get_initpoints(os.path.join(REF, "Inputs", "real_staub_input.csv"), ic_flags)
+    lengths = [311.0, 311.0, 311.0]
+    nS = len(states)
+    temps = np.array([1.0, 2.0, 8.0])
+    sigma = 1.0
+    pl_def = [[None] * 3 for _ in range(nS)]
+    logll = np.zeros(nS)
+    logll_T = np.zeros((nS, 3))
+    for s in range(nS):
+        for m in range(3):
+            pl_def[s][m] = ref_solve(ini[m], lengths[m], times[m], states[s], None, None)
+        sf = make_shared_fields(ini, times, vals, uncs, lengths, [NX] * 3, ["TRPL"] * 3, None, None)
+        ll, funcs = ref_tme.eval_trial_move(states[s].copy(), {"model_uncertainty": {"TRPL": sigma}, "_T": 1.0},
+                                            sf, LOGGER)
+        logll[s] = ll
+        logll_T[s] = [sum(f(T) for f in funcs) for T in temps]
+        print("real3 state", s, ll, flush=True)
+    n_t = np.array([len(tt) for tt in times])
+
+    def pad(rows):
+        return np.array([np.pad(np.asarray(r, dtype=float), (0, n_t.max() - len(r)), constant_values=np.nan)
+                         for r in rows])
+    np.savez_compressed(os.path.join(OUT, "staub_real3.npz"), names=np.array(NAMES), units=UNITS, states=states,
+                        ini=ini, lengths=np.array(lengths), nx=NX, n_t=n_t, t=pad(times), vals=pad(vals),
+                        uncs=pad(uncs), sigma=sigma, temps=temps, logll=logll, logll_T=logll_T,
+                        pl_default=np.array([pad(pl_def[s]) for s in range(nS)]))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rhs", "irf", "known", "staub", "traps"]
+    which = sys.argv[1:] or ["rhs", "irf", "known", "staub", "traps", "real3"]
     if "rhs" in which:
         gen_rhs_pins()
     if "irf" in which:
@@ -291,3 +332,5 @@ if __name__ == "__main__":
         gen_staub()
     if "traps" in which:
         gen_traps_irf()
+    if "real3" in which:
+        gen_real3()
