@@ -9,7 +9,7 @@ Differences from the reference that a caller can observe (all deliberate, see DE
   * solver=("solveivp",) / ("odeint",) both select the device integrator (RODAS4); ("NN", ...) is
     not part of this path and raises NotImplementedError.
   * ``state`` is not modified (the reference scales it in place and scales it back).
-  * RTOL means the same thing and has the same default; ATOL above 1e-20 nm^-3 is clamped
+  * RTOL means the same thing and has the same default; ATOL above 1e-30 nm^-3 is clamped
     (``_capi.effective_tolerances``).  ``g.hmax`` is honoured only with ``honor_hmax=True``.
 """
 from __future__ import annotations
