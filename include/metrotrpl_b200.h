@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TRPL_ABI_VERSION 3
+#define TRPL_ABI_VERSION 4
 #define TRPL_NPARAM 16  /* doubles per parameter set, model units (nm, ns, V) */
 #define TRPL_NAUX 6     /* doubles per trajectory, see below */
 #define TRPL_NTEMP 3    /* likelihoods are returned for three temperatures per trajectory */
@@ -54,7 +54,10 @@ enum trpl_status {
   TRPL_ST_EXPLICIT = 128 /* informational: non-stiff trajectory, integrated by the explicit RK path */
 };
 enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2, TRPL_OPT_LADDER = 4,
-                      TRPL_OPT_NO_EXPLICIT = 8 /* always use the Rosenbrock integrator */ };
+                      TRPL_OPT_NO_EXPLICIT = 8, /* always use the Rosenbrock integrator */
+                      TRPL_OPT_CTA_PER_TRAJ = 16 /* one trajectory per CTA of 128 threads instead of one per
+                                                    warp: lowest latency per trajectory, for small batches
+                                                    (tempering); 'std' model, nx = 128 only */ };
 
 /* one measurement (sim_info["lengths"/"nx"/"meas_types"][i] + its slice of the data arrays) */
 typedef struct trpl_meas_desc {
@@ -111,6 +114,15 @@ int trpl_set_irf(trpl_handle* h, int32_t n_rows_total, const double* moments);
  * model_uncertainty^2 (temperature 1).  Results: trpl_download_ladder, [n_sets][n_meas][n_temps]. */
 int trpl_set_ladder(trpl_handle* h, int32_t n_temps, const double* temps);
 int trpl_download_ladder(trpl_handle* h, double* out);
+/* The swap move only needs the sum over measurements (metropolis.py:73-76): rows [n_sets][n_temps],
+ * NaN -> -inf.  trpl_download_ladder_sums copies them (and, if nsteps != NULL, the step counts
+ * [n_sets][n_meas][2]) to the host with one stream synchronisation.  trpl_ladder_sums_resident leaves
+ * them in HBM and returns the device pointer (valid until the next run on this handle; the stream is
+ * synchronised, so a collective on another stream may read it): the rows of several GPUs are then
+ * all-gathered device to device (NCCL) without touching the host. */
+int trpl_download_ladder_sums(trpl_handle* h, double* rows, int32_t* nsteps);
+int trpl_ladder_sums_resident(trpl_handle* h, const double** dev_rows, int32_t* n_sets, int32_t* n_temps);
+int trpl_download_nsteps(trpl_handle* h, int32_t* nsteps);
 
 /* Whole-batch likelihood: n_sets parameter sets x n_meas measurements.
  *   params  [n_sets][TRPL_NPARAM]

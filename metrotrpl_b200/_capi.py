@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NPARAM = 16
 NAUX = 6
 NTEMP = 3
@@ -29,7 +29,7 @@ INI_IDS = {"density": 0, "fluence": 1}
 
 ST_MAX_STEPS, ST_H_UNDERFLOW, ST_NONFINITE, ST_FLOORED, ST_NEG_FRAC, ST_NAN_LL, ST_CONV_FAIL = 1, 2, 4, 8, 16, 32, 64
 ST_EXPLICIT = 128
-OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD, OPT_LADDER, OPT_NO_EXPLICIT = 1, 2, 4, 8
+OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD, OPT_LADDER, OPT_NO_EXPLICIT, OPT_CTA_PER_TRAJ = 1, 2, 4, 8, 16
 
 # Defaults of the integrator.  RTOL keeps the reference's default value and meaning
 # (forward_solver.py:18).  The reference's default ATOL (1e-10 nm^-3, forward_solver.py:19) is larger
@@ -233,6 +233,9 @@ def load_library() -> C.CDLL:
     lib.trpl_set_irf.argtypes = [H, C.c_int32, dp]
     lib.trpl_set_ladder.argtypes = [H, C.c_int32, dp]
     lib.trpl_download_ladder.argtypes = [H, dp]
+    lib.trpl_download_ladder_sums.argtypes = [H, dp, ip]
+    lib.trpl_ladder_sums_resident.argtypes = [H, C.POINTER(C.c_void_p), ip, ip]
+    lib.trpl_download_nsteps.argtypes = [H, ip]
     lib.trpl_loglik_batch.argtypes = [H, C.c_int32, dp, dp, C.POINTER(SolverOpts), dp, ip, ip, dp]
     lib.trpl_solve_batch.argtypes = [H, C.c_int32, dp, dp, C.POINTER(SolverOpts), dp, ip, ip]
     lib.trpl_upload_batch.argtypes = [H, C.c_int32, dp, dp]
@@ -324,6 +327,26 @@ class Context:
         out = np.empty((n_sets, self.problem.n_meas, self._n_ladder))
         self._check(self.lib.trpl_download_ladder(self.h, _ptr(out, C.c_double)))
         return out
+
+    def download_ladder_sums(self, n_sets, want_nsteps=True):
+        """[n_sets, n_temps] per-chain likelihood at every ladder temperature (summed over the
+        measurements, NaN -> -inf) and the step counts, one synchronisation."""
+        rows = np.empty((n_sets, self._n_ladder))
+        nsteps = np.empty((n_sets, self.problem.n_meas, 2), dtype=np.int32) if want_nsteps else None
+        self._check(self.lib.trpl_download_ladder_sums(self.h, _ptr(rows, C.c_double), _ptr(nsteps, C.c_int32)))
+        return rows, nsteps
+
+    def ladder_sums_resident(self):
+        """(device pointer, n_sets, n_temps) of the same rows, left in HBM (stream synchronised)."""
+        ptr = C.c_void_p()
+        n, k = C.c_int32(), C.c_int32()
+        self._check(self.lib.trpl_ladder_sums_resident(self.h, C.byref(ptr), C.byref(n), C.byref(k)))
+        return ptr.value, n.value, k.value
+
+    def download_nsteps(self, n_sets):
+        nsteps = np.empty((n_sets, self.problem.n_meas, 2), dtype=np.int32)
+        self._check(self.lib.trpl_download_nsteps(self.h, _ptr(nsteps, C.c_int32)))
+        return nsteps
 
     # -- whole-batch calls (host buffers in, host buffers out) --
     def loglik_batch(self, params, aux, opts: SolverOpts, want_curves=False):

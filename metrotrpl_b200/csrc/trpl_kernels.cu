@@ -20,6 +20,7 @@
 #include "../../include/metrotrpl_b200.h"
 #include "trajectory.h"
 #include "explicit.h"
+#include "cta_trajectory.h"
 #include "proposals.h"
 
 namespace {
@@ -215,6 +216,44 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_explicit
   tmem_release<SL>(warp, mem.tm);
 }
 
+// One trajectory per CTA of 128 threads (cta_trajectory.h): the low-latency instantiation for small
+// batches.  Persistent CTAs claim trajectories from the same queue as the one-warp kernel.
+__global__ void __launch_bounds__(cta::NX, 2) trpl_cta_kernel(const KernelArgs a) {
+  __shared__ cta::Smem s;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s.traj = atomicAdd(a.counter, 1);
+    __syncthreads();
+    int traj = s.traj;
+    if (traj >= a.n_traj) break;
+    if (a.queue) {
+      traj = a.queue[traj];
+    } else {
+      const int n_sets_q = a.n_traj / a.n_meas;
+      const int qm = traj / n_sets_q;
+      traj = (traj - qm * n_sets_q) * a.n_meas + a.meas_order[qm];
+    }
+    TrajIn in;
+    setup_traj(a, traj, 0, in);
+    TrajOut out;
+    TrajMid mid;
+    cta::run_trajectory_cta(in, a.opt, s, out, mid);
+    if (threadIdx.x < 32) finish_traj(a, traj, 0, in, mid, out);
+  }
+}
+
+// Replica exchange needs each chain's likelihood at every ladder temperature summed over its
+// measurements (the reference sums ll_func[ss](T) over ss, metropolis.py:73-76): [n_sets][n_temps].
+// NaN (a failed curve) becomes -inf, as eval_trial_move's callers treat it.
+__global__ void ladder_sum_kernel(const double* lad, double* out, int n_sets, int n_meas, int n_temps) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_sets * n_temps) return;
+  const int set = k / n_temps, tt = k - set * n_temps;
+  double acc = 0.0;
+  for (int m = 0; m < n_meas; ++m) acc += lad[((size_t)set * n_meas + m) * n_temps + tt];
+  out[k] = (acc != acc) ? -HUGE_VAL : acc;
+}
+
 // FP64 peak probe: 8 independent FMA chains per thread, no memory traffic.
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed) {
   double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
@@ -262,7 +301,10 @@ struct trpl_handle {
   int model = 0, n_meas = 0, n_times_total = 0, max_nx = 0;
   bool have_vals = false, have_profiles = false, all_full = false;
   DevBuf<MeasDesc> d_meas;
-  DevBuf<double> d_times, d_vals, d_uncs, d_profiles, d_irf, d_scratch, d_ladder_T, d_ladder_out, d_hist;
+  DevBuf<double> d_times, d_vals, d_uncs, d_profiles, d_irf, d_scratch, d_ladder_T, d_ladder_out, d_ladder_sum, d_hist;
+  double* h_ladder_sum = nullptr;      // pinned staging of the per-chain ladder rows
+  int* h_nsteps = nullptr;
+  size_t h_ladder_cap = 0, h_nsteps_cap = 0;
   int n_ladder = 0;
   bool ladder_valid = false;
   bool any_irf = false, have_irf = false;
@@ -345,6 +387,34 @@ int launch(trpl_handle* h, KernelArgs a) {
   return 0;
 }
 
+// CTA-per-trajectory launch (TRPL_OPT_CTA_PER_TRAJ): 'std' model, every measurement on 128 nodes
+int launch_cta(trpl_handle* h, KernelArgs a) {
+  if (h->model != TRPL_MODEL_STD || !h->all_full || h->max_nx != cta::NX)
+    return fail("TRPL_OPT_CTA_PER_TRAJ: this instantiation exists for the 'std' model with nx = 128 on every measurement");
+  a.warps_per_cta = 1;        // one step log / scratch slice per CTA (warp 0 runs the emission)
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trpl_cta_kernel, cta::NX, 0));
+  if (per_sm < 1) return fail("CTA-per-trajectory kernel does not fit on an SM");
+  int grid = std::min(h->prop.multiProcessorCount * per_sm, a.n_traj);
+  if (grid < 1) grid = 1;
+  if (getenv("TRPL_DEBUG"))
+    fprintf(stderr, "[trpl] launch CTA-per-trajectory: %d CTAs/SM, grid %d, %zu B smem/CTA\n", per_sm, grid, sizeof(cta::Smem));
+  if (a.scratch) {
+    CU(h->d_scratch.reserve((size_t)grid * a.scratch_stride));
+    a.scratch = h->d_scratch.p;
+  }
+  CU(h->d_hist.reserve((size_t)grid * 3 * HIST_CAP));
+  a.hist = h->d_hist.p;
+  CU(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(int), h->stream));
+  a.defer_list = nullptr; a.defer_count = h->d_counter.p + 2;
+  CU(cudaEventRecord(h->ev0, h->stream));
+  trpl_cta_kernel<<<grid, cta::NX, 0, h->stream>>>(a);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaEventRecord(h->ev1, h->stream));
+  return 0;
+}
+
 template <int MODEL>
 int launch_npl(trpl_handle* h, const KernelArgs& a) {
   const int nx = h->max_nx;
@@ -401,6 +471,8 @@ void trpl_destroy(trpl_handle* h) {
   cudaEventDestroy(h->tm0);
   cudaEventDestroy(h->tm1);
   cudaStreamDestroy(h->stream);
+  if (h->h_ladder_sum) cudaFreeHost(h->h_ladder_sum);
+  if (h->h_nsteps) cudaFreeHost(h->h_nsteps);
   delete h;
 }
 
@@ -522,8 +594,9 @@ int trpl_set_queue_order(trpl_handle* h, int32_t n_traj, const int32_t* order) {
   }
   CU(cudaSetDevice(h->device));
   CU(h->d_queue.reserve(n_traj));
+  // pageable source: the runtime stages it before returning, and the copy is ordered before the
+  // next launch on the same stream - no host synchronisation needed
   CU(cudaMemcpyAsync(h->d_queue.p, order, sizeof(int) * n_traj, cudaMemcpyHostToDevice, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
   h->queue_n = n_traj;
   return 0;
 }
@@ -544,6 +617,59 @@ int trpl_download_ladder(trpl_handle* h, double* out) {
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(out, h->d_ladder_out.p, sizeof(double) * (size_t)h->n_sets * h->n_meas * h->n_ladder,
                      cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int ladder_sums_launch(trpl_handle* h) {
+  if (!h->ladder_valid) return fail("the last run did not produce ladder likelihoods");
+  CU(cudaSetDevice(h->device));
+  const int n = h->n_sets * h->n_ladder;
+  CU(h->d_ladder_sum.reserve(n));
+  ladder_sum_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_ladder_out.p, h->d_ladder_sum.p, h->n_sets,
+                                                             h->n_meas, h->n_ladder);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+int trpl_ladder_sums_resident(trpl_handle* h, const double** dev_rows, int32_t* n_sets, int32_t* n_temps) {
+  if (!h || !dev_rows) return fail("null argument");
+  if (int r = ladder_sums_launch(h)) return r;
+  CU(cudaStreamSynchronize(h->stream));
+  *dev_rows = h->d_ladder_sum.p;
+  if (n_sets) *n_sets = h->n_sets;
+  if (n_temps) *n_temps = h->n_ladder;
+  return 0;
+}
+
+int trpl_download_ladder_sums(trpl_handle* h, double* rows, int32_t* nsteps) {
+  if (!h || !rows) return fail("null argument");
+  if (int r = ladder_sums_launch(h)) return r;
+  const size_t n = (size_t)h->n_sets * h->n_ladder, n_traj = (size_t)h->n_sets * h->n_meas;
+  // pinned staging: the copies are truly asynchronous and one synchronisation serves both
+  if (n > h->h_ladder_cap) {
+    if (h->h_ladder_sum) cudaFreeHost(h->h_ladder_sum);
+    CU(cudaMallocHost(&h->h_ladder_sum, n * sizeof(double)));
+    h->h_ladder_cap = n;
+  }
+  if (nsteps && 2 * n_traj > h->h_nsteps_cap) {
+    if (h->h_nsteps) cudaFreeHost(h->h_nsteps);
+    CU(cudaMallocHost(&h->h_nsteps, 2 * n_traj * sizeof(int)));
+    h->h_nsteps_cap = 2 * n_traj;
+  }
+  CU(cudaMemcpyAsync(h->h_ladder_sum, h->d_ladder_sum.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (nsteps) CU(cudaMemcpyAsync(h->h_nsteps, h->d_nsteps.p, 2 * n_traj * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  memcpy(rows, h->h_ladder_sum, n * sizeof(double));
+  if (nsteps) memcpy(nsteps, h->h_nsteps, 2 * n_traj * sizeof(int));
+  return 0;
+}
+
+int trpl_download_nsteps(trpl_handle* h, int32_t* nsteps) {
+  if (!h || !nsteps) return fail("null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(nsteps, h->d_nsteps.p, sizeof(int) * 2 * (size_t)h->n_sets * h->n_meas, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -616,6 +742,7 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
   a.queue = (h->queue_n > 0 && h->queue_n == h->n_sets * h->n_meas) ? h->d_queue.p : nullptr;
   a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;
   memcpy(&a.opt, opts, sizeof(SolverOpts));
+  if (opts->flags & TRPL_OPT_CTA_PER_TRAJ) return launch_cta(h, a);
   if (h->model == TRPL_MODEL_STD) return launch_npl<MODEL_STD>(h, a);
 #ifdef TRPL_DEV_HEADLINE_ONLY
   return fail("this developer build only holds the 'std' model");

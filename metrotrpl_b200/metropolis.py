@@ -45,48 +45,83 @@ def roll_acceptance(rng, logratio):
     return rng.random() < np.exp(logratio)
 
 
+# A tempering iteration is as slow as its slowest trajectory.  The CTA-per-trajectory kernel
+# (csrc/cta_trajectory.h) was built for that case, but measured on B200 it has the SAME latency per
+# integrator step as the one-warp kernel (6.5 us: a step is a chain of ~50 dependent
+# exchange-and-reduce levels either way, tools/latency_probe.py) at 0.3x the
+# throughput, so "auto" never picks it.  The choice is made from the GLOBAL number of trajectories
+# per iteration, never from this rank's share, so that a run gives the same chains on any number of
+# GPUs.
+CTA_KERNEL_MAX_TRAJ = 0
+
+
 class CudaEvaluator:
     """Likelihood of a batch of states at every ladder temperature, on this rank's GPU."""
 
-    def __init__(self, shared_fields, device=None):
+    def __init__(self, shared_fields, device=None, kernel="auto"):
         from .trial_move_evaluation import PathCache
         self.cache = PathCache(shared_fields, device=device)
-        self.ladder = np.asarray(shared_fields["_T"], dtype=np.float64)
-        self.cache.ctx.set_ladder(self.ladder)
+        self.ladder = np.ascontiguousarray(shared_fields["_T"], dtype=np.float64)
         self.flags = self.cache.flags | _capi.OPT_LADDER
+        sim = shared_fields["_sim_info"]
+        eligible = shared_fields.get("model", "std") == "std" and all(int(nx) == 128 for nx in sim["nx"])
+        n_global = int(shared_fields.get("_n_chains", 1)) * self.cache.n_meas
+        if kernel == "cta" or (kernel == "auto" and eligible and n_global <= CTA_KERNEL_MAX_TRAJ):
+            self.flags |= _capi.OPT_CTA_PER_TRAJ
+        self.kernel = "cta" if self.flags & _capi.OPT_CTA_PER_TRAJ else "warp"
         self._cost = None       # integrator steps of the previous call's trajectories
+        self.n_failed = 0       # trajectories of the last call with an integrator failure flag
 
-    def __call__(self, states, sigmas):
-        """states [n, n_params], sigmas: list of {meas_type: sigma}.  Returns [n, n_T]."""
+    def launch(self, states, sigmas):
+        """Upload and launch; nothing is waited for.  Returns the number of parameter sets."""
         n = states.shape[0]
         params, aux = self.cache.pack(states, sigmas, np.ones((n, 3)))   # slot 1 = sigma^2 (T = 1)
         sf = self.cache.sf
         opts = _capi.make_opts(sf.get("rtol", None), sf.get("atol", None), flags=self.flags)
         ctx = self.cache.ctx
         ctx.set_problem_if_needed(self.cache.prob)
+        # the ladder lives on the (process-wide) context: another evaluator may have replaced it
+        if getattr(ctx, "_ladder_key", None) != self.ladder.tobytes():
+            ctx.set_ladder(self.ladder)
+            ctx._ladder_key = self.ladder.tobytes()
         # Longest first: a chain's proposal costs about what its previous proposal cost, and an
-        # iteration is only as fast as its last trajectory (a few hundred trajectories are one or
-        # two waves of the GPU).  The order never changes a result.
+        # iteration is only as fast as its last trajectory.  The order never changes a result.
         if self._cost is not None and self._cost.size == n * self.cache.n_meas:
             ctx.set_queue_order(np.argsort(-self._cost, kind="stable"))
         else:
             ctx.set_queue_order(None)
-        _, _, nsteps, _ = ctx.loglik_batch(params, aux, opts, want_curves=False)
+        ctx.upload(params, aux)
+        ctx.run_resident(opts)
+        return n
+
+    def __call__(self, states, sigmas):
+        """states [n, n_params], sigmas: list of {meas_type: sigma}.  Returns [n, n_T] on the host
+        (one stream synchronisation)."""
+        n = self.launch(states, sigmas)
+        rows, nsteps = self.cache.ctx.download_ladder_sums(n)
         self._cost = nsteps.sum(axis=-1).ravel()
-        lad = ctx.download_ladder(n)
-        tot = lad.sum(axis=1)
-        return np.where(np.isnan(tot), -np.inf, tot)
+        return rows
+
+    def device_rows(self, states, sigmas):
+        """Same rows left in HBM: (device pointer, n, n_T).  The step counts (next call's queue
+        order) are fetched too."""
+        n = self.launch(states, sigmas)
+        ptr, n_sets, n_t = self.cache.ctx.ladder_sums_resident()
+        self._cost = self.cache.ctx.download_nsteps(n).sum(axis=-1).ravel()
+        return ptr, n_sets, n_t
 
 
 def sharded_eval(evaluator, comm, states, sigmas):
     """Evaluate all chains' states, each rank its own block; every rank gets all rows."""
     n = states.shape[0]
     lo, hi = comm.shard(n)
-    local = evaluator(states[lo:hi], sigmas[lo:hi]) if hi > lo else np.zeros((0, 0))
     if comm.world == 1:
-        return local
-    if hi == lo:
-        raise ValueError("more ranks than chains")
+        return evaluator(states, sigmas)
+    if comm.backend == "nccl" and hasattr(evaluator, "device_rows"):
+        # rows stay in HBM and cross NVLink device to device; one D2H of the gathered table
+        ptr, n_local, n_t = evaluator.device_rows(states[lo:hi], sigmas[lo:hi])
+        return comm.allgather_device_rows(ptr, n_local, n_t, n)
+    local = evaluator(states[lo:hi], sigmas[lo:hi])
     return comm.allgather_rows(local, n)
 
 
@@ -166,7 +201,8 @@ def metro(sim_info, iniPar, e_data, MCMC_fields, param_info, verbose=False, expo
     """Same call as the reference's metro() (metropolis.py:283-473).
 
     Extra keyword arguments: evaluator_factory (tests), comm (a parallel.Comm), irf_dir,
-    install_signal_handlers (default True, as the reference).
+    install_signal_handlers (default True, as the reference), kernel ("auto" | "warp" | "cta":
+    which instantiation of the integrator evaluates the proposals, see CudaEvaluator).
     """
     clock0 = perf_counter()
     comm = kwargs.get("comm", None) or Comm()
@@ -209,8 +245,12 @@ def metro(sim_info, iniPar, e_data, MCMC_fields, param_info, verbose=False, expo
     RNG.bit_generator.state = MS_list.random_state
     states, logll, accept = MS_list.H.states, MS_list.H.loglikelihood, MS_list.H.accept
 
+    if comm.world > shared_fields["_n_chains"]:
+        # every rank must own at least one chain; checked here, before any collective, on all ranks
+        raise ValueError(f"more ranks ({comm.world}) than chains ({shared_fields['_n_chains']})")
     factory = kwargs.get("evaluator_factory", None)
-    evaluator = factory(shared_fields) if factory is not None else CudaEvaluator(shared_fields, device=comm.local_rank)
+    evaluator = factory(shared_fields) if factory is not None else CudaEvaluator(
+        shared_fields, device=comm.local_rank, kernel=kwargs.get("kernel", "auto"))
 
     need_initial_state = load_checkpoint is None
     cur_ladder = None

@@ -62,6 +62,30 @@ class Comm:
         parts = [recv[r][:counts[r][1] - counts[r][0]].cpu().numpy() for r in range(self.world)]
         return np.concatenate(parts, axis=0)
 
+    def allgather_device_rows(self, dev_ptr, n_local, width, n_total):
+        """All-gather rows that already sit in this rank's HBM (a raw device pointer from the CUDA
+        library): device-to-device over NVLink, then ONE copy of the gathered table to pinned host
+        memory.  Returns [n_total, width] float64 on the host."""
+        torch = self.torch
+        dev = self._dev()
+        counts = [shard_range(n_total, r, self.world) for r in range(self.world)]
+        most = max(hi - lo for lo, hi in counts)
+        key = (most, width)
+        if getattr(self, "_gather_key", None) != key:
+            self._send = torch.zeros((most, width), dtype=torch.float64, device=dev)
+            self._recv = torch.empty((self.world * most, width), dtype=torch.float64, device=dev)
+            self._host = torch.empty((self.world * most, width), dtype=torch.float64).pin_memory()
+            self._gather_key = key
+        view = torch.as_tensor(_DeviceRows(dev_ptr, (n_local, width)), device=dev)
+        self._send[:n_local].copy_(view)
+        self.dist.all_gather_into_tensor(self._recv, self._send)
+        self._host.copy_(self._recv, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        out = self._host.numpy().reshape(self.world, most, width)
+        if all(hi - lo == most for lo, hi in counts):
+            return out.reshape(n_total, width).copy()
+        return np.concatenate([out[r, :counts[r][1] - counts[r][0]] for r in range(self.world)], axis=0)
+
     def broadcast_array(self, x, src=0):
         """Rank `src`'s float64 array on every rank (same shape everywhere)."""
         if self.dist is None:
@@ -83,6 +107,14 @@ class Comm:
                 self.dist.barrier(device_ids=[self.local_rank])
             else:
                 self.dist.barrier()
+
+
+class _DeviceRows:
+    """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), True),
+                                         "version": 2}
 
 
 def shard_range(n, rank, world):

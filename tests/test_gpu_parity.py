@@ -29,6 +29,15 @@ def make_backend(ctx):
     return backend
 
 
+def make_backend_cta(ctx):
+    """The CTA-per-trajectory instantiation (csrc/cta_trajectory.h) behind the same C ABI call."""
+    def backend(prob, params, aux, opts, want_curves):
+        ctx.set_problem(prob)
+        o = _capi.SolverOpts(opts.rtol, opts.atol, opts.hmax, opts.max_steps, opts.flags | _capi.OPT_CTA_PER_TRAJ)
+        return ctx.loglik_batch(params, aux, o, want_curves=want_curves)
+    return backend
+
+
 def test_device_is_blackwell(ctx):
     info = ctx.device_info()
     print(info)
@@ -210,3 +219,60 @@ def test_queue_order_never_changes_a_result(ctx):
     got = ctx.loglik_batch(params, aux, opts, want_curves=True)
     np.testing.assert_array_equal(base[0], got[0])
     ctx.set_queue_order(None)
+
+
+def test_cta_per_trajectory_kernel_staub_and_real_data(ctx):
+    """The low-latency instantiation against the same converged truth as the one-warp kernel."""
+    print(pc.check_staub(make_backend_cta(ctx), rtol=1e-7, tight_rtol=1e-10))
+    print(pc.check_real3(make_backend_cta(ctx), rtol=1e-7, tight_rtol=1e-10))
+
+
+def test_cta_per_trajectory_kernel_known_answers(ctx):
+    print(pc.check_known_answers(make_backend_cta(ctx)))
+
+
+def test_cta_per_trajectory_kernel_agrees_with_one_warp_kernel(ctx):
+    """Two instantiations of one method (different elimination order, different reductions): the
+    curves agree to integration accuracy, the log-likelihoods to 1e-6, at every temperature, with
+    the tempering ladder, and the results do not depend on the queue order."""
+    g, prob, params, aux = pc.staub_problem()
+    opts = _capi.make_opts(RTOL=1e-7)
+    ll_w, st_w, ns_w, cur_w = make_backend(ctx)(prob, params, aux, opts, True)
+    ll_c, st_c, ns_c, cur_c = make_backend_cta(ctx)(prob, params, aux, opts, True)
+    T = cur_w.reshape(17, 6, -1)
+    C = cur_c.reshape(17, 6, -1)
+    in_range = T >= 1e-14 * T[:, :, :1]
+    assert np.abs(np.where(in_range, C / T - 1, 0)).max() <= 1e-5
+    ok = ll_w[:, :, 0].sum(axis=1) > pc.LOGLL_FLOOR
+    np.testing.assert_allclose(ll_c[ok], ll_w[ok], rtol=1e-6)
+    assert abs(ns_c[..., 0].mean() / ns_w[..., 0].mean() - 1) < 0.05
+    # ladder likelihoods through the CTA kernel (aux slot 1 = sigma^2, i.e. T = 1) equal the three
+    # temperature slots of the plain call (the fixture's temps are 1, 2, 8)
+    ladder = np.array([1.0, 2.0, 8.0, 64.0])
+    ctx.set_ladder(ladder)
+    o = _capi.make_opts(RTOL=1e-7, flags=_capi.OPT_LADDER | _capi.OPT_CTA_PER_TRAJ)
+    aux1 = _capi.default_aux(params.shape[0], 6, [float(g["sigma"])] * 6, temps=(1.0, 1.0, 1.0))
+    ctx.loglik_batch(params, aux1, o, want_curves=False)
+    lad = ctx.download_ladder(params.shape[0])
+    np.testing.assert_allclose(lad[ok][:, :, :3], ll_c[ok], rtol=1e-12)
+    rows, _ = ctx.download_ladder_sums(params.shape[0])
+    np.testing.assert_allclose(rows[ok], lad[ok].sum(axis=1), rtol=1e-14)
+    # any queue order, bit-identical results
+    n_traj = params.shape[0] * 6
+    ctx.set_queue_order(np.random.default_rng(0).permutation(n_traj))
+    ll_p, _, _, cur_p = make_backend_cta(ctx)(prob, params, aux, opts, True)
+    ctx.set_queue_order(None)
+    np.testing.assert_array_equal(ll_p, ll_c)
+    np.testing.assert_array_equal(cur_p, cur_c)
+
+
+def test_cta_per_trajectory_kernel_refuses_what_it_does_not_hold(ctx):
+    names, units, idx = pc._known_units()
+    sim = {"lengths": [500.0], "nx": [64], "meas_types": ["TRPL"], "num_meas": 1}
+    t = np.linspace(0, 10, 11)
+    prob = _capi.pack_problem(sim, [1e16 * np.ones(64)], [t], None, None)
+    st = np.array([[pc.BASE[n] for n in names]], dtype=float)
+    ctx.set_problem(prob)
+    with pytest.raises(_capi.TrplError, match="nx = 128"):
+        ctx.loglik_batch(_capi.pack_params(st, idx, units), _capi.default_aux(1, 1, [1.0]),
+                         _capi.make_opts(flags=_capi.OPT_NO_LIKELIHOOD | _capi.OPT_CTA_PER_TRAJ), want_curves=True)

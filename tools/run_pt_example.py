@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=31)
     ap.add_argument("--chains", type=int, default=256)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "warp", "cta"])
     args = ap.parse_args()
     comm = Comm()
     ini, t = bench.workload_inputs()
@@ -49,7 +50,7 @@ def main():
     comm.barrier()
     t0 = time.perf_counter()
     ms = metro(sim_info, ini, ([t] * 6, vals, uncs), MCMC, param_info, export_path="pt.pik", comm=comm,
-               install_signal_handlers=False)
+               install_signal_handlers=False, kernel=args.kernel)
     comm.barrier()
     dt = time.perf_counter() - t0
     if comm.rank == 0:
@@ -58,7 +59,8 @@ def main():
                           "n_gpus": comm.world, "seconds": dt, "iters_per_s": args.iters / dt,
                           "sims_per_s": sims / dt, "accept_rate": float(ms.H.accept[:, 1:].mean()),
                           "swap_accept": int(ms.H.swap_accept.sum()), "swap_attempts": int(ms.H.swap_attempts.sum()),
-                          "checksum_logll": float(ms.H.loglikelihood[:, -1].sum())}))
+                          "checksum_logll": float(ms.H.loglikelihood[:, -1].sum()),
+                          "checksum_states": float(np.log10(ms.H.states[:, :, -1]).sum()), "kernel": args.kernel}))
 
 
 if __name__ == "__main__":
