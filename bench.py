@@ -119,6 +119,17 @@ class ClockSampler:
 # CPU baseline: the oracle port of the reference path (numba RHS + SciPy LSODA + likelihood)
 # ---------------------------------------------------------------------------------------------
 _W = {}
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def ref_available():
+    """oracle/_ref holds the unmodified reference modules (oracle/make_ref.py, build container)."""
+    return all(os.path.exists(os.path.join(REF_DIR, f)) for f in
+               ("trial_move_evaluation.py", "forward_solver.py", "utils.py", "laplace.py", "sim_utils.py"))
+
+
+def cpu_kind():
+    return "reference" if ref_available() else "port"
 
 
 def _cpu_init(ini, t, vals, uncs):
@@ -130,31 +141,50 @@ def _cpu_init(ini, t, vals, uncs):
         _W["tp"] = threadpool_limits(1)
     except Exception:
         pass
-    from oracle import trpl_oracle as orc
-    _W.update(orc=orc, ini=ini, t=t, vals=vals, uncs=uncs)
-    sim = {"num_meas": 1, "lengths": [311.0], "nx": [16], "meas_types": ["TRPL"]}
+    _W.update(ini=ini, t=t, vals=vals, uncs=uncs)
     tt = np.linspace(0, 1, 3)
-    orc.state_loglik(GUESS, sim, [1e15 * np.ones(16)], [tt], [np.ones(3)], [np.ones(3)], IDX, UNITS,
-                     {"TRPL": 1.0})   # numba JIT warm-up, untimed
+    sim = {"num_meas": 1, "lengths": [311.0], "nx": [16], "meas_types": ["TRPL"]}
+    if ref_available():
+        # the reference's own eval_trial_move, unmodified (numba RHS + SciPy LSODA + likelihood)
+        import logging
+        sys.path.insert(0, REF_DIR)
+        import trial_move_evaluation as ref_tme
+        _W.update(ref=ref_tme, logger=logging.getLogger("reference"))
+        sf = make_shared_fields([1e15 * np.ones(16)], tt, [np.ones(3)], [np.ones(3)])
+        sf["_sim_info"] = sim
+        sf["_times"], sf["_vals"], sf["_uncs"] = [tt], [np.ones(3)], [np.ones(3)]
+        ref_tme.eval_trial_move(GUESS.copy(), {"model_uncertainty": {"TRPL": 1.0}, "_T": 1}, sf, _W["logger"])
+    else:
+        from oracle import trpl_oracle as orc
+        _W.update(orc=orc)
+        orc.state_loglik(GUESS, sim, [1e15 * np.ones(16)], [tt], [np.ones(3)], [np.ones(3)], IDX, UNITS,
+                         {"TRPL": 1.0})   # numba JIT warm-up, untimed
 
 
 def _cpu_one(state):
+    t = _W["t"]
+    if "ref" in _W:
+        sf = make_shared_fields(np.array(_W["ini"], dtype=float), t, _W["vals"], _W["uncs"])
+        sf["rtol"], sf["atol"] = None, None          # the reference's defaults: 1e-7 / 1e-10, hmax = 4
+        ll, _ = _W["ref"].eval_trial_move(np.array(state, dtype=float), {"model_uncertainty": {"TRPL": SIGMA}, "_T": 1},
+                                          sf, _W["logger"])
+        return ll
     orc = _W["orc"]
     sim = {"num_meas": 6, "lengths": LENGTHS, "nx": [NX] * 6, "meas_types": ["TRPL"] * 6}
-    t = _W["t"]
     ll, _ = orc.state_loglik(state, sim, _W["ini"], [t] * 6, _W["vals"], _W["uncs"], IDX, UNITS,
                              {"TRPL": SIGMA}, rtol=None, atol=None)
     return ll
 
 
 def cpu_throughput(states, ini, t, vals, uncs, cores, pool=None):
-    """sims/s of the CPU path over `states` (6 curves each) with `cores` worker processes."""
+    """sims/s of the CPU path over `states` (6 curves each) with `cores` worker processes (a work
+    queue of single parameter sets: no core waits for another until the queue is empty)."""
     own = pool is None
     if own:
         pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init, initargs=(ini, t, vals, uncs))
         pool.map(_noop, range(cores * 2))
     t0 = time.perf_counter()
-    pool.map(_cpu_one, list(states), chunksize=1)
+    list(pool.imap_unordered(_cpu_one, list(states), chunksize=1))
     dt = time.perf_counter() - t0
     if own:
         pool.close()
@@ -300,6 +330,9 @@ def run_ours(args):
             "hbm_algorithmic_bytes_per_launch": alg_bytes,
             "hbm_gbs_if_all_traffic_were_dram": alg_bytes / (k_ms * 1e-3) / 1e9}
 
+    # ---- the other BASELINE configs at this N (reported under "extra"; the headline is untouched) --
+    extra = None if args.no_extras else run_extras(args, rank, world, local, dist, ini, t, vals, uncs, peak_tf)
+
     if rank != 0:
         if dist is not None:
             dist.barrier(device_ids=[local])
@@ -323,7 +356,8 @@ def run_ours(args):
         "config": {"workload": "configs[1]: 4096 random parameter sets x 6 TRPL curves "
                                "(staub_MAPI threepower_twothick), nx=128, std model, per GPU",
                    "sets_per_gpu": args.sets, "curves_per_set": 6, "times_per_curve": int(len(t)),
-                   "rtol": args.rtol, "hmax": "error-controlled (reference hmax not imposed)",
+                   "rtol": args.rtol, "hmax": "not imposed: steps are error-controlled (the reference arm runs "
+                                              "LSODA with its own max_step = 4 ns)",
                    "l2": "flushed between steps (256 MiB memset); inputs are 0.5 MB and L2-resident by design",
                    "parallelism": f"independent parameter-set shards x{world}, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
@@ -331,10 +365,11 @@ def run_ours(args):
         "gpu_launches": int(gpu_launches),
         "clocks": clocks,
         "roofline": roof,
-        "cpu_baseline": {"value": cpu_val, "unit": "sims/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_cpu_sets} of the same parameter sets x 6 curves "
-                                   f"({cpu_dt:.1f} s wall), oracle port of numba RHS + SciPy LSODA + likelihood"},
+        "cpu_baseline": {"value": cpu_val, "unit": "sims/s", "cores": cores, "kind": cpu_kind(),
+                         "sample": f"{n_cpu_sets} of the same parameter sets x 6 curves ({cpu_dt:.1f} s wall), "
+                                   + CPU_DESCRIPTION[cpu_kind()] + ", rtol 1e-7 / atol 1e-10 / hmax 4 ns"},
         "device": info,
+        "extra": extra,
         "stats": {"mean_steps_per_sim": float(nsteps[..., 0].mean()), "max_steps": int(nsteps[..., 0].max()),
                   "mean_rejected": float(nsteps[..., 1].mean()),
                   "frac_floored": float(np.mean((status & 8) != 0)),
@@ -347,9 +382,138 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+CPU_DESCRIPTION = {
+    "reference": "the reference's own eval_trial_move (oracle/_ref: unmodified numba RHS + SciPy LSODA + likelihood)",
+    "port": "oracle port of the reference's numba RHS + SciPy LSODA + likelihood (oracle/_ref absent)"}
+
+
+# Algorithmic flops per node and integrator step of the configs[3] instantiation (traps model, 8
+# nodes per lane), counted like FLOPS_PER_NODE_STEP: 6 right-hand sides x 40 +
+# Jacobian and trap condensation 54 + factorisation 155 + 6 solves x 53.3 + stage combinations and
+# error norm on three components 171 + readout 9.  The IRF convolution is not counted.
+FLOPS_PER_NODE_STEP_TRAPS_NX256 = 6 * 40 + 54 + 155 + 6 * 53.3 + 171 + 9   # = 949
+
+
+def run_extras(args, rank, world, local, dist, ini, t, vals, uncs, peak_tf):
+    """configs[2] (parallel tempering, 256 replicas sharded over the ranks), configs[3] (traps + IRF,
+    nx = 256, per GPU) and configs[4] (dense grid, sharded) at this N.  Every rank takes part."""
+    import tempfile
+    from metrotrpl_b200 import _capi
+    from metrotrpl_b200 import dense_sampling as ds
+    from metrotrpl_b200.metropolis import metro
+    from metrotrpl_b200.parallel import Comm
+    os.environ["TRPL_USE_LOCAL_RANK"] = "1"
+    comm = Comm()
+    out = {}
+    # ---- configs[3]: traps model + IRF convolution, nx = 256 (weak: every rank its own batch) ----
+    g = np.load(os.path.join(ROOT, "tests", "golden", "traps_irf.npz"))
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    tt = g["t"]
+    nx = int(g["nx"])
+    tables = {520: (g["moments"], g["t_irf"])}
+    sim = {"lengths": list(g["lengths"]), "nx": [nx] * 2, "meas_types": ["TRPL"] * 2, "num_meas": 2}
+    prob = _capi.pack_problem(sim, g["inis"], [tt] * 2, list(g["vals"]), list(g["uncs"]), model="traps",
+                              ini_mode="fluence", irf_convolution=[520, 520], irf_tables=tables)
+    n_sets = 4096
+    rng = np.random.default_rng(1 + rank)
+    base = g["states"][rng.integers(0, len(g["states"]), n_sets)]
+    jit = np.ones_like(base)
+    act = [idx[n] for n in names if n not in ("n0", "eps", "Tm", "m")]
+    jit[:, act] = 10 ** rng.uniform(-0.1, 0.1, size=(n_sets, len(act)))
+    params = _capi.pack_params(base * jit, idx, g["units"], model="traps")
+    aux = _capi.default_aux(n_sets, 2, [1.0] * 2)
+    c3 = _capi.Context(local)
+    try:
+        c3.set_problem(prob)
+        opts = _capi.make_opts(RTOL=1e-7)
+        c3.upload(params, aux)
+        c3.run_resident(opts)
+        c3.synchronize()
+        barrier(dist, local)
+        ms = []
+        c3.timer_begin()
+        for _ in range(3):
+            c3.flush_l2()
+            c3.run_resident(opts)
+            ms.append(c3.last_kernel_ms())
+        tot = c3.timer_end() / 3
+        ll3, st3, ns3, _ = c3.download()
+    finally:
+        c3.close()
+    step_ms = allreduce_max(dist, local, tot)
+    k_ms = float(np.mean(ms))
+    flops = float(ns3.sum()) * nx * FLOPS_PER_NODE_STEP_TRAPS_NX256
+    out["traps_nx256_sims_per_s"] = world * 2 * n_sets / (step_ms * 1e-3)
+    out["traps_nx256"] = {
+        "workload": "configs[3]: traps model + IRF convolution (irf_520nm), nx=256, 4096 parameter sets x 2 curves "
+                    "x 401 times per GPU, states jittered +-0.1 decade around the golden fixture's",
+        "ms_per_step": step_ms, "mean_steps_per_sim": float(ns3[..., 0].mean()),
+        "frac_failed": float(np.mean((st3 & 7) != 0)),
+        "roofline": {"bound": "fp64", "achieved": flops / (k_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": flops / (k_ms * 1e-3) / 1e12 / peak_tf, "kernel": "trpl_forward_kernel<8,traps>",
+                     "kernel_ms": k_ms, "flops_per_node_step": FLOPS_PER_NODE_STEP_TRAPS_NX256,
+                     "integrator_steps_per_launch": float(ns3.sum()), "traffic": None}}
+    # ---- configs[2]: parallel tempering, 256 replicas x 6 curves, swaps every 10 iterations -------
+    chains = 256
+    param_info = {"names": list(NAMES), "active": {n: int(n not in ("n0", "eps", "Tm", "m")) for n in NAMES},
+                  "unit_conversions": dict(zip(NAMES, UNITS)), "do_log": {n: 1 for n in NAMES},
+                  "prior_dist": {n: (lo, hi) if lo != hi else (0, np.inf) for n, lo, hi in zip(NAMES, LO, HI)},
+                  "init_guess": dict(zip(NAMES, GUESS)), "trial_move": {n: 0.02 for n in NAMES}}
+    sim_info = {"num_meas": 6, "lengths": LENGTHS, "nx": [NX] * 6, "meas_types": ["TRPL"] * 6}
+
+    def pt_run(iters):
+        import copy
+        tmp = tempfile.mkdtemp()
+        mc = {"init_cond_path": "synthetic", "measurement_path": "synthetic", "output_path": tmp,
+              "num_iters": iters, "solver": ("solveivp",), "model": "std", "ini_mode": "density", "log_y": 1,
+              "checkpoint_freq": iters, "hard_bounds": 1, "rtol": 1e-7, "atol": None,
+              "model_uncertainty": {"TRPL": 0.2}, "parallel_tempering": list(np.logspace(0, 3, chains)),
+              "temper_freq": 10}
+        comm.barrier()
+        t0 = time.perf_counter()
+        res = metro(sim_info, ini, ([t] * 6, vals, uncs), mc, copy.deepcopy(param_info), export_path="pt.pik",
+                    comm=comm, install_signal_handlers=False)
+        comm.barrier()
+        return time.perf_counter() - t0, res
+    short = 11
+    pt_run(short)                                                     # warm-up (imports, buffers)
+    t_short, _ = pt_run(short)
+    t_long, res = pt_run(args.pt_iters)
+    rate = (args.pt_iters - short) / max(t_long - t_short, 1e-9)
+    rate = 1.0 / allreduce_max(dist, local, 1.0 / rate)
+    out["pt_iters_per_s"] = rate
+    out["pt"] = {"workload": f"configs[2]: parallel tempering, {chains} replicas x 6 curves (nx=128), swaps every 10 "
+                             f"iterations, chains sharded over {world} GPU(s); steady state between iteration "
+                             f"{short} and {args.pt_iters}",
+                 "sims_per_s": rate * chains * 6, "checksum_logll": float(res.H.loglikelihood[:, -1].sum()),
+                 "swap_accept": int(res.H.swap_accept.sum()), "swap_attempts": int(res.H.swap_attempts.sum())}
+    # ---- configs[4]: dense grid, args.dense_points per GPU, sharded over the ranks ---------------
+    n_pts = args.dense_points * world
+    X = draw_states(n_pts, seed=4242)
+    sim_flags = {"num_iters": n_pts, "log_y": 1, "model": "std", "ini_mode": "density", "rtol": 1e-7, "atol": None,
+                 "likel2move_ratio": {"TRPL": 50.0}, "scale_factor": None, "irf_convolution": None,
+                 "current_sigma": {"TRPL": 1.0}, "IRF_tables": None}
+    P = np.zeros(n_pts)
+    ds.simulate(([t] * 6, vals, uncs), P[:2048 * world].copy(), X[:2048 * world], param_info, dict(sim_info), ini,
+                sim_flags, comm=comm)                                 # warm-up
+    comm.barrier()
+    t0 = time.perf_counter()
+    ds.simulate(([t] * 6, vals, uncs), P, X, param_info, dict(sim_info), ini, sim_flags, comm=comm)
+    comm.barrier()
+    dt = allreduce_max(dist, local, time.perf_counter() - t0)
+    out["dense_sims_per_s"] = 6 * n_pts / dt
+    out["dense"] = {"workload": f"configs[4]: dense grid, {args.dense_points} points per GPU x 6 curves (nx=128), "
+                                f"host buffers in and out, sharded over {world} GPU(s)",
+                    "seconds": dt, "n_nonfinite": int((~np.isfinite(P)).sum())}
+    return out
+
+
 def run_reference(args):
-    """The reference's CPU path (oracle port: the reference is Python and cannot travel) on all
-    host cores; each step is a bounded sample of the same workload."""
+    """The reference's CPU path on all host cores: the unmodified reference modules from oracle/_ref
+    when present (kind "reference"), else the pinned oracle port.  Each step is a bounded sample of
+    the same workload (the first sets of the same seeded parameter-set list the GPU arm draws),
+    dealt to the cores from a work queue."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -380,10 +544,13 @@ def run_reference(args):
            "unit": "sims/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "configs[1] sample: random parameter sets x 6 TRPL curves, nx=128, std model",
-                      "sets_per_step": per_step, "rtol": 1e-7, "atol": 1e-10, "hmax": 4},
-           "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port",
-                            "sample": f"{per_step} parameter sets x 6 curves per step"},
+           "config": {"workload": "configs[1] sample: random parameter sets x 6 TRPL curves "
+                                  "(staub_MAPI threepower_twothick), nx=128, std model",
+                      "sets_per_step": per_step, "curves_per_set": 6, "times_per_curve": int(len(t)),
+                      "rtol": 1e-7, "atol": 1e-10, "hmax": "4 ns (the reference's LSODA max_step, sim_utils.py:17)",
+                      "parallelism": f"{cores} worker processes, work queue of single parameter sets"},
+           "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": cpu_kind(),
+                            "sample": f"{per_step} parameter sets x 6 curves per step, " + CPU_DESCRIPTION[cpu_kind()]},
            "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -397,9 +564,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sets", type=int, default=4096, help="parameter sets per GPU")
     ap.add_argument("--cpu-sets", type=int, default=48, help="parameter sets in the CPU baseline sample")
-    ap.add_argument("--ref-sets-per-core", type=int, default=1)
+    ap.add_argument("--ref-sets-per-core", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="profiling runs only")
     ap.add_argument("--rtol", type=float, default=RTOL)
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs[2], [3], [4] segments")
+    ap.add_argument("--pt-iters", type=int, default=41)
+    ap.add_argument("--dense-points", type=int, default=32768, help="dense-grid points per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
