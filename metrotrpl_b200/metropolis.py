@@ -127,7 +127,7 @@ def sharded_eval(evaluator, comm, states, sigmas):
 
 def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, shared_fields,
                             unique_fields, RNG, logger, evaluator, comm, cur_ladder=None,
-                            need_initial_state=True):
+                            need_initial_state=True, reference_swap_aliasing=False):
     """Batched twin of main_metro_loop_serial (metropolis.py:93-137).
 
     states [n_chains, n_params, n_iters], logll/accept [n_chains, n_iters]; cur_ladder
@@ -177,10 +177,18 @@ def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, sha
                     swap_accept[i] += 1
                     logll[i, k] = bi_uj
                     logll[i + 1, k] = bj_ui
-                    tmp = states[i, :, k].copy()
-                    states[i, :, k] = states[i + 1, :, k]
-                    states[i + 1, :, k] = tmp
-                    cur_ladder[[i, i + 1]] = cur_ladder[[i + 1, i]]
+                    if reference_swap_aliasing:
+                        # metropolis.py:86 of the reference: a tuple swap of two NumPy views leaves
+                        # BOTH chains with the upper chain's state (and the upper chain's logll entry
+                        # with the lower state's likelihood).  Reproduced only on request, to compare
+                        # whole chains with the reference's serial path bit for bit.
+                        states[i, :, k] = states[i + 1, :, k]
+                        cur_ladder[i] = cur_ladder[i + 1]
+                    else:
+                        tmp = states[i, :, k].copy()
+                        states[i, :, k] = states[i + 1, :, k]
+                        states[i + 1, :, k] = tmp
+                        cur_ladder[[i, i + 1]] = cur_ladder[[i + 1, i]]
     return states, logll, accept, swap_attempts, swap_accept, cur_ladder
 
 
@@ -202,7 +210,9 @@ def metro(sim_info, iniPar, e_data, MCMC_fields, param_info, verbose=False, expo
 
     Extra keyword arguments: evaluator_factory (tests), comm (a parallel.Comm), irf_dir,
     install_signal_handlers (default True, as the reference), kernel ("auto" | "warp" | "cta":
-    which instantiation of the integrator evaluates the proposals, see CudaEvaluator).
+    which instantiation of the integrator evaluates the proposals, see CudaEvaluator),
+    reference_swap_aliasing (default False: swap correctly; True reproduces the reference's serial
+    swap, metropolis.py:86, which leaves both chains with the upper chain's state).
     """
     clock0 = perf_counter()
     comm = kwargs.get("comm", None) or Comm()
@@ -260,7 +270,8 @@ def metro(sim_info, iniPar, e_data, MCMC_fields, param_info, verbose=False, expo
         logger.info(f"Simulating from {starting_iter} to {ending_iter}")
         states, logll, accept, swap_att, swap_acc, cur_ladder = main_metro_loop_batched(
             states, logll, accept, starting_iter, ending_iter, shared_fields, unique_fields, RNG, logger,
-            evaluator, comm, cur_ladder=cur_ladder, need_initial_state=need_initial_state)
+            evaluator, comm, cur_ladder=cur_ladder, need_initial_state=need_initial_state,
+            reference_swap_aliasing=kwargs.get("reference_swap_aliasing", False))
         MS_list.H.swap_attempts += swap_att
         MS_list.H.swap_accept += swap_acc
         if ending_iter == num_iters:

@@ -191,7 +191,9 @@ def make_trial_moves(current_states, trial_moves, shared_fields, RNG, logger=Non
 
     Returns (proposals [n_chains, n_params], u [n_chains]).
     """
-    cur = np.asarray(current_states, dtype=float)
+    # contiguous copy: NumPy's log10 / power take different code paths (SIMD or scalar, last-bit
+    # different) for contiguous and strided operands, and states[:, :, k-1] is a strided view
+    cur = np.ascontiguousarray(current_states, dtype=float)
     n_chains, n_par = cur.shape
     bitgen = RNG.bit_generator
     can_batch = shared_fields.get("do_mu_constraint", None) is None and hasattr(bitgen, "advance")

@@ -191,3 +191,20 @@ def test_scale_fluence_and_absorption_factors_against_the_oracle():
     sf_d = dict(sf, ini_mode="density", _init_params=[np.full(64, 1e16)] * 3)
     with pytest.raises(ValueError, match="fluence"):
         eval_trial_moves(states, np.ones(2), {"TRPL": 1.0}, sf_d)
+
+
+@pytest.mark.parametrize("tag", ["bounds", "notemper"])
+def test_metro_on_gpu_equals_the_reference_golden_chains(tag):
+    """metro() on the CUDA evaluator against the golden chains of the unmodified reference's
+    metro(serial_fallback=True) (tests/golden/chains.npz): every accept and swap decision, the
+    states to rounding, the generator state at the end."""
+    from tests import test_golden_chains as gc
+    ms = gc.run_ours(tag, factory=None, reference_swap_aliasing=True)
+    G = gc.G
+    np.testing.assert_array_equal(ms.H.accept, G[f"{tag}_accept"])
+    np.testing.assert_allclose(ms.H.states, G[f"{tag}_states"], rtol=gc.STATE_RTOL, atol=0)
+    np.testing.assert_array_equal(ms.H.swap_accept, G[f"{tag}_swap_accept"])
+    np.testing.assert_allclose(ms.H.loglikelihood, G[f"{tag}_logll"], rtol=5e-3, atol=2e-3)
+    rng = np.random.default_rng(0)
+    rng.bit_generator.state = ms.random_state
+    assert gc.pcg_words(rng) == [int(x) for x in G[f"{tag}_final_rng"]]

@@ -320,8 +320,107 @@ def gen_real3():
                         pl_default=np.array([pad(pl_def[s]) for s in range(nS)]))
 
 
+def gen_chains():
+    """Golden chains: the reference's own metro(serial_fallback=True) (metropolis.py:283-473 ->
+    main_metro_loop_serial :93-137, trial_displacement_move :42-63, swap_move_serial :66-90,
+    trial_move_generation.make_trial_move :54-96), unmodified, on the small problem of
+    tests/test_metropolis_batched.small_problem (nx = 32, two curves, 4 chains, 20 iterations).
+    Recorded by wrapping (not replacing) the reference's functions: every proposal with the
+    generator state before it, every acceptance draw with its log-ratio, every swap attempt, the
+    final History.  Variants: hard bounds on (narrow prior: many retries), hard bounds off,
+    do_mu_constraint on (global np.random seeded), tempering off."""
+    import copy
+    import tempfile
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    import metropolis as ref_metro
+    from tests.test_metropolis_batched import small_problem
+
+    def pcg_words(state):
+        s = state["state"]
+        m = (1 << 64) - 1
+        return np.array([s["state"] >> 64, s["state"] & m, s["inc"] >> 64, s["inc"] & m,
+                         state["has_uint32"], state["uinteger"]], dtype=np.uint64)
+
+    def replay_u(state):
+        g = np.random.Generator(np.random.PCG64())
+        g.bit_generator.state = state
+        return g.random()
+
+    out = {}
+    variants = {
+        "bounds": dict(hard_bounds=1, narrow=True, temper=True, mu=None),
+        "free": dict(hard_bounds=0, narrow=True, temper=True, mu=None),
+        "mu": dict(hard_bounds=1, narrow=False, temper=False, mu=(20.0, 3.0)),
+        "notemper": dict(hard_bounds=1, narrow=True, temper=False, mu=None),
+    }
+    for tag, v in variants.items():
+        tmp = tempfile.mkdtemp()
+        sim_info, ini, e_data, MCMC, param_info = small_problem(tmp, n_chains=4, num_iters=20)
+        MCMC["checkpoint_freq"] = 20
+        MCMC["hard_bounds"] = v["hard_bounds"]
+        if v["narrow"]:
+            param_info["prior_dist"]["p0"] = (2e15, 4e15)
+            param_info["prior_dist"]["tauN"] = (400, 650)
+            param_info["prior_dist"]["Sf"] = (5, 20)
+        if not v["temper"]:
+            MCMC["temper_freq"] = 1000
+        if v["mu"] is not None:
+            MCMC["do_mu_constraint"] = v["mu"]
+            param_info["active"]["mu_n"] = 1
+            param_info["active"]["mu_p"] = 1
+        rec = {"prop_in": [], "prop_move": [], "prop_out": [], "prop_rng": [], "u": [], "logratio": [],
+               "acc": [], "acc_rng": [], "swap_i": [], "swap_k": [], "swap_ok": []}
+        orig_mtm, orig_roll, orig_swap = ref_metro.make_trial_move, ref_metro.roll_acceptance, ref_metro.swap_move_serial
+
+        def mtm(cur, move, sf, RNG, logger):
+            rec["prop_rng"].append(pcg_words(RNG.bit_generator.state))
+            rec["prop_in"].append(np.array(cur, dtype=float))
+            rec["prop_move"].append(np.array(move, dtype=float))
+            new = orig_mtm(cur, move, sf, RNG, logger)
+            rec["prop_out"].append(np.array(new, dtype=float))
+            return new
+
+        def roll(rng, logratio):
+            st = copy.deepcopy(rng.bit_generator.state)
+            res = orig_roll(rng, logratio)
+            rec["acc_rng"].append(pcg_words(st))
+            rec["u"].append(replay_u(st))
+            rec["logratio"].append(float(logratio))
+            rec["acc"].append(bool(res))
+            return res
+
+        def swap(k, i, *a, **kw):
+            res = orig_swap(k, i, *a, **kw)
+            rec["swap_i"].append(int(i)); rec["swap_k"].append(int(k)); rec["swap_ok"].append(bool(res))
+            return res
+        ref_metro.make_trial_move, ref_metro.roll_acceptance, ref_metro.swap_move_serial = mtm, roll, swap
+        ref_metro.all_signal_handler = lambda f: None          # leave this process's signal handlers alone
+        np.random.seed(1234)                                   # the reference's mu constraint draws from np.random
+        try:
+            ref_metro.metro(sim_info, ini, e_data, copy.deepcopy(MCMC), copy.deepcopy(param_info),
+                            export_path="gold.pik", serial_fallback=True)
+        finally:
+            ref_metro.make_trial_move, ref_metro.roll_acceptance, ref_metro.swap_move_serial = orig_mtm, orig_roll, orig_swap
+        import pickle
+        with open(os.path.join(tmp, "gold.pik"), "rb") as f:
+            sys.path.insert(0, REF)
+            MS = pickle.load(f)
+        for k, val in rec.items():
+            out[f"{tag}_{k}"] = np.array(val)
+        out[f"{tag}_states"] = MS.H.states
+        out[f"{tag}_logll"] = MS.H.loglikelihood
+        out[f"{tag}_accept"] = MS.H.accept
+        out[f"{tag}_swap_accept"] = MS.H.swap_accept
+        out[f"{tag}_swap_attempts"] = MS.H.swap_attempts
+        out[f"{tag}_final_rng"] = pcg_words(MS.random_state)
+        out[f"{tag}_vals"] = np.array(e_data[1])
+        print(tag, "accept", MS.H.accept.sum(axis=1), "swaps", MS.H.swap_accept, "proposals", len(rec["prop_out"]),
+              "acceptance draws", len(rec["u"]), flush=True)
+    np.savez_compressed(os.path.join(OUT, "chains.npz"), **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rhs", "irf", "known", "staub", "traps", "real3"]
+    which = sys.argv[1:] or ["rhs", "irf", "known", "staub", "traps", "real3", "chains"]
     if "rhs" in which:
         gen_rhs_pins()
     if "irf" in which:
@@ -334,3 +433,5 @@ if __name__ == "__main__":
         gen_traps_irf()
     if "real3" in which:
         gen_real3()
+    if "chains" in which:
+        gen_chains()
