@@ -180,14 +180,22 @@ int trpl_fp64_peak_probe(trpl_handle* h, int32_t iters, double* tflops, float* m
  *   proposals [n_chains][n_par], u [n_chains], n_draws = doubles consumed (advance the generator
  *   by this), n_failed [n_chains] failed attempts, fail_masks [n_chains][TRPL_MAX_LOGGED_FAILS]
  *   checks failed by each of the first failed attempts: bit i = parameter i out of bounds,
- *   bit 30 = p0 <= n0, bit 31 = tauN and tauP more than two decades apart.  n_par <= 30. */
+ *   bit 30 = p0 <= n0, bit 31 = tauN and tauP more than two decades apart.  n_par <= 30.
+ *   idx_mun >= 0 switches on do_mu_constraint (trial_move_generation.py:77-83): every attempt takes
+ *   the next of the caller's pre-drawn np.random uniforms ambi_u[n_ambi_u] (the reference draws the
+ *   ambipolar mobility from the GLOBAL np.random stream), new_ambi = ambi_lo + (ambi_hi - ambi_lo) u,
+ *   and mu_p is set from new_ambi and the proposed mu_n; n_ambi_used tells the caller how many to
+ *   consume from np.random.  mu_arg [n_chains] receives the linear mu_p of each chain's final attempt:
+ *   the caller overwrites proposals[:, idx_mup] with ITS log10 of it (NumPy's log10 is not libm's). */
 #define TRPL_MAX_LOGGED_FAILS 8
 int trpl_make_trial_moves(int32_t n_chains, int32_t n_par, const double* cur, const double* moves,
                           const uint8_t* do_log, const uint8_t* active, const double* lo,
                           const double* hi, int32_t idx_p0, int32_t idx_n0, int32_t idx_taun,
                           int32_t idx_taup, int32_t hard_bounds, int32_t max_tries,
                           const uint64_t pcg_state[2], const uint64_t pcg_inc[2], double* proposals,
-                          double* u, int64_t* n_draws, int32_t* n_failed, uint32_t* fail_masks);
+                          double* u, int64_t* n_draws, int32_t* n_failed, uint32_t* fail_masks,
+                          int32_t idx_mun, int32_t idx_mup, double ambi_lo, double ambi_hi,
+                          const double* ambi_u, int32_t n_ambi_u, int32_t* n_ambi_used, double* mu_arg);
 
 #ifdef __cplusplus
 }

@@ -247,7 +247,8 @@ def load_library() -> C.CDLL:
     u8p, u64p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
     lib.trpl_make_trial_moves.argtypes = [C.c_int32, C.c_int32, dp, dp, u8p, u8p, dp, dp, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_int32, C.c_int32, C.c_int32, u64p, u64p, dp, dp,
-                                          C.POINTER(C.c_int64), ip, u32p]
+                                          C.POINTER(C.c_int64), ip, u32p, C.c_int32, C.c_int32, C.c_double,
+                                          C.c_double, dp, C.c_int32, ip, dp]
     lib.trpl_set_queue_order.argtypes = [H, C.c_int32, ip]
     lib.trpl_synchronize.argtypes = [H]
     lib.trpl_timer_begin.argtypes = [H]

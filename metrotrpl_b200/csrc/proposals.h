@@ -5,7 +5,8 @@
 // Plain host C++.  Input and output are in the sampler's own scale (log10 of the parameters that
 // are sampled in log space): the transcendental conversions stay in NumPy on both sides of the
 // call, what happens here is one multiply-add per draw, so the proposals equal the Python mirror's
-// bit for bit (tests/test_metropolis_batched.py).  pow(10, x) is only used for the bounds test.
+// bit for bit (tests/test_metropolis_batched.py, tests/test_golden_chains.py).  pow(10, x) is only
+// used for the bounds test and for the mobility constraint.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -30,20 +31,36 @@ inline int make_trial_moves(int n_chains, int n_par, const double* cur, const do
                             const uint8_t* do_log, const uint8_t* active, const double* lo, const double* hi,
                             int idx_p0, int idx_n0, int idx_taun, int idx_taup, int hard_bounds, int max_tries,
                             const uint64_t pcg_state[2], const uint64_t pcg_inc[2], double* proposals, double* u,
-                            int64_t* n_draws, int32_t* n_failed, uint32_t* fail_masks, int max_logged) {
+                            int64_t* n_draws, int32_t* n_failed, uint32_t* fail_masks, int max_logged,
+                            int idx_mun, int idx_mup, double ambi_lo, double ambi_hi, const double* ambi_u,
+                            int n_ambi_u, int32_t* n_ambi_used, double* mu_arg) {
   Pcg64 g;
   g.state = ((unsigned __int128)pcg_state[0] << 64) | pcg_state[1];
   g.inc = ((unsigned __int128)pcg_inc[0] << 64) | pcg_inc[1];
   int64_t draws = 0;
+  int ambi_used = 0;
   double cand[32];
   const int tries = hard_bounds ? max_tries : 1;
   for (int m = 0; m < n_chains; ++m) {
     const double* logcur = cur + (size_t)m * n_par;       // already log-scaled where do_log
     const double* mv = moves + (size_t)m * n_par;
     int failed = 0;
+    double mu_last = 0.0;
     for (int t = 0; t < tries; ++t) {
       for (int i = 0; i < n_par; ++i) cand[i] = logcur[i] + mv[i] * (2 * g.next_double() - 1);
       draws += n_par;
+      if (idx_mun >= 0) {
+        // do_mu_constraint (trial_move_generation.py:77-83): the ambipolar mobility is drawn from the
+        // caller's pre-drawn np.random uniforms and mu_p follows from it and the proposed mu_n; the
+        // same libm calls NumPy's scalar math makes, in the same order
+        if (ambi_used >= n_ambi_u) return 2;
+        const double new_ambi = ambi_lo + (ambi_hi - ambi_lo) * ambi_u[ambi_used++];
+        // NumPy's log10 is its own implementation (7% of arguments differ from libm's in the last
+        // bit): the argument goes back to the caller, which applies np.log10 to the final attempt's;
+        // here the libm value only feeds the bounds test
+        mu_last = pow(2 / new_ambi - 1 / pow(10.0, cand[idx_mun]), -1.0);
+        cand[idx_mup] = log10(mu_last);
+      }
       if (!hard_bounds) break;                       // no checks without hard bounds (one attempt)
       uint32_t mask = 0;
       for (int i = 0; i < n_par; ++i) {
@@ -64,10 +81,12 @@ inline int make_trial_moves(int n_chains, int n_par, const double* cur, const do
     n_failed[m] = failed;
     double* p = proposals + (size_t)m * n_par;
     for (int i = 0; i < n_par; ++i) p[i] = cand[i];          // the last attempt, admissible or not
+    if (idx_mun >= 0 && mu_arg) mu_arg[m] = mu_last;
     u[m] = g.next_double();
     draws += 1;
   }
   *n_draws = draws;
+  if (n_ambi_used) *n_ambi_used = ambi_used;
   return 0;
 }
 

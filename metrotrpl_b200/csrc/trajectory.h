@@ -602,7 +602,8 @@ TRPL_FN void stage_combine(TrajMem& mem, double ih, const Vec<NPL, MODEL>& u, co
 //   PH_ACCEPTED  evaluate f(u) at the newly accepted state, read the signal out, emit measurement
 //                times, then start a step (Jacobian + factorisation), stage 1 uses f(u)
 //   PH_STAGE     evaluate f(stage argument), add the c-combination, solve
-//   PH_RETRY     step rejected: same u, same f(u) (kept in shared memory), new h
+//   PH_RETRY     step rejected: same u, new h; f(u) is re-evaluated (rejections are ~0.5% of the
+//                steps, and this keeps f(u) out of registers and shared memory)
 enum Phase { PH_ACCEPTED = 0, PH_STAGE = 1, PH_RETRY = 2 };
 
 // K = W^{-1} r with the factorisation of this step (traps: occupancy condensed out, see the

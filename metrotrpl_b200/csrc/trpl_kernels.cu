@@ -834,14 +834,21 @@ int trpl_make_trial_moves(int32_t n_chains, int32_t n_par, const double* cur, co
                           int32_t idx_p0, int32_t idx_n0, int32_t idx_taun, int32_t idx_taup,
                           int32_t hard_bounds, int32_t max_tries, const uint64_t pcg_state[2],
                           const uint64_t pcg_inc[2], double* proposals, double* u, int64_t* n_draws,
-                          int32_t* n_failed, uint32_t* fail_masks) {
+                          int32_t* n_failed, uint32_t* fail_masks, int32_t idx_mun, int32_t idx_mup,
+                          double ambi_lo, double ambi_hi, const double* ambi_u, int32_t n_ambi_u,
+                          int32_t* n_ambi_used, double* mu_arg) {
   if (n_chains < 1 || n_par < 1 || n_par > 30) return fail("trpl_make_trial_moves: 1..30 parameters");
   if (!cur || !moves || !do_log || !active || !lo || !hi || !pcg_state || !pcg_inc || !proposals || !u ||
       !n_draws || !n_failed || !fail_masks || max_tries < 1)
     return fail("trpl_make_trial_moves: bad arguments");
-  return trpl_host::make_trial_moves(n_chains, n_par, cur, moves, do_log, active, lo, hi, idx_p0, idx_n0,
-                                     idx_taun, idx_taup, hard_bounds, max_tries, pcg_state, pcg_inc,
-                                     proposals, u, n_draws, n_failed, fail_masks, TRPL_MAX_LOGGED_FAILS);
+  if (idx_mun >= 0 && (idx_mup < 0 || idx_mun >= n_par || idx_mup >= n_par || !ambi_u || n_ambi_u < 1 || !mu_arg))
+    return fail("trpl_make_trial_moves: the mobility constraint needs both indices and pre-drawn uniforms");
+  const int rc = trpl_host::make_trial_moves(n_chains, n_par, cur, moves, do_log, active, lo, hi, idx_p0, idx_n0,
+                                             idx_taun, idx_taup, hard_bounds, max_tries, pcg_state, pcg_inc,
+                                             proposals, u, n_draws, n_failed, fail_masks, TRPL_MAX_LOGGED_FAILS,
+                                             idx_mun, idx_mup, ambi_lo, ambi_hi, ambi_u, n_ambi_u, n_ambi_used, mu_arg);
+  if (rc == 2) return fail("trpl_make_trial_moves: ran out of pre-drawn uniforms for the mobility constraint");
+  return rc;
 }
 
 int trpl_fp64_peak_probe(trpl_handle* h, int32_t iters, double* tflops, float* ms_out) {

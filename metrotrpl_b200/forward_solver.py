@@ -97,42 +97,3 @@ def solve(iniPar, g: Grid, state, indexes, meas="TRPL", units=None, solver=("sol
                       meas_types=[meas], units=units, model=model, ini_mode=ini_mode, RTOL=RTOL,
                       ATOL=ATOL, honor_hmax=honor_hmax)
     return out[0][0]
-
-
-# --- small host-side readouts kept for API compatibility (forward_solver.py:228-274) -------------
-
-def integrate_1D(dx, y):
-    y = np.asarray(y, dtype=np.float64)
-    acc = y[0] * dx / 2
-    for i in range(1, len(y)):
-        acc += dx * (y[i] + y[i - 1]) / 2
-    acc += y[-1] * dx / 2
-    return acc
-
-
-def integrate_2D(dx, y):
-    return np.array([integrate_1D(dx, row) for row in np.asarray(y)])
-
-
-def calculate_RR(N, P, ks, n0, p0):
-    return ks * (N * P - n0 * p0)
-
-
-def calculate_photoc(N, P, mu_n, mu_p, n0, p0):
-    return q_C * (mu_n * (N - n0) + mu_p * (P - p0))
-
-
-def _integrate_any(dx, f):
-    if f.ndim == 2:
-        return integrate_2D(dx, f)
-    if f.ndim == 1:
-        return integrate_1D(dx, f)
-    raise ValueError(f"Invalid number of dims (got {f.ndim} dims) in Solution")
-
-
-def calculate_PL(dx, N, P, ks, n0, p0):
-    return _integrate_any(dx, calculate_RR(np.asarray(N), np.asarray(P), ks, n0, p0))
-
-
-def calculate_TRTS(dx, N, P, mu_n, mu_p, n0, p0):
-    return _integrate_any(dx, calculate_photoc(np.asarray(N), np.asarray(P), mu_n, mu_p, n0, p0))

@@ -156,6 +156,12 @@ def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, sha
         proposals, u = make_trial_moves(states[:, :, k - 1], moves, shared_fields, RNG, logger)
         new_ladder = sharded_eval(evaluator, comm, proposals, sigmas)
         new_ll = new_ladder[own, own]
+        n_bad = int(np.count_nonzero(np.isneginf(new_ll)))
+        if n_bad:
+            # the reference warns once per failed simulation (trial_move_evaluation.py:66-72, 103-106,
+            # 117-123, 159-165); here one line per iteration
+            logger.warning(f"Iter {k}: {n_bad} of {n_chains} proposals have likelihood -inf "
+                           "(integrator failure, failed convolution, too many negative values or NaN)")
         logratio = new_ll - logll[:, k - 1]
         logratio = np.where(np.isnan(logratio), -np.inf, logratio)
         with np.errstate(over="ignore"):

@@ -1,6 +1,10 @@
-"""Grid and constants of the reference's sim_utils.py that the hot path touches.
+"""Grid, History, Ensemble and the constants of the reference's sim_utils.py that the path touches.
 
-Mirrors /root/reference/sim_utils.py:13-23 (constants) and :248-283 (Grid).
+When this package is dropped into a MetroTRPL checkout the reference's own
+`sim_utils` is importable and ITS History / Ensemble / Grid are used - existing checkpoints then
+unpickle into the classes that wrote them and nothing is duplicated.  Stand-alone (tests, bench,
+the GPU box) the minimal twins below are used: /root/reference/sim_utils.py:13-23 (constants),
+:25-99 (History), :100-196 (Ensemble), :248-283 (Grid).
 """
 import pickle
 from sys import float_info
@@ -130,3 +134,22 @@ class Ensemble:
         self.H.update(self.ensemble_fields["names"])
         with open(fname, "wb+") as f:
             pickle.dump(self, f)
+
+
+def _bind_reference_classes():
+    """Prefer the reference's own classes when its sim_utils is importable (and really is it)."""
+    global Grid, History, Ensemble
+    try:
+        import sim_utils as ref
+    except Exception:
+        return False
+    if ref is globals().get("__module_self__"):
+        return False
+    need = ("Grid", "History", "Ensemble", "MAX_PROPOSALS", "NEGATIVE_FRAC_TOL", "DEFAULT_HMAX")
+    if not all(hasattr(ref, n) for n in need) or ref.MAX_PROPOSALS != MAX_PROPOSALS:
+        return False
+    Grid, History, Ensemble = ref.Grid, ref.History, ref.Ensemble
+    return True
+
+
+USING_REFERENCE_CLASSES = _bind_reference_classes()

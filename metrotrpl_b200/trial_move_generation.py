@@ -144,6 +144,22 @@ def _make_trial_moves_native(lib, cur, trial_moves, shared_fields, RNG, logger):
     masks = np.zeros((n_chains, MAX_LOGGED_FAILS), dtype=np.uint32)
     n_draws = C.c_int64(0)
     dp = C.POINTER(C.c_double)
+    mu = shared_fields.get("do_mu_constraint", None)
+    if mu is not None:
+        # The reference draws the ambipolar mobility from the GLOBAL np.random stream, one draw per
+        # attempt.  Enough uniforms for the worst case are pre-drawn, the C side reports how many it
+        # used, and the global stream is then rewound and advanced by exactly that many.
+        np_state = np.random.get_state()
+        max_tries = MAX_PROPOSALS if shared_fields.get("hard_bounds", 0) else 1
+        ambi_u = np.random.random_sample(n_chains * max_tries)
+        ambi_lo, ambi_hi = float(mu[0] - mu[1]), float(mu[0] + mu[1])
+        i_mun, i_mup = idx["mu_n"], idx["mu_p"]
+    else:
+        ambi_u = np.zeros(1)
+        ambi_lo = ambi_hi = 0.0
+        i_mun = i_mup = -1
+    n_ambi_used = C.c_int32(0)
+    mu_arg = np.zeros(n_chains)
     rc = lib.trpl_make_trial_moves(
         n_chains, n_par, cur.ctypes.data_as(dp), moves.ctypes.data_as(dp),
         do_log.ctypes.data_as(C.POINTER(C.c_uint8)), active.ctypes.data_as(C.POINTER(C.c_uint8)),
@@ -153,7 +169,15 @@ def _make_trial_moves_native(lib, cur, trial_moves, shared_fields, RNG, logger):
         idx["tauP"] if "tauN" in order and "tauP" in order else -1,
         1 if shared_fields.get("hard_bounds", 0) else 0, MAX_PROPOSALS, pcg_state, pcg_inc,
         proposals.ctypes.data_as(dp), u.ctypes.data_as(dp), C.byref(n_draws),
-        n_failed.ctypes.data_as(C.POINTER(C.c_int32)), masks.ctypes.data_as(C.POINTER(C.c_uint32)))
+        n_failed.ctypes.data_as(C.POINTER(C.c_int32)), masks.ctypes.data_as(C.POINTER(C.c_uint32)),
+        i_mun, i_mup, ambi_lo, ambi_hi, ambi_u.ctypes.data_as(dp), int(ambi_u.size), C.byref(n_ambi_used),
+        mu_arg.ctypes.data_as(dp))
+    if mu is not None:
+        np.random.set_state(np_state)
+        if n_ambi_used.value:
+            np.random.random_sample(n_ambi_used.value)
+        with np.errstate(invalid="ignore"):
+            proposals[:, i_mup] = [np.log10(x) for x in mu_arg]     # NumPy's scalar log10, as the reference
     if rc != 0:
         raise RuntimeError(lib.trpl_last_error().decode())
     _advance_keeping_buffer(RNG.bit_generator, n_draws.value)
@@ -197,7 +221,7 @@ def make_trial_moves(current_states, trial_moves, shared_fields, RNG, logger=Non
     n_chains, n_par = cur.shape
     bitgen = RNG.bit_generator
     can_batch = shared_fields.get("do_mu_constraint", None) is None and hasattr(bitgen, "advance")
-    if native and can_batch and n_par <= 30 and bitgen.state.get("bit_generator") == "PCG64":
+    if native and hasattr(bitgen, "advance") and n_par <= 30 and bitgen.state.get("bit_generator") == "PCG64":
         lib = _native_lib()
         if lib is not None and hasattr(lib, "trpl_make_trial_moves"):
             return _make_trial_moves_native(lib, cur, trial_moves, shared_fields, RNG, logger)

@@ -13,6 +13,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a box without a CUDA device skips the GPU tier; `-m gpu` asked for
+    explicitly still runs it there and fails loudly (the product has no CPU fallback)."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device on this box (run the GPU tier with -m gpu on a B200)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
