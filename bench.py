@@ -569,7 +569,7 @@ def main():
     ap.add_argument("--rtol", type=float, default=RTOL)
     ap.add_argument("--no-extras", action="store_true", help="skip the configs[2], [3], [4] segments")
     ap.add_argument("--pt-iters", type=int, default=41)
-    ap.add_argument("--dense-points", type=int, default=32768, help="dense-grid points per GPU")
+    ap.add_argument("--dense-points", type=int, default=65536, help="dense-grid points per GPU")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -418,6 +418,10 @@ int launch_cta(trpl_handle* h, KernelArgs a) {
 template <int MODEL>
 int launch_npl(trpl_handle* h, const KernelArgs& a) {
   const int nx = h->max_nx;
+#ifdef TRPL_DEV_NX256_ONLY      // developer builds of tuning variants: the nx = 256 instantiation only
+  if (h->all_full && nx == 256) return launch<8, MODEL, true>(h, a);
+  return fail("this developer build only holds the nx=256 instantiation");
+#else
   // the padding-free instantiation exists for the headline grid (nx = 128) and nx = 256
   if (h->all_full && nx == 128) return launch<4, MODEL, true>(h, a);
 #ifdef TRPL_DEV_HEADLINE_ONLY   // developer builds of tuning variants: compile one instantiation only
@@ -429,6 +433,7 @@ int launch_npl(trpl_handle* h, const KernelArgs& a) {
   if (nx <= 128) return launch<4, MODEL, false>(h, a);
   if (nx <= 256) return launch<8, MODEL, false>(h, a);
   return fail("nx > 256 is not supported by this build");
+#endif
 #endif
 }
 

@@ -113,7 +113,7 @@ class _DeviceRows:
     """Zero-copy view of library-owned device memory for torch (CUDA array interface)."""
 
     def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), True),
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False),
                                          "version": 2}
 
 
