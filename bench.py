@@ -462,7 +462,7 @@ def run_extras(args, rank, world, local, dist, ini, t, vals, uncs, peak_tf):
                   "init_guess": dict(zip(NAMES, GUESS)), "trial_move": {n: 0.02 for n in NAMES}}
     sim_info = {"num_meas": 6, "lengths": LENGTHS, "nx": [NX] * 6, "meas_types": ["TRPL"] * 6}
 
-    def pt_run(iters):
+    def pt_run(iters, kernel="auto"):
         import copy
         tmp = tempfile.mkdtemp()
         mc = {"init_cond_path": "synthetic", "measurement_path": "synthetic", "output_path": tmp,
@@ -473,7 +473,7 @@ def run_extras(args, rank, world, local, dist, ini, t, vals, uncs, peak_tf):
         comm.barrier()
         t0 = time.perf_counter()
         res = metro(sim_info, ini, ([t] * 6, vals, uncs), mc, copy.deepcopy(param_info), export_path="pt.pik",
-                    comm=comm, install_signal_handlers=False)
+                    comm=comm, install_signal_handlers=False, kernel=kernel)
         comm.barrier()
         return time.perf_counter() - t0, res
     short = 11
@@ -488,6 +488,17 @@ def run_extras(args, rank, world, local, dist, ini, t, vals, uncs, peak_tf):
                              f"{short} and {args.pt_iters}",
                  "sims_per_s": rate * chains * 6, "checksum_logll": float(res.H.loglikelihood[:, -1].sum()),
                  "swap_accept": int(res.H.swap_accept.sum()), "swap_attempts": int(res.H.swap_attempts.sum())}
+    # the same chains through the low-latency integrator (order-6 extrapolation, one CTA per
+    # trajectory): pays off once an iteration's trajectories fit one wave of a GPU (N >= 4 here)
+    pt_run(short, "seulex")
+    t_short, _ = pt_run(short, "seulex")
+    t_long, res_x = pt_run(args.pt_iters, "seulex")
+    rate_x = (args.pt_iters - short) / max(t_long - t_short, 1e-9)
+    rate_x = 1.0 / allreduce_max(dist, local, 1.0 / rate_x)
+    out["pt_seulex_iters_per_s"] = rate_x
+    out["pt"]["seulex_kernel"] = {"iters_per_s": rate_x, "checksum_logll": float(res_x.H.loglikelihood[:, -1].sum()),
+                                  "note": "metro(kernel='seulex'): csrc/extrapolation.h; a different integrator, so its "
+                                          "chains equal the default kernel's only until a decision differs"}
     # ---- configs[4]: dense grid, args.dense_points per GPU, sharded over the ranks ---------------
     n_pts = args.dense_points * world
     X = draw_states(n_pts, seed=4242)

@@ -55,9 +55,14 @@ enum trpl_status {
 };
 enum trpl_opt_flags { TRPL_OPT_FORCE_MIN_Y = 1, TRPL_OPT_NO_LIKELIHOOD = 2, TRPL_OPT_LADDER = 4,
                       TRPL_OPT_NO_EXPLICIT = 8, /* always use the Rosenbrock integrator */
-                      TRPL_OPT_CTA_PER_TRAJ = 16 /* one trajectory per CTA of 128 threads instead of one per
+                      TRPL_OPT_CTA_PER_TRAJ = 16, /* one trajectory per CTA of 128 threads instead of one per
                                                     warp: lowest latency per trajectory, for small batches
-                                                    (tempering); 'std' model, nx = 128 only */ };
+                                                    (tempering); 'std' model, nx = 128 only */
+                      TRPL_OPT_EXTRAPOLATION = 32 /* integrate with the order-6 extrapolation method
+                                                    (csrc/extrapolation.h) instead of RODAS4; together with
+                                                    TRPL_OPT_CTA_PER_TRAJ its six columns run in parallel on
+                                                    the four warps of a CTA: a quarter of the latency per
+                                                    trajectory; 'std' model, nx = 128 only */ };
 
 /* one measurement (sim_info["lengths"/"nx"/"meas_types"][i] + its slice of the data arrays) */
 typedef struct trpl_meas_desc {

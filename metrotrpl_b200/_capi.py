@@ -29,7 +29,7 @@ INI_IDS = {"density": 0, "fluence": 1}
 
 ST_MAX_STEPS, ST_H_UNDERFLOW, ST_NONFINITE, ST_FLOORED, ST_NEG_FRAC, ST_NAN_LL, ST_CONV_FAIL = 1, 2, 4, 8, 16, 32, 64
 ST_EXPLICIT = 128
-OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD, OPT_LADDER, OPT_NO_EXPLICIT, OPT_CTA_PER_TRAJ = 1, 2, 4, 8, 16
+OPT_FORCE_MIN_Y, OPT_NO_LIKELIHOOD, OPT_LADDER, OPT_NO_EXPLICIT, OPT_CTA_PER_TRAJ, OPT_EXTRAPOLATION = 1, 2, 4, 8, 16, 32
 
 # Defaults of the integrator.  RTOL keeps the reference's default value and meaning
 # (forward_solver.py:18).  The reference's default ATOL (1e-10 nm^-3, forward_solver.py:19) is larger

@@ -85,7 +85,8 @@ enum StatusBits {
   ST_EXPLICIT = 128     // informational: integrated by the explicit Runge-Kutta path (explicit.h)
 };
 
-enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2, OPT_LADDER = 4, OPT_NO_EXPLICIT = 8, OPT_CTA_PER_TRAJ = 16 };
+enum OptFlags { OPT_FORCE_MIN_Y = 1, OPT_NO_LIKELIHOOD = 2, OPT_LADDER = 4, OPT_NO_EXPLICIT = 8, OPT_CTA_PER_TRAJ = 16,
+                OPT_EXTRAPOLATION = 32 };
 
 struct SolverOpts {
   double rtol, atol;

@@ -21,6 +21,7 @@
 #include "trajectory.h"
 #include "explicit.h"
 #include "cta_trajectory.h"
+#include "extrapolation.h"
 #include "proposals.h"
 
 namespace {
@@ -212,6 +213,73 @@ __global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_explicit
     run_trajectory_explicit<NPL, MODEL, FULL>(in, a.opt, mem, out, mid);
     out.status |= ST_EXPLICIT;
     finish_traj(a, traj, warp, in, mid, out);
+  }
+  tmem_release<SL>(warp, mem.tm);
+}
+
+// The order-6 extrapolation integrator (extrapolation.h), one warp per trajectory: persistent warps
+// exactly like trpl_forward_kernel (same storage layout, same queue).  Exists for A/B measurements
+// and as the bit-for-bit twin of the cooperative kernel below.
+template <int NPL, int MODEL, bool FULL>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_seulex_kernel(const KernelArgs a) {
+  typedef Slots<NPL, MODEL> SL;
+  extern __shared__ double2 smem[];
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  TrajMem mem{LaneMem{smem + warp * (SL::COUNT * 32)}, tmem_acquire<SL>(warp)};
+  for (;;) {
+    int traj = 0;
+    if (lane == 0) traj = atomicAdd(a.counter, 1);
+    traj = __shfl_sync(0xffffffffu, traj, 0);
+    if (traj >= a.n_traj) break;
+    if (a.queue) {
+      traj = a.queue[traj];
+    } else {
+      const int n_sets_q = a.n_traj / a.n_meas;
+      const int qm = traj / n_sets_q;
+      traj = (traj - qm * n_sets_q) * a.n_meas + a.meas_order[qm];
+    }
+    TrajIn in;
+    setup_traj(a, traj, warp, in);
+    TrajOut out;
+    TrajMid mid;
+    run_trajectory_seulex<NPL, MODEL, FULL>(in, a.opt, mem, out, mid);
+    finish_traj(a, traj, warp, in, mid, out);
+  }
+  tmem_release<SL>(warp, mem.tm);
+}
+
+// The same integrator with the six columns of every step spread over the four warps of the CTA:
+// ONE trajectory per CTA, a quarter of the sequential depth.  Each warp keeps the full state and its
+// own factorisation storage (its slices of tensor and shared memory, as in trpl_forward_kernel); the
+// increments of the columns cross warps through a double-buffered exchange area behind the slices.
+template <int NPL, int MODEL, bool FULL>
+__global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_seulex_cta_kernel(const KernelArgs a) {
+  typedef Slots<NPL, MODEL> SL;
+  extern __shared__ double2 smem[];
+  __shared__ int s_traj, s_flag;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  TrajMem mem{LaneMem{smem + warp * (SL::COUNT * 32)}, tmem_acquire<SL>(warp)};
+  double2* xch = smem + WARPS_PER_CTA * (SL::COUNT * 32);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_traj = atomicAdd(a.counter, 1);
+    __syncthreads();
+    int traj = s_traj;
+    if (traj >= a.n_traj) break;
+    if (a.queue) {
+      traj = a.queue[traj];
+    } else {
+      const int n_sets_q = a.n_traj / a.n_meas;
+      const int qm = traj / n_sets_q;
+      traj = (traj - qm * n_sets_q) * a.n_meas + a.meas_order[qm];
+    }
+    TrajIn in;
+    setup_traj(a, traj, 0, in);               // warps_per_cta == 1: one step log / scratch slice per CTA
+    TrajOut out;
+    TrajMid mid;
+    run_trajectory_seulex_cta<NPL, MODEL, FULL>(in, a.opt, mem, xch, &s_flag, warp, out, mid);
+    if (warp == 0) finish_traj(a, traj, 0, in, mid, out);
   }
   tmem_release<SL>(warp, mem.tm);
 }
@@ -409,6 +477,44 @@ int launch_cta(trpl_handle* h, KernelArgs a) {
   a.defer_list = nullptr; a.defer_count = h->d_counter.p + 2;
   CU(cudaEventRecord(h->ev0, h->stream));
   trpl_cta_kernel<<<grid, cta::NX, 0, h->stream>>>(a);
+  CU(cudaGetLastError());
+  h->launches += 1;
+  CU(cudaEventRecord(h->ev1, h->stream));
+  return 0;
+}
+
+// TRPL_OPT_EXTRAPOLATION: the order-6 extrapolation integrator, one warp per trajectory or (with
+// TRPL_OPT_CTA_PER_TRAJ) one CTA per trajectory.  'std' model, every measurement on 128 nodes.
+int launch_seulex(trpl_handle* h, KernelArgs a, bool cooperative) {
+  typedef Slots<4, MODEL_STD> SL;
+  if (h->model != TRPL_MODEL_STD || !h->all_full || h->max_nx != 128)
+    return fail("TRPL_OPT_EXTRAPOLATION: this integrator is built for the 'std' model with nx = 128 on every measurement");
+  const int wpc = WARPS_PER_CTA;
+  const size_t xch_bytes = cooperative ? (size_t)2 * Seulex::K * 4 * 32 * sizeof(double2) : 0;
+  const size_t smem = (size_t)wpc * SL::BYTES + xch_bytes;
+  auto kern = cooperative ? trpl_seulex_cta_kernel<4, MODEL_STD, true> : trpl_seulex_kernel<4, MODEL_STD, true>;
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int by_smem = (int)((size_t)h->prop.sharedMemPerMultiprocessor / (smem + 1024 + 16));
+  const int per_sm = std::min(std::min(CTAS_PER_SM, by_smem), 512 / TmCta<SL>::COLS);
+  if (per_sm < 1) return fail("extrapolation kernel does not fit on an SM");
+  a.warps_per_cta = cooperative ? 1 : wpc;
+  const int slots = cooperative ? 1 : wpc;                       // trajectories per CTA
+  int grid = std::min(h->prop.multiProcessorCount * per_sm, (a.n_traj + slots - 1) / slots);
+  if (grid < 1) grid = 1;
+  if (getenv("TRPL_DEBUG"))
+    fprintf(stderr, "[trpl] launch extrapolation (%s): %zu B smem/CTA, %d CTAs/SM, grid %d\n",
+            cooperative ? "one CTA per trajectory" : "one warp per trajectory", smem, per_sm, grid);
+  if (a.scratch) {
+    CU(h->d_scratch.reserve((size_t)grid * slots * a.scratch_stride));
+    a.scratch = h->d_scratch.p;
+  }
+  CU(h->d_hist.reserve((size_t)grid * slots * 3 * HIST_CAP));
+  a.hist = h->d_hist.p;
+  CU(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(int), h->stream));
+  a.defer_list = nullptr; a.defer_count = h->d_counter.p + 2;
+  CU(cudaEventRecord(h->ev0, h->stream));
+  kern<<<grid, 32 * wpc, smem, h->stream>>>(a);
   CU(cudaGetLastError());
   h->launches += 1;
   CU(cudaEventRecord(h->ev1, h->stream));
@@ -747,6 +853,7 @@ int trpl_run_resident(trpl_handle* h, const trpl_solver_opts* opts, int32_t want
   a.queue = (h->queue_n > 0 && h->queue_n == h->n_sets * h->n_meas) ? h->d_queue.p : nullptr;
   a.n_traj = h->n_sets * h->n_meas; a.n_meas = h->n_meas; a.n_times_total = h->n_times_total;
   memcpy(&a.opt, opts, sizeof(SolverOpts));
+  if (opts->flags & TRPL_OPT_EXTRAPOLATION) return launch_seulex(h, a, (opts->flags & TRPL_OPT_CTA_PER_TRAJ) != 0);
   if (opts->flags & TRPL_OPT_CTA_PER_TRAJ) return launch_cta(h, a);
   if (h->model == TRPL_MODEL_STD) return launch_npl<MODEL_STD>(h, a);
 #ifdef TRPL_DEV_HEADLINE_ONLY

@@ -66,9 +66,21 @@ class CudaEvaluator:
         sim = shared_fields["_sim_info"]
         eligible = shared_fields.get("model", "std") == "std" and all(int(nx) == 128 for nx in sim["nx"])
         n_global = int(shared_fields.get("_n_chains", 1)) * self.cache.n_meas
-        if kernel == "cta" or (kernel == "auto" and eligible and n_global <= CTA_KERNEL_MAX_TRAJ):
+        if kernel not in ("auto", "warp", "cta", "seulex"):
+            raise ValueError(f"unknown kernel {kernel!r}")
+        if kernel == "seulex":
+            # order-6 extrapolation integrator, its columns in parallel on the four warps of a CTA
+            # (csrc/extrapolation.h): 1.4-2x lower latency per trajectory than RODAS4 while the whole
+            # iteration fits the GPU in one wave (<= ~300 trajectories per GPU), lower throughput
+            # beyond.  A different integrator: results agree with RODAS4's to integration accuracy
+            # (log-likelihoods to 2e-7), not bit for bit, so it is never chosen automatically.
+            if not eligible:
+                raise ValueError("kernel='seulex' needs the 'std' model with nx = 128 on every measurement")
+            self.flags |= _capi.OPT_EXTRAPOLATION | _capi.OPT_CTA_PER_TRAJ
+        elif kernel == "cta" or (kernel == "auto" and eligible and n_global <= CTA_KERNEL_MAX_TRAJ):
             self.flags |= _capi.OPT_CTA_PER_TRAJ
-        self.kernel = "cta" if self.flags & _capi.OPT_CTA_PER_TRAJ else "warp"
+        self.kernel = ("seulex" if self.flags & _capi.OPT_EXTRAPOLATION else
+                       "cta" if self.flags & _capi.OPT_CTA_PER_TRAJ else "warp")
         self._cost = None       # integrator steps of the previous call's trajectories
         self.n_failed = 0       # trajectories of the last call with an integrator failure flag
 
@@ -215,7 +227,7 @@ def metro(sim_info, iniPar, e_data, MCMC_fields, param_info, verbose=False, expo
     """Same call as the reference's metro() (metropolis.py:283-473).
 
     Extra keyword arguments: evaluator_factory (tests), comm (a parallel.Comm), irf_dir,
-    install_signal_handlers (default True, as the reference), kernel ("auto" | "warp" | "cta":
+    install_signal_handlers (default True, as the reference), kernel ("auto" | "warp" | "cta" | "seulex":
     which instantiation of the integrator evaluates the proposals, see CudaEvaluator),
     reference_swap_aliasing (default False: swap correctly; True reproduces the reference's serial
     swap, metropolis.py:86, which leaves both chains with the upper chain's state).

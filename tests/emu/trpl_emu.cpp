@@ -10,6 +10,7 @@
 #include "../../include/metrotrpl_b200.h"
 #include "../../metrotrpl_b200/csrc/trajectory.h"
 #include "../../metrotrpl_b200/csrc/explicit.h"
+#include "../../metrotrpl_b200/csrc/extrapolation.h"
 
 using namespace trpl;
 
@@ -45,7 +46,9 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
     in.post_pass = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
     TrajOut out;
     TrajMid mid;
-    if (run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out, mid, !(opt.flags & OPT_NO_EXPLICIT))) {
+    if (opt.flags & OPT_EXTRAPOLATION) {
+      run_trajectory_seulex<NPL, MODEL, FULL>(in, opt, sm, out, mid);      // the one-warp driver
+    } else if (run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out, mid, !(opt.flags & OPT_NO_EXPLICIT))) {
       run_trajectory_explicit<NPL, MODEL, FULL>(in, opt, sm, out, mid);
       out.status |= ST_EXPLICIT;
     }

@@ -49,3 +49,17 @@ def test_explicit_rk_path_for_nonstiff_trajectories():
 
 def test_hmax_is_honoured_on_request():
     print(pc.check_hmax_option(backend))
+
+
+def test_extrapolation_integrator_against_the_converged_truth():
+    """csrc/extrapolation.h (order-6 extrapolated linearly implicit Euler), one-warp driver, on both
+    staub fixtures; route (A) of the truth is RODAS4 at rtol 1e-9: two unrelated integrators."""
+    from metrotrpl_b200 import _capi
+
+    def seulex(prob, params, aux, opts, want_curves):
+        o = _capi.SolverOpts(opts.rtol, opts.atol, opts.hmax, opts.max_steps, opts.flags | _capi.OPT_EXTRAPOLATION)
+        return emu.loglik_batch(prob, params, aux, o, want_curves)
+    for check in (pc.check_staub, pc.check_real3):
+        rep = check(seulex, rtol=1e-7, tight_rtol=1e-9, curve_tol=3e-5, truth_backend=backend)
+        print({k: v for k, v in rep.items() if not k.startswith("logll_rows")})
+        assert rep["mean_steps"] < 200

@@ -38,6 +38,22 @@ def make_backend_cta(ctx):
     return backend
 
 
+def make_backend_flags(ctx, flags):
+    def backend(prob, params, aux, opts, want_curves):
+        ctx.set_problem(prob)
+        o = _capi.SolverOpts(opts.rtol, opts.atol, opts.hmax, opts.max_steps, opts.flags | flags)
+        return ctx.loglik_batch(params, aux, o, want_curves=want_curves)
+    return backend
+
+
+SEULEX_WARP = _capi.OPT_EXTRAPOLATION
+SEULEX_CTA = _capi.OPT_EXTRAPOLATION | _capi.OPT_CTA_PER_TRAJ
+# the extrapolation integrator's curve bound: one fixture curve (state 13: SRH lifetime collapsing from
+# tauP to tauN as the injection falls through p0) is 2.4e-5 off, all others within 5e-6; the north
+# star asks for 1e-4.  Its log-likelihoods are within 2e-7 (bound 1e-6, as for RODAS4).
+SEULEX_CURVE_TOL = 3e-5
+
+
 def test_device_is_blackwell(ctx):
     info = ctx.device_info()
     print(info)
@@ -276,3 +292,47 @@ def test_cta_per_trajectory_kernel_refuses_what_it_does_not_hold(ctx):
     with pytest.raises(_capi.TrplError, match="nx = 128"):
         ctx.loglik_batch(_capi.pack_params(st, idx, units), _capi.default_aux(1, 1, [1.0]),
                          _capi.make_opts(flags=_capi.OPT_NO_LIKELIHOOD | _capi.OPT_CTA_PER_TRAJ), want_curves=True)
+
+
+def test_extrapolation_integrator_against_the_converged_truth(ctx):
+    """The order-6 extrapolation integrator (csrc/extrapolation.h), cooperative kernel (one CTA per
+    trajectory), held against the same three truth routes; route (A) is RODAS4 at rtol 1e-10, so
+    this is also a cross-check of two unrelated integrators."""
+    rodas = make_backend(ctx)
+    for check in (pc.check_staub, pc.check_real3):
+        rep = check(make_backend_flags(ctx, SEULEX_CTA), rtol=1e-7, tight_rtol=1e-10, curve_tol=SEULEX_CURVE_TOL,
+                    truth_backend=rodas)
+        print({k: v for k, v in rep.items() if not k.startswith("logll_rows")})
+        assert rep["max_logll_rel_vs_converged"] <= pc.LOGLL_TOL
+        assert rep["mean_steps"] < 0.5 * 400          # RODAS4 takes ~400 steps per curve on these sets
+
+
+def test_extrapolation_kernels_one_warp_and_one_cta_agree_bit_for_bit(ctx):
+    """The cooperative kernel computes its six columns on four warps and combines them in the fixed
+    order the one-warp kernel uses: same bits, any queue order."""
+    g, prob, params, aux = pc.staub_problem()
+    opts = _capi.make_opts(RTOL=1e-7)
+    ll_w, st_w, ns_w, cur_w = make_backend_flags(ctx, SEULEX_WARP)(prob, params, aux, opts, True)
+    ll_c, st_c, ns_c, cur_c = make_backend_flags(ctx, SEULEX_CTA)(prob, params, aux, opts, True)
+    np.testing.assert_array_equal(ns_c, ns_w)
+    np.testing.assert_array_equal(cur_c, cur_w)
+    np.testing.assert_array_equal(ll_c, ll_w)
+    np.testing.assert_array_equal(st_c, st_w)
+    ctx.set_queue_order(np.random.default_rng(1).permutation(params.shape[0] * 6))
+    ll_p, _, _, cur_p = make_backend_flags(ctx, SEULEX_CTA)(prob, params, aux, opts, True)
+    ctx.set_queue_order(None)
+    np.testing.assert_array_equal(cur_p, cur_c)
+    np.testing.assert_array_equal(ll_p, ll_c)
+
+
+def test_extrapolation_kernel_known_answers_and_ladder(ctx):
+    print(pc.check_known_answers(make_backend_flags(ctx, SEULEX_CTA)))
+    g, prob, params, aux = pc.staub_problem()
+    ctx.set_problem(prob)
+    ctx.set_ladder(np.array([1.0, 2.0, 8.0, 64.0]))
+    aux1 = _capi.default_aux(params.shape[0], 6, [float(g["sigma"])] * 6, temps=(1.0, 1.0, 1.0))
+    ll, _, _, _ = ctx.loglik_batch(params, aux, _capi.make_opts(RTOL=1e-7, flags=SEULEX_CTA), want_curves=False)
+    ctx.loglik_batch(params, aux1, _capi.make_opts(RTOL=1e-7, flags=SEULEX_CTA | _capi.OPT_LADDER), want_curves=False)
+    lad = ctx.download_ladder(params.shape[0])
+    ok = ll[:, :, 0].sum(axis=1) > pc.LOGLL_FLOOR
+    np.testing.assert_allclose(lad[ok][:, :, :3], ll[ok], rtol=1e-12)

@@ -1,4 +1,5 @@
-"""Latency of small batches: one-warp-per-trajectory kernel against the CTA-per-trajectory kernel.
+"""Latency of small batches: RODAS4 one warp / one CTA per trajectory, and the order-6 extrapolation
+integrator one warp / one CTA per trajectory.
 usage (GPU box): python tools/latency_probe.py [n_sets ...]"""
 import json
 import sys
@@ -18,7 +19,8 @@ ctx.set_problem(prob)
 out = []
 for n in [int(a) for a in sys.argv[1:]] or [1, 8, 32, 64, 128, 256, 1024, 4096]:
     row = {"n_sets": n, "n_traj": n * prob.n_meas}
-    for name, flag in (("warp", 0), ("cta", _capi.OPT_CTA_PER_TRAJ)):
+    for name, flag in (("warp", 0), ("cta", _capi.OPT_CTA_PER_TRAJ), ("seulex_warp", _capi.OPT_EXTRAPOLATION),
+                       ("seulex_cta", _capi.OPT_EXTRAPOLATION | _capi.OPT_CTA_PER_TRAJ)):
         opts = _capi.make_opts(RTOL=1e-7, flags=flag | _capi.OPT_NO_EXPLICIT)
         ms = []
         for rep in range(6):
@@ -29,6 +31,7 @@ for n in [int(a) for a in sys.argv[1:]] or [1, 8, 32, 64, 128, 256, 1024, 4096]:
         row[name + "_ms"] = float(np.median(ms[1:]))
         row[name + "_steps_max"] = int(ns.sum(axis=-1).max())
         row[name + "_steps_mean"] = float(ns.sum(axis=-1).mean())
-    row["speedup"] = row["warp_ms"] / row["cta_ms"]
+    row["speedup_cta"] = row["warp_ms"] / row["cta_ms"]
+    row["speedup_seulex_cta"] = row["warp_ms"] / row["seulex_cta_ms"]
     out.append(row)
     print(json.dumps(row), flush=True)

@@ -27,7 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=31)
     ap.add_argument("--chains", type=int, default=256)
-    ap.add_argument("--kernel", default="auto", choices=["auto", "warp", "cta"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "warp", "cta", "seulex"])
     args = ap.parse_args()
     comm = Comm()
     ini, t = bench.workload_inputs()
