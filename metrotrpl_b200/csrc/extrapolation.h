@@ -293,7 +293,8 @@ TRPL_FN void run_trajectory_seulex(const TrajIn& in, const SolverOpts& opt, Traj
       if (log_point(in, want_ll, em, nh, t, val, dval)) break;
       if (t >= tend || val < min_y) break;
       h = (n_acc == 0) ? seulex_first_step<NPL, MODEL>(opt, m, u, f0, aux, tend) : h_new;
-      h_cap = (dval != 0.0) ? TRPL_SEULEX_EFOLDS * fabs(val / dval) : tend;
+      // (no cap once the signal is below the controlled dynamic range: nothing is claimed there)
+      h_cap = (dval != 0.0 && val > val_floor) ? TRPL_SEULEX_EFOLDS * fabs(val / dval) : tend;
     }
     for (;;) {
       if (n_acc + n_rej >= opt.max_steps) { status |= ST_MAX_STEPS; done = true; break; }
@@ -418,7 +419,8 @@ __device__ __forceinline__ void run_trajectory_seulex_cta(const TrajIn& in, cons
       ++nh;
       if (t >= tend || val < min_y) break;
       h = (n_acc == 0) ? seulex_first_step<NPL, MODEL>(opt, m, u, f0, aux, tend) : h_new;
-      h_cap = (dval != 0.0) ? TRPL_SEULEX_EFOLDS * fabs(val / dval) : tend;
+      // (no cap once the signal is below the controlled dynamic range: nothing is claimed there)
+      h_cap = (dval != 0.0 && val > val_floor) ? TRPL_SEULEX_EFOLDS * fabs(val / dval) : tend;
     }
     for (;;) {
       if (n_acc + n_rej >= opt.max_steps) { status |= ST_MAX_STEPS; done = true; break; }
