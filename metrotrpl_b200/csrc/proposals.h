@@ -40,6 +40,15 @@ inline int make_trial_moves(int n_chains, int n_par, const double* cur, const do
   int64_t draws = 0;
   int ambi_used = 0;
   double cand[32];
+  // The reference tests lo < 10^x < hi in linear units.  pow() is the most expensive thing in this
+  // loop (hot chains need tens of attempts), so the test is made in log space first and pow() only
+  // decides candidates within 1e-9 decades of a bound (its own error is 4e-17 decades).
+  double loglo[32], loghi[32];
+  for (int i = 0; i < n_par; ++i) {
+    loglo[i] = lo[i] > 0 ? log10(lo[i]) : -HUGE_VAL;
+    loghi[i] = hi[i] > 0 ? log10(hi[i]) : -HUGE_VAL;
+  }
+  const double LOG_MARGIN = 1e-9;
   const int tries = hard_bounds ? max_tries : 1;
   for (int m = 0; m < n_chains; ++m) {
     const double* logcur = cur + (size_t)m * n_par;       // already log-scaled where do_log
@@ -65,6 +74,11 @@ inline int make_trial_moves(int n_chains, int n_par, const double* cur, const do
       uint32_t mask = 0;
       for (int i = 0; i < n_par; ++i) {
         if (!active[i]) continue;
+        if (do_log[i]) {
+          const double x = cand[i];
+          if (x > loglo[i] + LOG_MARGIN && x < loghi[i] - LOG_MARGIN) continue;                    // inside
+          if (x < loglo[i] - LOG_MARGIN || x > loghi[i] + LOG_MARGIN) { mask |= (1u << i); continue; }  // outside
+        }
         const double lin = do_log[i] ? pow(10.0, cand[i]) : cand[i];
         if (!(lo[i] < lin && lin < hi[i])) mask |= (1u << i);
       }

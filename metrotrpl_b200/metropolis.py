@@ -82,7 +82,10 @@ class CudaEvaluator:
         self.kernel = ("seulex" if self.flags & _capi.OPT_EXTRAPOLATION else
                        "cta" if self.flags & _capi.OPT_CTA_PER_TRAJ else "warp")
         self._cost = None       # integrator steps of the previous call's trajectories
-        self.n_failed = 0       # trajectories of the last call with an integrator failure flag
+        # trajectories this GPU holds at once (148 SMs x 2 CTAs x 4 warps, or x 1 per CTA): a batch
+        # that fits starts all at once and the queue order (and the step counts it needs) is moot
+        sm = self.cache.ctx.device_info()["sm_count"] if hasattr(self.cache.ctx, "device_info") else 148
+        self._resident = sm * 2 * (1 if self.flags & _capi.OPT_CTA_PER_TRAJ else 4)
 
     def launch(self, states, sigmas):
         """Upload and launch; nothing is waited for.  Returns the number of parameter sets."""
@@ -98,10 +101,12 @@ class CudaEvaluator:
             ctx._ladder_key = self.ladder.tobytes()
         # Longest first: a chain's proposal costs about what its previous proposal cost, and an
         # iteration is only as fast as its last trajectory.  The order never changes a result.
-        if self._cost is not None and self._cost.size == n * self.cache.n_meas:
+        self._ordered = n * self.cache.n_meas > self._resident
+        if self._ordered and self._cost is not None and self._cost.size == n * self.cache.n_meas:
             ctx.set_queue_order(np.argsort(-self._cost, kind="stable"))
-        else:
+        elif self._ordered or self._cost is not None:
             ctx.set_queue_order(None)
+            self._cost = None
         ctx.upload(params, aux)
         ctx.run_resident(opts)
         return n
@@ -110,8 +115,9 @@ class CudaEvaluator:
         """states [n, n_params], sigmas: list of {meas_type: sigma}.  Returns [n, n_T] on the host
         (one stream synchronisation)."""
         n = self.launch(states, sigmas)
-        rows, nsteps = self.cache.ctx.download_ladder_sums(n)
-        self._cost = nsteps.sum(axis=-1).ravel()
+        rows, nsteps = self.cache.ctx.download_ladder_sums(n, want_nsteps=self._ordered)
+        if self._ordered:
+            self._cost = nsteps.sum(axis=-1).ravel()
         return rows
 
     def device_rows(self, states, sigmas):
@@ -119,7 +125,8 @@ class CudaEvaluator:
         order) are fetched too."""
         n = self.launch(states, sigmas)
         ptr, n_sets, n_t = self.cache.ctx.ladder_sums_resident()
-        self._cost = self.cache.ctx.download_nsteps(n).sum(axis=-1).ravel()
+        if self._ordered:
+            self._cost = self.cache.ctx.download_nsteps(n).sum(axis=-1).ravel()
         return ptr, n_sets, n_t
 
 
