@@ -166,14 +166,22 @@ def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, sha
     elif cur_ladder is None:
         cur_ladder = sharded_eval(evaluator, comm,
                                   np.ascontiguousarray(states[:, :, starting_iter - 1]), sigmas)
+    prof = {"proposals": 0.0, "evaluate": 0.0, "accept": 0.0, "swaps": 0.0} if os.environ.get("TRPL_PT_PROFILE") else None
     for k in range(starting_iter, num_iters):
+        t_a = perf_counter()
         if k % MSG_FREQ == 0 or k < starting_iter + MSG_COOLDOWN:
             for m in range(n_chains):
                 logger.info(f"Iter {k} MetroState #{m} Current state: {states[m, :, k-1]} logll {logll[m, k-1]}")
         # proposals and acceptance draws in the reference's generator order
         moves = np.sqrt(T)[:, None] * shared_fields["base_trial_move"][None, :]
-        proposals, u = make_trial_moves(states[:, :, k - 1], moves, shared_fields, RNG, logger)
+        # The reference warns for every failed proposal attempt; with hundreds of hot chains that is
+        # thousands of lines per iteration.  A one-line summary is written on the iterations whose
+        # states are logged anyway (every MSG_FREQ-th and the first few).
+        verbose_iter = k % MSG_FREQ == 0 or k < starting_iter + MSG_COOLDOWN
+        proposals, u = make_trial_moves(states[:, :, k - 1], moves, shared_fields, RNG, logger if verbose_iter else None)
+        t_b = perf_counter()
         new_ladder = sharded_eval(evaluator, comm, proposals, sigmas)
+        t_c = perf_counter()
         new_ll = new_ladder[own, own]
         n_bad = int(np.count_nonzero(np.isneginf(new_ll)))
         if n_bad:
@@ -189,6 +197,7 @@ def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, sha
         states[:, :, k] = np.where(accepted[:, None], proposals, states[:, :, k - 1])
         accept[accepted, k] = 1
         cur_ladder[accepted] = new_ladder[accepted]
+        t_d = perf_counter()
         if shared_fields["do_parallel_tempering"] and k % shared_fields["temper_freq"] == 0:
             for _ in range(n_chains - 1):
                 i = RNG.integers(0, n_chains - 1)
@@ -214,6 +223,14 @@ def main_metro_loop_batched(states, logll, accept, starting_iter, num_iters, sha
                         states[i, :, k] = states[i + 1, :, k]
                         states[i + 1, :, k] = tmp
                         cur_ladder[[i, i + 1]] = cur_ladder[[i + 1, i]]
+        if prof is not None:
+            t_e = perf_counter()
+            prof["proposals"] += t_b - t_a; prof["evaluate"] += t_c - t_b
+            prof["accept"] += t_d - t_c; prof["swaps"] += t_e - t_d
+    if prof is not None and num_iters > starting_iter:
+        n_it = num_iters - starting_iter
+        logger.info("host profile, ms per iteration: " + ", ".join(f"{k_} {1e3 * v / n_it:.3f}" for k_, v in prof.items()))
+        print("[trpl] host profile, ms per iteration (rank %d): " % comm.rank + ", ".join(f"{k_} {1e3 * v / n_it:.3f}" for k_, v in prof.items()), flush=True)
     return states, logll, accept, swap_attempts, swap_accept, cur_ladder
 
 
