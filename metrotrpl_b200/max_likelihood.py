@@ -103,11 +103,13 @@ def nelder_mead_batched(fun_batch, x0, xatol=1e-4, fatol=1e-4, maxiter=None, max
 
 
 def mle(e_data, sim_params, param_info, init_params, sim_flags, export_path, logger, evaluator=None,
-        irf_dir="IRFs", device=None):
+        irf_dir="IRFs", device=None, kernel="warp"):
     """Same call and result as max_likelihood.py:113-160: the Ensemble whose single chain holds the
     visited states (column k = k-th accepted best vertex) and their log-likelihoods.
 
     evaluator(states[n, n_params]) -> logll[n] may be injected (tests); by default the CUDA path.
+    kernel="seulex": the low-latency integrator (PathCache) - a simplex iteration is a handful of
+    trajectories, i.e. pure latency.
     """
     names = list(param_info["names"])
     sigma = sim_flags.get("current_sigma", None) or sim_flags.get("model_uncertainty", None)
@@ -130,7 +132,7 @@ def mle(e_data, sim_params, param_info, init_params, sim_flags, export_path, log
     base = MS_list.H.states[0, :, 0].copy()
     if evaluator is None:
         from .trial_move_evaluation import PathCache, eval_trial_moves
-        cache = PathCache(ef, device=device)
+        cache = PathCache(ef, device=device, kernel=kernel)
 
         def evaluator(states):
             return eval_trial_moves(states, np.ones(len(states)), sigma, ef, cache=cache).logll

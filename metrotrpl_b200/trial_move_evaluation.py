@@ -37,9 +37,13 @@ class BatchLikelihood:
 class PathCache:
     """Packs shared_fields once and keeps the problem resident on the device."""
 
-    def __init__(self, shared_fields, device=None, ctx=None):
+    def __init__(self, shared_fields, device=None, ctx=None, kernel="warp"):
         """ctx: a private _capi.Context (own stream and device buffers) instead of the process-wide
-        one of `device`; two caches on two contexts let consecutive launches overlap."""
+        one of `device`; two caches on two contexts let consecutive launches overlap.
+        kernel: "warp" (RODAS4, one trajectory per warp: throughput) or "seulex" (order-6
+        extrapolation, one trajectory per CTA, csrc/extrapolation.h: half the latency for batches of
+        a few hundred trajectories - single states, Nelder-Mead simplices, tempering ladders; 'std'
+        model with nx = 128 only)."""
         sf = shared_fields
         if any(m == "pa" for m in sf["_sim_info"]["meas_types"]):
             raise NotImplementedError("'pa' toy measurements are not simulations; not on the CUDA path")
@@ -79,6 +83,12 @@ class PathCache:
         self.a_idx = group_index(sf.get("fittable_absps", None), "_a")
         self.s_idx = group_index(sf.get("scale_factor", None), "_s")
         self.flags = _capi.OPT_FORCE_MIN_Y if sf.get("force_min_y", False) else 0
+        if kernel == "seulex":
+            if sf.get("model", "std") != "std" or any(int(nx) != 128 for nx in sf["_sim_info"]["nx"]):
+                raise ValueError("kernel='seulex' needs the 'std' model with nx = 128 on every measurement")
+            self.flags |= _capi.OPT_EXTRAPOLATION | _capi.OPT_CTA_PER_TRAJ
+        elif kernel != "warp":
+            raise ValueError(f"unknown kernel {kernel!r}")
 
     def opts(self, honor_hmax=False):
         sf = self.sf

@@ -208,3 +208,26 @@ def test_metro_on_gpu_equals_the_reference_golden_chains(tag):
     rng = np.random.default_rng(0)
     rng.bit_generator.state = ms.random_state
     assert gc.pcg_words(rng) == [int(x) for x in G[f"{tag}_final_rng"]]
+
+
+def test_single_states_through_the_low_latency_kernel():
+    """PathCache(kernel="seulex"): eval_trial_moves / eval_trial_move on one and a few states through
+    the extrapolation integrator equal the default kernel's to integration accuracy."""
+    import bench
+    from metrotrpl_b200.trial_move_evaluation import PathCache, eval_trial_moves
+    from tests import parity_cases as pc
+    g, prob, params, aux = pc.staub_problem()
+    t = g["t"]
+    sf = bench.make_shared_fields(g["ini"], t, list(g["vals"]), list(g["uncs"]))
+    states = g["states"][[0, 1, 3, 5, 15]]
+    a = eval_trial_moves(states, np.ones(5), {"TRPL": 1.0}, sf, cache=PathCache(sf), want_curves=True)
+    b = eval_trial_moves(states, np.ones(5), {"TRPL": 1.0}, sf, cache=PathCache(sf, kernel="seulex"), want_curves=True)
+    np.testing.assert_allclose(b.logll, a.logll, rtol=1e-6)
+    np.testing.assert_allclose(b.curves, a.curves, rtol=1e-5)
+    assert b.nsteps[..., 0].mean() < 0.5 * a.nsteps[..., 0].mean()
+    one, funcs = eval_trial_move(states[0], {"model_uncertainty": {"TRPL": 1.0}, "_T": 1.0}, sf,
+                                 cache=PathCache(sf, kernel="seulex"))
+    assert abs(one / a.logll[0] - 1) < 1e-6 and abs(sum(f(1.0) for f in funcs) - one) < 1e-9 * abs(one)
+    with pytest.raises(ValueError, match="nx = 128"):
+        sim = dict(sf["_sim_info"], nx=[64] * 6)
+        PathCache(dict(sf, _sim_info=sim, _init_params=[np.ones(64)] * 6), kernel="seulex")
