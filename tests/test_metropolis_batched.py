@@ -328,3 +328,44 @@ def test_approve_move_reference_cases_python_and_native():
     sf = _approve_fields([1, 1, 1], [0, 0, 1])
     assert approve_move(np.log10([0.11, 0.1, 1]), sf) == []
     assert _native_failed_names(np.log10([0.11, 0.1, 1]), sf) == []
+
+
+def _dense_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from metrotrpl_b200 import dense_sampling as ds
+    from metrotrpl_b200.parallel import Comm
+    comm = Comm(backend="gloo")
+    sim_info, ini, e_data, MCMC, param_info = small_problem(tempfile.mkdtemp())
+    param_info["prior_dist"]["tauN"] = (100, 1000)
+    param_info["prior_dist"]["p0"] = (1e15, 1e16)
+    for n in NAMES:
+        if n not in ("tauN", "p0"):
+            param_info["active"][n] = 0
+    flags = {"num_iters": 9, "log_y": 1, "likel2move_ratio": {"TRPL": 1.0}, "model": "std",
+             "ini_mode": "density", "rtol": 1e-6}
+    np.random.seed(100 + rank)           # every rank's global generator is in a DIFFERENT state
+    N, P, X = ds.bayes(np.array([0]), None, ini, sim_info, e_data, flags, param_info,
+                       evaluator=lambda s: -np.log10(s[:, 9]) + np.log10(s[:, 1]), comm=comm)
+    q.put((rank, P, X))
+    comm.barrier()
+
+
+def test_dense_grid_is_rank_zeros_on_every_rank_gloo():
+    """bayes() draws its grid from the unseeded global np.random (as the reference does, which never
+    shards): rank 0's grid is broadcast, so the gathered likelihoods belong to the X every rank returns."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29100 + (os.getpid() % 500)
+    procs = [ctx.Process(target=_dense_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=600) for _ in range(2)), key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+    (_, P0, X0), (_, P1, X1) = got
+    np.testing.assert_array_equal(X0, X1)
+    np.testing.assert_array_equal(P0, P1)
+    np.testing.assert_allclose(P0, -np.log10(X0[:, 9]) + np.log10(X0[:, 1]))
