@@ -316,12 +316,15 @@ def run_ours(args):
     k_ms = float(np.mean(kernel_ms))
     achieved = flops / (k_ms * 1e-3) / 1e12
     alg_bytes = h2d + d2h + ini.nbytes + 3 * 6 * len(t) * 8
-    traffic = None
+    # DRAM traffic per launch cannot be measured without a profiler: it is the committed figure of
+    # the last `ncu --set full` capture of this launch size, and says so (traffic_source)
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_dram_traffic.json")
     if os.path.exists(tpath) and args.sets == 4096:
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic, traffic_source = tj.get("dram_bytes_per_launch"), "committed ncu figure, not measured in this run: " + tj.get("source", tpath)
     roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved / peak_tf, "traffic": traffic,
+            "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_source,
             "peak_source": "in-run DFMA probe (trpl_fp64_peak_probe); B200 nominal FP64 = 37 TFLOP/s; "
                            "MEASURED_PEAKS.json has no FP64 entry",
             "kernel": "trpl_forward_kernel<4,std>", "kernel_ms": k_ms,
