@@ -336,3 +336,38 @@ def test_extrapolation_kernel_known_answers_and_ladder(ctx):
     lad = ctx.download_ladder(params.shape[0])
     ok = ll[:, :, 0].sum(axis=1) > pc.LOGLL_FLOOR
     np.testing.assert_allclose(lad[ok][:, :, :3], ll[ok], rtol=1e-12)
+
+
+def test_two_integrators_agree_at_full_size(ctx):
+    """BASELINE configs[1] size: 4096 random parameter sets of the whole prior box x 6 curves through
+    RODAS4 (one warp per trajectory) and through the order-6 extrapolation integrator (one CTA per
+    trajectory) - two unrelated time integrators on the same right-hand side.  Every point of every
+    curve within twelve decades of its start agrees to 1e-4 (the north star's curve tolerance;
+    measured 4e-5), every log-likelihood above -1e4 of a set that stays in range to 2e-6, and the extrapolation integrator needs
+    less than half the steps."""
+    import bench
+    g, prob, _, _ = pc.staub_problem()
+    n = 4096
+    params = _capi.pack_params(bench.draw_states(n, seed=20261018), bench.IDX, bench.UNITS)
+    aux = _capi.default_aux(n, 6, [1.0] * 6)
+    ctx.set_problem(prob)
+    ll_r, st_r, ns_r, cur_r = ctx.loglik_batch(params, aux, _capi.make_opts(RTOL=1e-7), want_curves=True)
+    ll_x, st_x, ns_x, cur_x = ctx.loglik_batch(params, aux, _capi.make_opts(RTOL=1e-7, flags=SEULEX_CTA), want_curves=True)
+    nt = len(g["t"])
+    R, X = cur_r.reshape(n, 6, nt), cur_x.reshape(n, 6, nt)
+    in_range = R >= 1e-12 * R[:, :, :1]
+    with np.errstate(all="ignore"):
+        e = np.where(in_range, np.abs(X / R - 1), 0.0)
+    print("max curve difference", e.max(), "mean steps", ns_r[..., 0].mean(), ns_x[..., 0].mean())
+    assert e.max() <= 1e-4
+    # log-likelihoods: the sets whose six curves stay inside the controlled range over the whole
+    # window (beyond twelve decades neither integrator - nor the reference - claims anything, and
+    # where a curve meets the DBL_MIN floor there is arbitrary: one floored point costs 1e5)
+    tot_r, tot_x = ll_r[:, :, 0].sum(axis=1), ll_x[:, :, 0].sum(axis=1)
+    ok = (tot_r > pc.LOGLL_FLOOR) & in_range.all(axis=(1, 2))
+    assert ok.sum() > 100
+    rel = np.abs(tot_x[ok] / tot_r[ok] - 1)
+    print("states above the floor", int(ok.sum()), "max logll difference", rel.max())
+    assert rel.max() <= 2e-6
+    assert np.all((st_x & 7) == 0) and np.all((st_r & 7) == 0)
+    assert ns_x[..., 0].mean() < 0.5 * ns_r[..., 0].mean()
