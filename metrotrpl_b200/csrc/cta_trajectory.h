@@ -1,6 +1,11 @@
-// cta_trajectory.h - one (parameter set, measurement) trajectory per CTA: the low-latency
-// instantiation of the integrator for small batches (parallel tempering: a few hundred
-// trajectories per GPU per iteration, where an iteration is as slow as its slowest trajectory).
+// cta_trajectory.h - RODAS4 with one (parameter set, measurement) trajectory per CTA: the north
+// star's mapping taken literally, built in round 2 to find out whether more threads per trajectory
+// shorten a tempering iteration (which is as slow as its slowest trajectory).  MEASURED ANSWER: no.
+// 6.5 us per integrator step against the one-warp kernel's 6.8, at 0.3x its throughput (DESIGN.md
+// section 5, tools/latency_probe.py): a RODAS4 step is a chain of ~50 dependent exchange-and-reduce
+// levels however it is decomposed.  The latency path that does work is extrapolation.h (parallelism
+// inside the method).  This kernel stays behind TRPL_OPT_CTA_PER_TRAJ, parity-tested against the
+// same converged truth, and nothing selects it by default.
 //
 // Same method as trajectory.h - RODAS4, exact Jacobian, the same controller, error norm, step log,
 // dense output and likelihood code - but one space node per THREAD (nx = 128 threads, four warps):
@@ -18,10 +23,8 @@
 //     same bits and control flow stays CTA-uniform without broadcasts);
 //   * emission / likelihood: warp 0 alone runs the step log, emit_history and finalize_trajectory of
 //     trajectory.h (they are one-warp routines); the other three warps wait at the next barrier.
-// The dependent chain of a step is ~6 x (1 exchange + 7 levels) short operations instead of the
-// one-warp kernel's per-lane sweeps over four nodes, which is what cuts the latency; the price is
-// ~60 bar.sync per step and a 7-level reduction, so throughput per SM is lower: launch() picks
-// this kernel only when TRPL_OPT_CTA_PER_TRAJ is set (metropolis.py sets it for tempering runs).
+// It trades the one-warp kernel's in-lane sweeps (no synchronisation, four FP64 chains in flight) for
+// two more exchange levels per solve and ~60 bar.sync per step.
 // Restrictions of this instantiation: 'std' model, nx = 128 for every measurement.
 #pragma once
 #include "trajectory.h"

@@ -398,7 +398,7 @@ def check_edges(backend):
     return True
 
 
-def check_traps_irf(backend):
+def check_traps_irf(backend, curve_tol=CURVE_TOL_CLEAN):
     """BASELINE configs[3]: trap-assisted model + IRF convolution (IRFs/irf_520nm.csv), nx=256,
     fluence-mode initial condition, stiff capture.  Curves against the reference at tight
     tolerances; likelihood (resample -> convolve -> max-shift -> trim -> log residuals) against the
@@ -420,7 +420,7 @@ def check_traps_irf(backend):
     rep = {}
     e_t = np.abs(cur / g["pl_tight"] - 1).max()
     rep["curve_err_vs_tight"] = float(e_t)
-    assert e_t <= CURVE_TOL_CLEAN, e_t
+    assert e_t <= curve_tol, e_t
     # the reference at its default tolerances is itself off by up to 1.5e-3 on the stiff states
     ref_ok = np.abs(g["pl_default"] / g["pl_tight"] - 1) <= 5e-5
     e_d = np.where(ref_ok, np.abs(cur / g["pl_default"] - 1), 0).max()

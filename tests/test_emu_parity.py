@@ -63,3 +63,23 @@ def test_extrapolation_integrator_against_the_converged_truth():
         rep = check(seulex, rtol=1e-7, tight_rtol=1e-9, curve_tol=3e-5, truth_backend=backend)
         print({k: v for k, v in rep.items() if not k.startswith("logll_rows")})
         assert rep["mean_steps"] < 200
+
+
+def _seulex_backend(prob, params, aux, opts, want_curves):
+    from metrotrpl_b200 import _capi
+    o = _capi.SolverOpts(opts.rtol, opts.atol, opts.hmax, opts.max_steps, opts.flags | _capi.OPT_EXTRAPOLATION)
+    return emu.loglik_batch(prob, params, aux, o, want_curves)
+
+
+def test_extrapolation_integrator_closed_forms_and_ragged_inputs():
+    """The one-warp driver of the extrapolation integrator is generic in nodes per lane and model:
+    closed forms (nx = 100), ragged curve lengths, fluence mode both ways, nx = 16 / 200 with padding,
+    the traps model at nx = 100, the reference's known answers and unit-test parameter sets."""
+    print(pc.check_analytic(_seulex_backend))
+    assert pc.check_edges(_seulex_backend)
+    print(pc.check_known_answers(_seulex_backend))
+    print(pc.check_reference_unit_cases(_seulex_backend))
+
+
+def test_extrapolation_integrator_traps_model_with_irf_convolution_nx256():
+    print(pc.check_traps_irf(_seulex_backend, curve_tol=5e-6))     # measured 1.1e-6 (RODAS4: 3e-7)
