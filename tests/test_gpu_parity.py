@@ -371,3 +371,21 @@ def test_two_integrators_agree_at_full_size(ctx):
     assert rel.max() <= 2e-6
     assert np.all((st_x & 7) == 0) and np.all((st_r & 7) == 0)
     assert ns_x[..., 0].mean() < 0.5 * ns_r[..., 0].mean()
+
+
+@pytest.mark.parametrize("flags", [_capi.OPT_CTA_PER_TRAJ, SEULEX_CTA, SEULEX_WARP, 0])
+def test_step_log_flush_with_more_than_1024_steps(ctx, flags):
+    """A step cap of 1 ns forces ~2000 steps per curve: the 1024-entry step log is flushed mid-run
+    (in the one-CTA kernels by warp 0, with the result broadcast to the other warps).  Same curves as
+    the uncapped run."""
+    g, prob, params, aux = pc.staub_problem()
+    sel = [0, 3, 7]
+    free = make_backend_flags(ctx, flags)(prob, params[sel], aux[sel], _capi.make_opts(RTOL=1e-7), True)
+    capped = make_backend_flags(ctx, flags)(prob, params[sel], aux[sel],
+                                            _capi.make_opts(RTOL=1e-7, hmax=1.0, honor_hmax=True), True)
+    assert capped[2][..., 0].min() >= 1999 and free[2][..., 0].max() < 1024
+    T = free[3]
+    in_range = T >= 1e-12 * T.max()
+    np.testing.assert_allclose(np.where(in_range, capped[3], 1.0), np.where(in_range, T, 1.0), rtol=3e-5)
+    ok = free[0][:, :, 0].sum(axis=1) > pc.LOGLL_FLOOR
+    np.testing.assert_allclose(capped[0][ok], free[0][ok], rtol=2e-6)
