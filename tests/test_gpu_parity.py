@@ -383,7 +383,7 @@ def test_step_log_flush_with_more_than_1024_steps(ctx, flags):
     free = make_backend_flags(ctx, flags)(prob, params[sel], aux[sel], _capi.make_opts(RTOL=1e-7), True)
     capped = make_backend_flags(ctx, flags)(prob, params[sel], aux[sel],
                                             _capi.make_opts(RTOL=1e-7, hmax=1.0, honor_hmax=True), True)
-    assert capped[2][..., 0].min() >= 1999 and free[2][..., 0].max() < 1024
+    assert capped[2][..., 0].min() > 1500 and free[2][..., 0].max() < 1024
     T = free[3]
     in_range = T >= 1e-12 * T.max()
     np.testing.assert_allclose(np.where(in_range, capped[3], 1.0), np.where(in_range, T, 1.0), rtol=3e-5)
