@@ -146,3 +146,45 @@ def test_tempering_chains_equal_the_reference_serial_path(tag):
         ref_k0 = G[f"{tag}_states"][:, :, k0]
         np.testing.assert_allclose(ms2.H.states[i0, :, k0], ref_k0[i0], rtol=STATE_RTOL)   # lower chain: the upper chain's state
         assert not np.allclose(ms2.H.states[i0 + 1, :, k0], ref_k0[i0 + 1], rtol=1e-6)     # upper chain: the lower one's, not its own
+
+
+# ---- configs[0]: one chain on the reference's real measurement ---------------------------------
+def real_chain_problem(tmp):
+    from tests import parity_cases as pc
+    import bench
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "staub_real3.npz"))
+    n_t = g["n_t"]
+    e_data = ([g["t"][m, :n_t[m]] for m in range(3)], [g["vals"][m, :n_t[m]] for m in range(3)],
+              [g["uncs"][m, :n_t[m]] for m in range(3)])
+    names = list(bench.NAMES)
+    sim_info = {"lengths": [311.0] * 3, "nx": [128] * 3, "meas_types": ["TRPL"] * 3, "num_meas": 3}
+    active = {n: int(n not in ("n0", "eps", "Tm", "m")) for n in names}
+    param_info = {"names": names, "active": active, "unit_conversions": dict(zip(names, bench.UNITS)),
+                  "do_log": {n: 1 for n in names},
+                  "prior_dist": {n: ((lo, hi) if active[n] else (0, np.inf)) for n, lo, hi in zip(names, bench.LO, bench.HI)},
+                  "init_guess": dict(zip(names, bench.GUESS)), "trial_move": {n: 0.1 for n in names}}
+    param_info["prior_dist"]["m"] = (-np.inf, np.inf)
+    MCMC = {"init_cond_path": "real_staub_input.csv", "measurement_path": "real_staub_aug_corr_renoised.csv",
+            "output_path": tmp, "num_iters": 16, "solver": ("solveivp",), "model": "std", "ini_mode": "density",
+            "log_y": 1, "checkpoint_freq": 16, "hard_bounds": 1, "rtol": None, "atol": None,
+            "model_uncertainty": {"TRPL": 1.0}}
+    return sim_info, g["ini"].copy(), e_data, MCMC, param_info
+
+
+def check_real_chain(ms):
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "chain_real.npz"))
+    np.testing.assert_array_equal(ms.H.accept, G["accept"])                       # every decision
+    np.testing.assert_allclose(ms.H.states, G["states"], rtol=STATE_RTOL, atol=0)
+    # the reference runs LSODA at its default tolerances: its own likelihoods are good to ~1e-4 here
+    np.testing.assert_allclose(ms.H.loglikelihood, G["logll"], rtol=2e-3, atol=2e-3)
+
+
+def test_single_chain_on_the_real_staub_data_equals_the_reference():
+    """configs[0]: Inputs/mcmc0.txt's parameter set on the reference's real measurement (three curves,
+    nx = 128), one chain, against the chain the unmodified reference's metro(serial_fallback=True)
+    walks (tools/make_golden.py gen_chain_real)."""
+    with tempfile.TemporaryDirectory() as tmp:
+        sim_info, ini, e_data, MCMC, param_info = real_chain_problem(tmp)
+        ms = metro(sim_info, ini, e_data, MCMC, param_info, export_path="out.pik", evaluator_factory=emu_factory,
+                   install_signal_handlers=False)
+    check_real_chain(ms)

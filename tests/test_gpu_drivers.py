@@ -231,3 +231,14 @@ def test_single_states_through_the_low_latency_kernel():
     with pytest.raises(ValueError, match="nx = 128"):
         sim = dict(sf["_sim_info"], nx=[64] * 6)
         PathCache(dict(sf, _sim_info=sim, _init_params=[np.ones(64)] * 6), kernel="seulex")
+
+
+@pytest.mark.parametrize("kernel", ["auto", "seulex"])
+def test_single_chain_on_the_real_staub_data_on_gpu(kernel):
+    """configs[0] through the CUDA evaluator (both integrators) against the reference's golden chain."""
+    from tests import test_golden_chains as gc
+    with tempfile.TemporaryDirectory() as tmp:
+        sim_info, ini, e_data, MCMC, param_info = gc.real_chain_problem(tmp)
+        ms = metro(sim_info, ini, e_data, MCMC, param_info, export_path="out.pik", install_signal_handlers=False,
+                   kernel=kernel)
+    gc.check_real_chain(ms)

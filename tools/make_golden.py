@@ -419,8 +419,44 @@ def gen_chains():
     np.savez_compressed(os.path.join(OUT, "chains.npz"), **out)
 
 
+def gen_chain_real():
+    """configs[0]: a single chain of the reference's metro(serial_fallback=True) on the REAL staub
+    measurement (tests/golden/staub_real3.npz: Inputs/real_staub_input.csv against
+    Inputs/real_staub_aug_corr_renoised.csv, nx = 128, three curves) with Inputs/mcmc0.txt's parameter
+    names, unit conversions, log-scale and activity flags, priors and initial guess; box half-width
+    0.1 decades, model uncertainty 1, hard bounds, 16 iterations."""
+    import copy
+    import pickle
+    import tempfile
+    import metropolis as ref_metro
+    g = np.load(os.path.join(OUT, "staub_real3.npz"))
+    n_t = g["n_t"]
+    e_data = ([g["t"][m, :n_t[m]] for m in range(3)], [g["vals"][m, :n_t[m]] for m in range(3)],
+              [g["uncs"][m, :n_t[m]] for m in range(3)])
+    sim_info = {"lengths": [311.0] * 3, "nx": [NX] * 3, "meas_types": ["TRPL"] * 3, "num_meas": 3}
+    active = {n: int(n not in ("n0", "eps", "Tm", "m")) for n in NAMES}            # mcmc0.txt "Active"
+    param_info = {"names": list(NAMES), "active": active, "unit_conversions": dict(zip(NAMES, UNITS)),
+                  "do_log": {n: 1 for n in NAMES},
+                  "prior_dist": {n: ((lo, hi) if active[n] else (0, np.inf)) for n, lo, hi in zip(NAMES, LO, HI)},
+                  "init_guess": dict(zip(NAMES, GUESS)), "trial_move": {n: 0.1 for n in NAMES}}
+    param_info["prior_dist"]["m"] = (-np.inf, np.inf)
+    tmp = tempfile.mkdtemp()
+    MCMC = {"init_cond_path": "real_staub_input.csv", "measurement_path": "real_staub_aug_corr_renoised.csv",
+            "output_path": tmp, "num_iters": 16, "solver": ("solveivp",), "model": "std", "ini_mode": "density",
+            "log_y": 1, "checkpoint_freq": 16, "hard_bounds": 1, "rtol": None, "atol": None,
+            "model_uncertainty": {"TRPL": 1.0}}
+    ref_metro.all_signal_handler = lambda f: None
+    ref_metro.metro(copy.deepcopy(sim_info), g["ini"].copy(), e_data, copy.deepcopy(MCMC), copy.deepcopy(param_info),
+                    export_path="gold.pik", serial_fallback=True)
+    with open(os.path.join(tmp, "gold.pik"), "rb") as f:
+        MS = pickle.load(f)
+    print("real-data chain: accepted", int(MS.H.accept.sum()), "of 15; logll", MS.H.loglikelihood[0])
+    np.savez_compressed(os.path.join(OUT, "chain_real.npz"), states=MS.H.states, logll=MS.H.loglikelihood,
+                        accept=MS.H.accept, num_iters=16, trial_move=0.1, sigma=1.0)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["rhs", "irf", "known", "staub", "traps", "real3", "chains"]
+    which = sys.argv[1:] or ["rhs", "irf", "known", "staub", "traps", "real3", "chains", "chain_real"]
     if "rhs" in which:
         gen_rhs_pins()
     if "irf" in which:
@@ -435,3 +471,5 @@ if __name__ == "__main__":
         gen_real3()
     if "chains" in which:
         gen_chains()
+    if "chain_real" in which:
+        gen_chain_real()
