@@ -129,7 +129,7 @@ TRPL_FN V2 sub_mv_upper(const V2& r, const Blk& m, const V2& v) {
 // level by level (PmRun: 4 pairs per level + 2 for the inverse, first TM_PAIRS pairs in `tm`, the
 // rest in `sm`), which takes 88 registers per thread out of the integration loop.
 struct PmRegs {
-  Blk al[5], ga[5];
+  Blk al[LOG2_LANES], ga[LOG2_LANES];
   Blk binv_;
   TRPL_FN void put(int k, const Blk& a, const Blk& g) { al[k] = a; ga[k] = g; }
   TRPL_FN void put_binv(const Blk& b) { binv_ = b; }
@@ -145,7 +145,7 @@ template <class TM, class SM, int TM_BASE, int SM_BASE, int TM_PAIRS>
 struct PmRun {
   TM& tm;
   SM& sm;
-  static constexpr int BINV = 20;        // pair index of the inverse
+  static constexpr int BINV = 4 * LOG2_LANES;        // pair index of the inverse
   TRPL_FN void put(int k, const Blk& a, const Blk& g) {
     real v[8];
     put_blk(v, 0, a); put_blk(v, 2, g);
@@ -239,10 +239,10 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
   }
   // Parallel cyclic reduction on (ra, rb, rc) across the 32 lanes.  Neighbour rows travel through
   // 2 x 6 scratch pairs (double buffered, one warp_sync per level) instead of 24 64-bit shuffles.
-  // No masking at the ends: ra is an exact zero block on lanes < stride and rc on lanes >= 32 -
+  // No masking at the ends: ra is an exact zero block on lanes < stride and rc on lanes >= LANES -
   // stride (they are products with the zero sub/super-diagonal of the first/last row), and
   // out-of-range reads are clamped to the lane's own (finite) row.
-  TRPL_UNROLL for (int k = 0; k < 5; ++k) {
+  TRPL_UNROLL for (int k = 0; k < LOG2_LANES; ++k) {
     const int s = 1 << k;
     const int xb = xch + 6 * (k & 1);
     const Blk bi = blk_inv(rb);
@@ -300,11 +300,11 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch
   // it is needed, so that its latency hides behind the last lane exchanges.
   real f2[2 * (S::RUN2 > 0 ? S::RUN2 : 1)];
   typename PM::Inverse inv;
-  TRPL_UNROLL for (int k = 0; k < 5; ++k) {
+  TRPL_UNROLL for (int k = 0; k < LOG2_LANES; ++k) {
     const int s = 1 << k;
     V2 up, dn;
     typename PM::Level lv = pf.fetch(k);                    // in flight during the lane exchange
-    if (k == 3) {
+    if (k == LOG2_LANES - 2) {
       if constexpr (NI > 0) mem_ld_pairs<S::RUN2>(fm, base + S::RUN1, f2);
       inv = pf.fetch_binv();
     }

@@ -64,7 +64,7 @@ TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t
 
   // ---- 1. resample (laplace.py:68-74) ----
   mask any_nan = mconst(false);
-  for (int j0 = 0; j0 < n_rs; j0 += 32) {
+  for (int j0 = 0; j0 < n_rs; j0 += LANES) {
     const ivec j = iadd(lane, j0);
     const mask take = j < n_rs;
     real x = to_real(j) * half;
@@ -79,11 +79,11 @@ TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t
   // ---- 2. moment convolution (laplace.py:178-222) ----
   real best = splat(-DBL_MAX);
   ivec best_k = isplat(0x7fffffff);
-  for (int k0 = 0; k0 <= nk; k0 += 32) {
+  for (int k0 = 0; k0 <= nk; k0 += LANES) {
     const ivec k = iadd(lane, k0);
     const mask take = k <= nk;
     real acc = splat(0.0);
-    const int m_hi = (k0 + 31 < f.nk) ? k0 + 31 : f.nk;      // lags needed by the largest k of this batch
+    const int m_hi = (k0 + LANES - 1 < f.nk) ? k0 + LANES - 1 : f.nk;      // lags needed by the largest k of this batch
     // c carries ry[2kp+2] of the previous lag (= ry[2kp] of this one shifted): two new loads per lag
     real c = gather(f.ry, imul(k, 2), mand(take, k >= 1), 0.0);
     for (int m = 0; m < m_hi; ++m) {
@@ -118,7 +118,7 @@ TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t
 
   // ---- 4. trim to the convolved span and interpolate back (laplace.py:119-127) ----
   real cnt = splat(0.0);
-  for (int i0 = 0; i0 < n_t; i0 += 32) {
+  for (int i0 = 0; i0 < n_t; i0 += LANES) {
     const ivec i = iadd(lane, i0);
     const mask take = i < n_t;
     const real te = gather(times, i, take, DBL_MAX);
@@ -126,7 +126,7 @@ TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t
   }
   n_c = (int)uni(warp_sum(cnt));                              // times ascend: a prefix
   if (n_c < 1) return false;
-  for (int i0 = 0; i0 < n_c; i0 += 32) {
+  for (int i0 = 0; i0 < n_c; i0 += LANES) {
     const ivec i = iadd(lane, i0);
     const mask take = i < n_c;
     const real x = gather(times, i, take, 0.0);
@@ -167,7 +167,7 @@ TRPL_FN void array_loglik(const double* sol, int n_c, const double* vals, const 
     // utils.py:16-32: raise |sol| to 10**min(vals - shift) from the index np.searchsorted finds on
     // -|sol| (a plain bisection, reproduced step for step)
     real mn = splat(DBL_MAX);
-    for (int k0 = 0; k0 < n_c; k0 += 32) {
+    for (int k0 = 0; k0 < n_c; k0 += LANES) {
       const ivec k = iadd(lane, k0);
       mn = vmin(mn, gather(vals, k, k < n_c, DBL_MAX) - shift);
     }
@@ -180,7 +180,7 @@ TRPL_FN void array_loglik(const double* sol, int n_c, const double* vals, const 
     first_floor = lo;
   }
   real l0 = splat(0.0), l1 = splat(0.0), l2 = splat(0.0), neg = splat(0.0);
-  for (int k0 = 0; k0 < n_c; k0 += 32) {
+  for (int k0 = 0; k0 < n_c; k0 += LANES) {
     const ivec k = iadd(lane, k0);
     const mask take = k < n_c;
     const real y = gather(sol, k, take, 1.0);
@@ -209,7 +209,7 @@ TRPL_FN void array_loglik(const double* sol, int n_c, const double* vals, const 
 TRPL_FN void ladder_loglik(const double* r2, const double* u2, int n_c, double sigma2,
                            const double* temps, int n_T, double* out, bool failed) {
   const ivec lane = lane_id();
-  for (int j0 = 0; j0 < n_T; j0 += 32) {
+  for (int j0 = 0; j0 < n_T; j0 += LANES) {
     const ivec j = iadd(lane, j0);
     const mask take = j < n_T;
     const real s = sigma2 * gather(temps, j, take, 1.0);

@@ -103,7 +103,7 @@ struct NodeMask {
   mask first_lane;       // lane 0 (owns node 0)
 };
 
-// FULL: L == 32*NPL is known at compile time (no padding), so every mask but the two contact
+// FULL: L == LANES*NPL is known at compile time (no padding), so every mask but the two contact
 // lanes folds to a constant and the selects disappear from the unrolled node loops.
 template <int NPL, bool FULL>
 TRPL_FN NodeMask<NPL> make_mask(int L) {
@@ -113,8 +113,8 @@ TRPL_FN NodeMask<NPL> make_mask(int L) {
     if (FULL) {
       m.real_node[j] = mconst(true);
       if (j == NPL - 1) {
-        m.last_node[j] = lane_id() == 31;
-        m.inner_face[j] = lane_id() < 31;
+        m.last_node[j] = lane_id() == LANES - 1;
+        m.inner_face[j] = lane_id() < LANES - 1;
       } else {
         m.last_node[j] = mconst(false);
         m.inner_face[j] = mconst(true);

@@ -14,6 +14,20 @@
 #include <math.h>
 #include <stdint.h>
 
+// TRPL_TEAM: warps that integrate one trajectory together.  1 (default): the one-warp vocabulary
+// described above.  2: a TEAM of two warps is the "wide warp" - 64 lanes, lane_id() 0..63 - and
+// every cross-lane primitive spans both warps: shuffles between neighbours hand the one value that
+// crosses the warp boundary through a shared-memory mailbox, reductions combine the two warps'
+// partials there, warp_sync() is a named barrier of the team's 64 threads.  The integrator source
+// is the same; team_kernels.cu compiles it a second time with this vocabulary for the grids of more
+// than 128 nodes (4 nodes per lane instead of 8: the state fits the register file again).
+#ifndef TRPL_TEAM
+#define TRPL_TEAM 1
+#endif
+#if TRPL_TEAM != 1 && TRPL_TEAM != 2
+#error "TRPL_TEAM must be 1 or 2"
+#endif
+
 #if defined(__CUDACC__) && !defined(TRPL_HOST_EMU)
 // ------------------------------------------------------------------------------------------
 // device
@@ -26,22 +40,85 @@ typedef double real;
 typedef bool mask;
 typedef int ivec;
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int LANES = 32 * TRPL_TEAM;            // lanes of the (wide) warp that owns a trajectory
+constexpr int LOG2_LANES = TRPL_TEAM == 2 ? 6 : 5;
 
-TRPL_FN ivec lane_id() { return (int)(threadIdx.x & 31u); }
+TRPL_FN ivec lane_id() { return (int)(threadIdx.x & (unsigned)(LANES - 1)); }
 TRPL_FN real splat(double x) { return x; }
 TRPL_FN double uni(real x) { return x; }                 // x is known to be warp-uniform
+#if TRPL_TEAM == 1
+typedef unsigned lanebits;                                // one bit per lane (warp_ballot)
 TRPL_FN double lane0(real x) { return __shfl_sync(FULL, x, 0); }
 TRPL_FN real shfl_up(real x, int d) { return __shfl_up_sync(FULL, x, d); }     // from lane-d (own if out of range)
 TRPL_FN real shfl_down(real x, int d) { return __shfl_down_sync(FULL, x, d); } // from lane+d (own if out of range)
 TRPL_FN real shfl_idx(real x, int src) { return __shfl_sync(FULL, x, src); }
+#else
+// ---- two-warp team: every cross-lane primitive is  [write mailbox] -> team barrier -> [read] ----
+// One barrier per primitive, no barrier after the read: a mailbox slot may therefore be written
+// again only after ANOTHER team primitive (whose barrier every reader has reached) has run in
+// between.  Every CALL SITE has a slot of its own (the macros at the end of this file hand out
+// __COUNTER__; team_kernels.cu asserts that there are at most TEAM_SLOTS sites), so only a site
+// that runs twice in a row with no other team primitive in between could collide; the host
+// lock-step build runs the same slot numbers and aborts if two consecutive primitives of a
+// trajectory share one.
+typedef unsigned long long lanebits;
+constexpr int TEAM_SLOTS = 64;
+TRPL_FN double* team_box(int slot) {
+  __shared__ double box[2][TEAM_SLOTS][2];               // [team of the CTA][slot][value]
+  return &box[(threadIdx.x >> 6) & 1][slot][0];
+}
+TRPL_FN void team_bar() { asm volatile("bar.sync %0, 64;" :: "r"(1 + (int)((threadIdx.x >> 6) & 1)) : "memory"); }
+template <int S> TRPL_FN double lane0_s(real x) {
+  volatile double* b = team_box(S);
+  if ((threadIdx.x & 63u) == 0u) b[0] = x;
+  team_bar();
+  return b[0];
+}
+template <int S> TRPL_FN real shfl_idx_s(real x, int src) {
+  volatile double* b = team_box(S);
+  if ((int)(threadIdx.x & 63u) == src) b[0] = x;
+  team_bar();
+  return b[0];
+}
+// neighbour shuffles: distance 1 only (all the integrator uses); lane 31 -> 32 and back through the mailbox
+template <int S> TRPL_FN real shfl_up_s(real x, int) {
+  volatile double* b = team_box(S);
+  real y = __shfl_up_sync(FULL, x, 1);
+  const unsigned tl = threadIdx.x & 63u;
+  if (tl == 31u) b[0] = x;
+  team_bar();
+  if (tl == 32u) y = b[0];
+  return y;
+}
+template <int S> TRPL_FN real shfl_down_s(real x, int) {
+  volatile double* b = team_box(S);
+  real y = __shfl_down_sync(FULL, x, 1);
+  const unsigned tl = threadIdx.x & 63u;
+  if (tl == 32u) b[0] = x;
+  team_bar();
+  if (tl == 31u) y = b[0];
+  return y;
+}
+#endif
 TRPL_FN real sel(mask m, real a, real b) { return m ? a : b; }
 TRPL_FN ivec seli(mask m, ivec a, ivec b) { return m ? a : b; }
 TRPL_FN mask mand(mask a, mask b) { return a && b; }
 TRPL_FN mask mor(mask a, mask b) { return a || b; }
 TRPL_FN mask mnot(mask a) { return !a; }
 TRPL_FN mask mconst(bool b) { return b; }
+#if TRPL_TEAM == 1
 TRPL_FN bool warp_any(mask m) { return __any_sync(FULL, m) != 0; }
-TRPL_FN unsigned warp_ballot(mask m) { return __ballot_sync(FULL, m); }
+TRPL_FN lanebits warp_ballot(mask m) { return __ballot_sync(FULL, m); }
+#else
+template <int S> TRPL_FN lanebits warp_ballot_s(mask m) {
+  volatile double* b = team_box(S);
+  const unsigned mine = __ballot_sync(FULL, m);
+  if ((threadIdx.x & 31u) == 0u) b[(threadIdx.x >> 5) & 1u] = (double)mine;      // exact: < 2^32
+  team_bar();
+  return (lanebits)(unsigned)b[0] | ((lanebits)(unsigned)b[1] << 32);
+}
+template <int S> TRPL_FN bool warp_any_s(mask m) { return warp_ballot_s<S>(m) != 0ull; }
+#endif
 TRPL_FN mask lane_lt(ivec l, int k) { return l < k; }
 TRPL_FN real fmadd(real a, real b, real c) { return fma(a, b, c); }
 // Reciprocal: hardware seed (MUFU.RCP64H, ~2^-23) + two Newton steps, no special-case slow path.
@@ -75,6 +152,7 @@ TRPL_FN real vlog(real x) { return log(x); }
 TRPL_FN real vlog10(real x) { return log10(x); }
 TRPL_FN real vsqrt(real x) { return sqrt(x); }
 TRPL_FN mask is_nan(real x) { return x != x; }
+#if TRPL_TEAM == 1
 TRPL_FN real warp_sum(real x) {
   TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
   return x;  // bit-identical on every lane (fp add is commutative)
@@ -92,6 +170,37 @@ TRPL_FN real warp_scan_incl(real x) {
   }
   return x;
 }
+#else
+// reductions: each warp reduces with shuffles, the two partials meet in the mailbox and both warps
+// add them in the same order (identical bits on all 64 lanes: control flow stays team-uniform)
+template <int S> TRPL_FN real warp_sum_s(real x) {
+  volatile double* b = team_box(S);
+  TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+  if ((threadIdx.x & 31u) == 0u) b[(threadIdx.x >> 5) & 1u] = x;
+  team_bar();
+  return b[0] + b[1];
+}
+template <int S> TRPL_FN real warp_max_s(real x) {
+  volatile double* b = team_box(S);
+  TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
+  if ((threadIdx.x & 31u) == 0u) b[(threadIdx.x >> 5) & 1u] = x;
+  team_bar();
+  return fmax(b[0], b[1]);
+}
+template <int S> TRPL_FN real warp_min_s(real x) { return -warp_max_s<S>(-x); }
+template <int S> TRPL_FN real warp_scan_incl_s(real x) {
+  volatile double* b = team_box(S);
+  const int l = (int)(threadIdx.x & 31u);
+  TRPL_UNROLL for (int o = 1; o < 32; o <<= 1) {
+    real y = __shfl_up_sync(FULL, x, o);
+    if (l >= o) x += y;
+  }
+  if ((threadIdx.x & 63u) == 31u) b[0] = x;               // total of the first warp
+  team_bar();
+  if (threadIdx.x & 32u) x += b[0];
+  return x;
+}
+#endif
 TRPL_FN real gather(const double* p, ivec idx, mask m, double other) { return m ? p[idx] : other; }
 TRPL_FN void scatter(double* p, ivec idx, mask m, real v) { if (m) p[idx] = v; }
 TRPL_FN ivec iadd(ivec a, int b) { return a + b; }
@@ -103,24 +212,30 @@ TRPL_FN ivec ishr1(ivec a) { return a >> 1; }
 TRPL_FN ivec iclamp(ivec a, int lo, int hi) { return a < lo ? lo : (a > hi ? hi : a); }
 TRPL_FN ivec isplat(int a) { return a; }
 TRPL_FN ivec to_int_floor(real x) { return (int)floor(x); }
+#if TRPL_TEAM == 1
 TRPL_FN real warp_min(real x) { return -warp_max(-x); }
+#endif
 TRPL_FN real to_real(ivec a) { return (double)a; }
-TRPL_FN ivec lane_minus(int d) { const int l = (int)(threadIdx.x & 31u); return l >= d ? l - d : l; }   // own lane if out of range
-TRPL_FN ivec lane_plus(int d) { const int l = (int)(threadIdx.x & 31u); return l + d < 32 ? l + d : l; }
+TRPL_FN ivec lane_minus(int d) { const int l = lane_id(); return l >= d ? l - d : l; }   // own lane if out of range
+TRPL_FN ivec lane_plus(int d) { const int l = lane_id(); return l + d < LANES ? l + d : l; }
 
 // Per-warp scratch in shared memory, pair-major: pair p of lane l is the 16-byte word
 // base[p*32 + l].  Every access is one 128-bit LDS/STS per lane, conflict-free across the warp.
 struct LaneMem {
   double2* base;
-  TRPL_FN void ld2(int p, real& a, real& b) const { const double2 v = base[p * 32 + (threadIdx.x & 31u)]; a = v.x; b = v.y; }
-  TRPL_FN void st2(int p, real a, real b) const { base[p * 32 + (threadIdx.x & 31u)] = make_double2(a, b); }
+  TRPL_FN void ld2(int p, real& a, real& b) const { const double2 v = base[p * LANES + lane_id()]; a = v.x; b = v.y; }
+  TRPL_FN void st2(int p, real a, real b) const { base[p * LANES + lane_id()] = make_double2(a, b); }
   // read another lane's pair (lane exchange through shared memory; caller orders with warp_sync)
-  TRPL_FN void ld2_from(int p, ivec src, real& a, real& b) const { const double2 v = base[p * 32 + src]; a = v.x; b = v.y; }
+  TRPL_FN void ld2_from(int p, ivec src, real& a, real& b) const { const double2 v = base[p * LANES + src]; a = v.x; b = v.y; }
   // warp-uniform scalars parked in pair slot p (64 doubles): every lane reads the same word (broadcast)
-  TRPL_FN double uld(int p, int i) const { return reinterpret_cast<const double*>(base + p * 32)[i]; }
-  TRPL_FN void ust(int p, int i, double v) const { reinterpret_cast<double*>(base + p * 32)[i] = v; }
+  TRPL_FN double uld(int p, int i) const { return reinterpret_cast<const double*>(base + p * LANES)[i]; }
+  TRPL_FN void ust(int p, int i, double v) const { reinterpret_cast<double*>(base + p * LANES)[i] = v; }
 };
+#if TRPL_TEAM == 1
 TRPL_FN void warp_sync() { __syncwarp(); }
+#else
+TRPL_FN void warp_sync() { team_bar(); }
+#endif
 
 // Per-warp scratch in TENSOR MEMORY (sm_100a TMEM, 128 lanes x 512 columns x 32 bit per SM), used
 // as lane-private storage: warp w of a CTA owns TMEM lanes 32*(w%4)..+31, thread l of the warp
@@ -208,102 +323,113 @@ template <int N> TRPL_FN void mem_st_pairs(const LaneTm& m, int p, const real* v
 // ------------------------------------------------------------------------------------------
 #include <vector>
 #include <algorithm>
+#include <stdio.h>
+#include <stdlib.h>
 #define TRPL_FN inline
 #define TRPL_UNROLL
 
 namespace simt {
+constexpr int LANES = 32 * TRPL_TEAM;
+constexpr int LOG2_LANES = TRPL_TEAM == 2 ? 6 : 5;
+typedef unsigned long long lanebits;
 struct real {
-  double v[32];
+  double v[LANES];
   real() {}
-  real(double x) { for (int i = 0; i < 32; ++i) v[i] = x; }
+  real(double x) { for (int i = 0; i < LANES; ++i) v[i] = x; }
 };
-struct mask { bool v[32]; };
-struct ivec { int v[32]; };
+struct mask { bool v[LANES]; };
+struct ivec { int v[LANES]; };
 
 #define TRPL_BIN(op)                                                                          \
-  inline real operator op(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b.v[i]; return r; } \
-  inline real operator op(const real& a, double b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b; return r; }           \
-  inline real operator op(double a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a op b.v[i]; return r; }
+  inline real operator op(const real& a, const real& b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] op b.v[i]; return r; } \
+  inline real operator op(const real& a, double b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] op b; return r; }           \
+  inline real operator op(double a, const real& b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = a op b.v[i]; return r; }
 TRPL_BIN(+) TRPL_BIN(-) TRPL_BIN(*) TRPL_BIN(/)
 #undef TRPL_BIN
-inline real operator-(const real& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = -a.v[i]; return r; }
-inline real& operator+=(real& a, const real& b) { for (int i = 0; i < 32; ++i) a.v[i] += b.v[i]; return a; }
-inline real& operator-=(real& a, const real& b) { for (int i = 0; i < 32; ++i) a.v[i] -= b.v[i]; return a; }
-inline real& operator*=(real& a, const real& b) { for (int i = 0; i < 32; ++i) a.v[i] *= b.v[i]; return a; }
+inline real operator-(const real& a) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = -a.v[i]; return r; }
+inline real& operator+=(real& a, const real& b) { for (int i = 0; i < LANES; ++i) a.v[i] += b.v[i]; return a; }
+inline real& operator-=(real& a, const real& b) { for (int i = 0; i < LANES; ++i) a.v[i] -= b.v[i]; return a; }
+inline real& operator*=(real& a, const real& b) { for (int i = 0; i < LANES; ++i) a.v[i] *= b.v[i]; return a; }
 #define TRPL_CMP(op)                                                                          \
-  inline mask operator op(const real& a, const real& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b.v[i]; return r; } \
-  inline mask operator op(const real& a, double b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b; return r; }
+  inline mask operator op(const real& a, const real& b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] op b.v[i]; return r; } \
+  inline mask operator op(const real& a, double b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] op b; return r; }
 TRPL_CMP(<) TRPL_CMP(<=) TRPL_CMP(>) TRPL_CMP(>=) TRPL_CMP(!=) TRPL_CMP(==)
 #undef TRPL_CMP
 #define TRPL_ICMP(op)                                                                         \
-  inline mask operator op(const ivec& a, int b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b; return r; } \
-  inline mask operator op(const ivec& a, const ivec& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] op b.v[i]; return r; }
+  inline mask operator op(const ivec& a, int b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] op b; return r; } \
+  inline mask operator op(const ivec& a, const ivec& b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] op b.v[i]; return r; }
 TRPL_ICMP(<) TRPL_ICMP(<=) TRPL_ICMP(>) TRPL_ICMP(>=) TRPL_ICMP(==) TRPL_ICMP(!=)
 #undef TRPL_ICMP
 
-inline ivec lane_id() { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i; return r; }
+inline ivec lane_id() { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = i; return r; }
 inline real splat(double x) { return real(x); }
 inline double uni(const real& x) { return x.v[0]; }
 inline double lane0(const real& x) { return x.v[0]; }
-inline real shfl_up(const real& x, int d) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (i - d >= 0) ? x.v[i - d] : x.v[i]; return r; }
-inline real shfl_down(const real& x, int d) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (i + d < 32) ? x.v[i + d] : x.v[i]; return r; }
+inline real shfl_up(const real& x, int d) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = (i - d >= 0) ? x.v[i - d] : x.v[i]; return r; }
+inline real shfl_down(const real& x, int d) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = (i + d < LANES) ? x.v[i + d] : x.v[i]; return r; }
 inline real shfl_idx(const real& x, int s) { return real(x.v[s]); }
-inline real sel3(const mask& m, const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
+inline real sel3(const mask& m, const real& a, const real& b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
 template <class A, class B> inline real sel(const mask& m, const A& a, const B& b) { return sel3(m, real(a), real(b)); }
-inline ivec seli(const mask& m, const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
-inline mask mand(const mask& a, const mask& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] && b.v[i]; return r; }
-inline mask mor(const mask& a, const mask& b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] || b.v[i]; return r; }
-inline mask mnot(const mask& a) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = !a.v[i]; return r; }
-inline mask mconst(bool b) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = b; return r; }
-inline bool warp_any(const mask& m) { for (int i = 0; i < 32; ++i) if (m.v[i]) return true; return false; }
-inline unsigned warp_ballot(const mask& m) { unsigned b = 0; for (int i = 0; i < 32; ++i) if (m.v[i]) b |= (1u << i); return b; }
+inline ivec seli(const mask& m, const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
+inline mask mand(const mask& a, const mask& b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] && b.v[i]; return r; }
+inline mask mor(const mask& a, const mask& b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] || b.v[i]; return r; }
+inline mask mnot(const mask& a) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = !a.v[i]; return r; }
+inline mask mconst(bool b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = b; return r; }
+inline bool warp_any(const mask& m) { for (int i = 0; i < LANES; ++i) if (m.v[i]) return true; return false; }
+inline lanebits warp_ballot(const mask& m) { lanebits b = 0; for (int i = 0; i < LANES; ++i) if (m.v[i]) b |= (1ull << i); return b; }
 inline mask lane_lt(const ivec& l, int k) { return l < k; }
-inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
+inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
 template <class A, class B, class C> inline real fmadd(const A& a, const B& b, const C& c) { return fmadd3(real(a), real(b), real(c)); }
 inline real vdiv(const real& a, const real& b) { return a / b; }
-inline real rcp_approx(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
-inline real vmax_fast(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] > b.v[i] ? a.v[i] : b.v[i]; return r; }
+inline real rcp_approx(const real& x) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
+inline real vmax_fast(const real& a, const real& b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] > b.v[i] ? a.v[i] : b.v[i]; return r; }
 inline float ctl_powf(float x, float y) { return powf(x, y); }
-inline real rcp(const real& x) { real r; for (int i = 0; i < 32; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
-#define TRPL_UN(name, expr) inline real name(const real& x) { real r; for (int i = 0; i < 32; ++i) { double a = x.v[i]; r.v[i] = (expr); } return r; }
+inline real rcp(const real& x) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = 1.0 / x.v[i]; return r; }
+#define TRPL_UN(name, expr) inline real name(const real& x) { real r; for (int i = 0; i < LANES; ++i) { double a = x.v[i]; r.v[i] = (expr); } return r; }
 TRPL_UN(vabs, fabs(a)) TRPL_UN(vexp, exp(a)) TRPL_UN(vlog, log(a)) TRPL_UN(vlog10, log10(a)) TRPL_UN(vsqrt, sqrt(a))
 #undef TRPL_UN
-inline real vmax2(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fmax(a.v[i], b.v[i]); return r; }
-inline real vmin2(const real& a, const real& b) { real r; for (int i = 0; i < 32; ++i) r.v[i] = fmin(a.v[i], b.v[i]); return r; }
+inline real vmax2(const real& a, const real& b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = fmax(a.v[i], b.v[i]); return r; }
+inline real vmin2(const real& a, const real& b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = fmin(a.v[i], b.v[i]); return r; }
 template <class A, class B> inline real vmax(const A& a, const B& b) { return vmax2(real(a), real(b)); }
 template <class A, class B> inline real vmin(const A& a, const B& b) { return vmin2(real(a), real(b)); }
-inline mask is_nan(const real& x) { mask r; for (int i = 0; i < 32; ++i) r.v[i] = (x.v[i] != x.v[i]); return r; }
+inline mask is_nan(const real& x) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = (x.v[i] != x.v[i]); return r; }
 inline real warp_sum(real x) {
-  for (int o = 16; o > 0; o >>= 1) { real y; for (int i = 0; i < 32; ++i) y.v[i] = x.v[i] + x.v[i ^ o]; x = y; }
+  for (int o = 16; o > 0; o >>= 1) { real y; for (int i = 0; i < LANES; ++i) y.v[i] = x.v[i] + x.v[i ^ o]; x = y; }
+#if TRPL_TEAM == 2
+  return real(x.v[0] + x.v[32]);       // the device build's order: first warp's partial + second warp's
+#else
   return x;
+#endif
 }
 inline real warp_max(real x) {
-  for (int o = 16; o > 0; o >>= 1) { real y; for (int i = 0; i < 32; ++i) y.v[i] = fmax(x.v[i], x.v[i ^ o]); x = y; }
+  for (int o = LANES / 2; o > 0; o >>= 1) { real y; for (int i = 0; i < LANES; ++i) y.v[i] = fmax(x.v[i], x.v[i ^ o]); x = y; }
   return x;
 }
 inline real warp_min(const real& x) { return -warp_max(-x); }
 inline real warp_scan_incl(real x) {
-  for (int o = 1; o < 32; o <<= 1) { real y = x; for (int i = o; i < 32; ++i) y.v[i] = x.v[i] + x.v[i - o]; x = y; }
+  // (two warps: a scan inside each warp, then the first warp's total onto the second, as on the device)
+  for (int o = 1; o < 32; o <<= 1) { real y = x; for (int i = 0; i < LANES; ++i) if ((i & 31) >= o) y.v[i] = x.v[i] + x.v[i - o]; x = y; }
+  if (LANES > 32) { const double tot = x.v[31]; for (int i = 32; i < LANES; ++i) x.v[i] += tot; }
   return x;
 }
 inline real gather(const double* p, const ivec& idx, const mask& m, double other) {
-  real r; for (int i = 0; i < 32; ++i) r.v[i] = m.v[i] ? p[idx.v[i]] : other; return r;
+  real r; for (int i = 0; i < LANES; ++i) r.v[i] = m.v[i] ? p[idx.v[i]] : other; return r;
 }
 inline void scatter(double* p, const ivec& idx, const mask& m, const real& v) {
-  for (int i = 0; i < 32; ++i) if (m.v[i]) p[idx.v[i]] = v.v[i];
+  for (int i = 0; i < LANES; ++i) if (m.v[i]) p[idx.v[i]] = v.v[i];
 }
-inline ivec iadd(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] + b; return r; }
-inline ivec imul(const ivec& a, int b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] * b; return r; }
-inline ivec iaddv(const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
-inline ivec isubv(const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] - b.v[i]; return r; }
-inline ivec ishr1(const ivec& a) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] >> 1; return r; }
-inline ivec iclamp(const ivec& a, int lo, int hi) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a.v[i] < lo ? lo : (a.v[i] > hi ? hi : a.v[i]); return r; }
-inline ivec isplat(int a) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a; return r; }
-inline ivec irsub(int a, const ivec& b) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = a - b.v[i]; return r; }
-inline ivec lane_minus(int d) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i >= d ? i - d : i; return r; }
-inline ivec lane_plus(int d) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = i + d < 32 ? i + d : i; return r; }
-inline ivec to_int_floor(const real& x) { ivec r; for (int i = 0; i < 32; ++i) r.v[i] = (int)floor(x.v[i]); return r; }
-inline real to_real(const ivec& a) { real r; for (int i = 0; i < 32; ++i) r.v[i] = (double)a.v[i]; return r; }
+inline ivec iadd(const ivec& a, int b) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] + b; return r; }
+inline ivec imul(const ivec& a, int b) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] * b; return r; }
+inline ivec iaddv(const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline ivec isubv(const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] - b.v[i]; return r; }
+inline ivec ishr1(const ivec& a) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] >> 1; return r; }
+inline ivec iclamp(const ivec& a, int lo, int hi) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a.v[i] < lo ? lo : (a.v[i] > hi ? hi : a.v[i]); return r; }
+inline ivec isplat(int a) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a; return r; }
+inline ivec irsub(int a, const ivec& b) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = a - b.v[i]; return r; }
+inline ivec lane_minus(int d) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = i >= d ? i - d : i; return r; }
+inline ivec lane_plus(int d) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = i + d < LANES ? i + d : i; return r; }
+inline ivec to_int_floor(const real& x) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = (int)floor(x.v[i]); return r; }
+inline real to_real(const ivec& a) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = (double)a.v[i]; return r; }
 
 // every access is bounds-checked (std::vector::at): the pair indices are the same compile-time
 // layout constants the device build uses, so the CPU test tier doubles as the bounds check of the
@@ -314,12 +440,17 @@ struct LaneMem {
   void ld2(int p, real& a, real& b) const { a = slots.at(2 * p); b = slots.at(2 * p + 1); }
   void st2(int p, const real& a, const real& b) { slots.at(2 * p) = a; slots.at(2 * p + 1) = b; }
   void ld2_from(int p, const ivec& src, real& a, real& b) const {
-    for (int i = 0; i < 32; ++i) { a.v[i] = slots.at(2 * p).v[src.v[i] & 31]; b.v[i] = slots.at(2 * p + 1).v[src.v[i] & 31]; }
+    for (int i = 0; i < LANES; ++i) { a.v[i] = slots.at(2 * p).v[src.v[i] & (LANES - 1)]; b.v[i] = slots.at(2 * p + 1).v[src.v[i] & (LANES - 1)]; }
   }
   double uld(int p, int i) const { return slots.at(2 * p + (i & 1)).v[i >> 1]; }
   void ust(int p, int i, double v) { slots.at(2 * p + (i & 1)).v[i >> 1] = v; }
 };
+#if TRPL_TEAM == 2
+inline void team_other_sync();
+inline void warp_sync() { team_other_sync(); }
+#else
 inline void warp_sync() {}
+#endif
 // host stand-in of the tensor-memory slice (see the device half): just another array of pairs
 struct LaneTm {
   std::vector<real> slots;
@@ -331,5 +462,40 @@ template <class M> inline void mem_wait_ld(const M&) {}
 template <class M> inline void mem_wait_st(const M&) {}
 template <int N, class M> inline void mem_ld_pairs(const M& m, int p, real* v) { for (int i = 0; i < N; ++i) m.ld2(p + i, v[2 * i], v[2 * i + 1]); }
 template <int N, class M> inline void mem_st_pairs(M& m, int p, const real* v) { for (int i = 0; i < N; ++i) m.st2(p + i, v[2 * i], v[2 * i + 1]); }
+#if TRPL_TEAM == 2
+// The device build's mailbox discipline, checked: two consecutive team primitives of a trajectory
+// must not use the same mailbox slot (see the device half).  Slot numbers come from the same macros.
+inline int& team_last_slot() { static thread_local int last = -1; return last; }
+inline void team_slot_check(int s) {
+  if (team_last_slot() == s) { fprintf(stderr, "simt: mailbox slot %d used by two consecutive team primitives\n", s); abort(); }
+  team_last_slot() = s;
+}
+inline void team_other_sync() { team_last_slot() = -1; }     // a barrier that uses no mailbox (warp_sync)
+template <int S> inline double lane0_s(const real& x) { team_slot_check(S); return lane0(x); }
+template <int S> inline real shfl_idx_s(const real& x, int s) { team_slot_check(S); return shfl_idx(x, s); }
+template <int S> inline real shfl_up_s(const real& x, int d) { team_slot_check(S); if (d != 1) abort(); return shfl_up(x, d); }
+template <int S> inline real shfl_down_s(const real& x, int d) { team_slot_check(S); if (d != 1) abort(); return shfl_down(x, d); }
+template <int S> inline bool warp_any_s(const mask& m) { team_slot_check(S); return warp_any(m); }
+template <int S> inline lanebits warp_ballot_s(const mask& m) { team_slot_check(S); return warp_ballot(m); }
+template <int S> inline real warp_sum_s(const real& x) { team_slot_check(S); return warp_sum(x); }
+template <int S> inline real warp_max_s(const real& x) { team_slot_check(S); return warp_max(x); }
+template <int S> inline real warp_min_s(const real& x) { team_slot_check(S); return warp_min(x); }
+template <int S> inline real warp_scan_incl_s(const real& x) { team_slot_check(S); return warp_scan_incl(x); }
+#endif
 }  // namespace simt
+#endif
+
+#if TRPL_TEAM == 2
+// One mailbox slot per call site (see the device half of the team vocabulary).
+#define TRPL_TEAM_SLOT (__COUNTER__ & 63)
+#define lane0(x) lane0_s<TRPL_TEAM_SLOT>(x)
+#define shfl_idx(x, s) shfl_idx_s<TRPL_TEAM_SLOT>(x, s)
+#define shfl_up(x, d) shfl_up_s<TRPL_TEAM_SLOT>(x, d)
+#define shfl_down(x, d) shfl_down_s<TRPL_TEAM_SLOT>(x, d)
+#define warp_any(m) warp_any_s<TRPL_TEAM_SLOT>(m)
+#define warp_ballot(m) warp_ballot_s<TRPL_TEAM_SLOT>(m)
+#define warp_sum(x) warp_sum_s<TRPL_TEAM_SLOT>(x)
+#define warp_max(x) warp_max_s<TRPL_TEAM_SLOT>(x)
+#define warp_min(x) warp_min_s<TRPL_TEAM_SLOT>(x)
+#define warp_scan_incl(x) warp_scan_incl_s<TRPL_TEAM_SLOT>(x)
 #endif

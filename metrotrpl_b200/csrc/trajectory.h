@@ -169,8 +169,9 @@ struct Slots {
   static constexpr int KP = NKS * KSTRIDE;
   static constexpr int FACP = FacSlots<NPL>::COUNT;
   static constexpr int TRP = (MODEL == MODEL_TRAPS) ? 3 * NPL : 0;   // traps: 5 condensation coefficients per node
-  // PCR multipliers: 5 levels x 4 pairs + the inverse (2 pairs, padded to 4)
-  static constexpr int PMP = 24;
+  // PCR multipliers: one level per doubling of the stride (5 for a warp, 6 for a two-warp team) x 4
+  // pairs + the inverse (2 pairs, padded to 4)
+  static constexpr int PMP = 4 * LOG2_LANES + 4;
 #if TRPL_PM_REGS
   static constexpr bool PM_IN_REGS = true;
 #else
@@ -189,7 +190,7 @@ struct Slots {
   static constexpr bool FAC_IN_TM = FACP <= TM_BUDGET;
   static constexpr int TM_LEFT1 = TM_BUDGET - (FAC_IN_TM ? FACP : 0);
   static constexpr int PM_TM_PAIRS = PM_IN_REGS ? 0 : (TM_LEFT1 >= PMP ? PMP : (TM_LEFT1 / 4) * 4);
-  static constexpr int PM_SM_PAIRS = PM_IN_REGS ? 0 : (PM_TM_PAIRS == PMP ? 0 : 22 - PM_TM_PAIRS);
+  static constexpr int PM_SM_PAIRS = PM_IN_REGS ? 0 : (PM_TM_PAIRS == PMP ? 0 : PMP - 2 - PM_TM_PAIRS);
   static constexpr int TM_LEFT2 = TM_LEFT1 - PM_TM_PAIRS;
   static constexpr bool K_IN_TM = FAC_IN_TM && KP <= TM_LEFT2;
   static constexpr int TM_LEFT3 = TM_LEFT2 - (K_IN_TM ? KP : 0);
@@ -224,7 +225,7 @@ struct Slots {
   // shared memory the slice is at least the 7 stages the explicit path keeps from KBASE on
   static constexpr int UNI = (K_IN_TM || XCH + XCH_PAIRS >= 7 * KSTRIDE) ? XCH + XCH_PAIRS : 7 * KSTRIDE;
   static constexpr int COUNT = UNI + 1;
-  static constexpr int BYTES = COUNT * 32 * 16;
+  static constexpr int BYTES = COUNT * LANES * 16;
   // region bases in whichever memory holds them
   static constexpr int KBASE = K_IN_TM ? TM_K : SM_K;
   static constexpr int FAC = FAC_IN_TM ? TM_FAC : SM_FAC;
@@ -431,7 +432,7 @@ TRPL_FN void emitter_finish(Emitter& e, const TrajIn& in, bool want_ll, TrajMid&
   while (e.io < n_t) {                              // floor reached or integrator failure
     const ivec k = iadd(lane, e.io);
     emitter_accumulate(e, in, want_ll, k, k < n_t, splat(in.md->min_y));
-    e.io += 32;
+    e.io += LANES;
   }
   if (want_ll && !in.post_pass) {
     mid.l[0] = -uni(warp_sum(e.ll0)); mid.l[1] = -uni(warp_sum(e.ll1)); mid.l[2] = -uni(warp_sum(e.ll2));
@@ -459,10 +460,10 @@ TRPL_NOINLINE void emit_history(const TrajIn& in, bool want_ll, double* hist, in
     const ivec k = iadd(lane, e.io);
     const mask in_range = k < n_t;
     const real tq = gather(in.times, k, in_range, DBL_MAX);
-    const unsigned bits = warp_ballot(mand(in_range, tq <= t_last));
+    const lanebits bits = warp_ballot(mand(in_range, tq <= t_last));
     if (bits == 0u) break;
     int cnt = 0;
-    { unsigned b = bits; while (b & 1u) { ++cnt; b >>= 1; } }     // times ascend: the ready lanes are a prefix
+    { lanebits b = bits; while (b & 1u) { ++cnt; b >>= 1; } }     // times ascend: the ready lanes are a prefix
     const mask take = lane < cnt;
     const real tqe = sel(take, tq, t_last);                        // idle lanes: a harmless exact hit
     // newest point of the containing step: the first log entry with t >= tq
@@ -487,15 +488,15 @@ TRPL_NOINLINE void emit_history(const TrajIn& in, bool want_ll, double* hist, in
     const mask two = mand(g >= 1, i2 >= 1);
     real y = hermite_lane(tqe, mand(g >= 2, i2 >= 2), t0, y0, s0, sel(two, t1, t2 - 1.0), y1, s1, t2, y2, s2);
     y = sel(mor(mnot(two), tqe >= t2), y2, y);
-    const unsigned low = warp_ballot(mand(take, y < md.min_y));
+    const lanebits low = warp_ballot(mand(take, y < md.min_y));
     if (low != 0u) {
-      int firstlow = 0; { unsigned b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
+      int firstlow = 0; { lanebits b = low; while (!(b & 1u)) { ++firstlow; b >>= 1; } }
       y = sel(lane >= firstlow, md.min_y, y);
       e.floored = true; e.status |= ST_FLOORED;
     }
     emitter_accumulate(e, in, want_ll, k, take, y);
     e.io += cnt;
-    if (cnt < 32) break;
+    if (cnt < LANES) break;
   }
   if (carry && n >= 4) {
     const real v = gather(hist, iadd(lane, 3 * (n - 2)), lane < 6, 0.0);

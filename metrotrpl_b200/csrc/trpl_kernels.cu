@@ -24,137 +24,13 @@
 #include "extrapolation.h"
 #include "proposals.h"
 
-namespace {
+#include "kernel_common.h"
 
-using namespace trpl;
+namespace {
 
 static_assert(sizeof(trpl_meas_desc) == sizeof(MeasDesc), "ABI struct mismatch");
 static_assert(sizeof(trpl_solver_opts) == sizeof(SolverOpts), "ABI struct mismatch");
 static_assert(TRPL_NPARAM == trpl::NPARAM, "ABI constant mismatch");
-
-// Residency: 8 trajectories per SM - two CTAs of four warps at 255 registers per thread.  (Twelve
-// per SM at 168 registers, with the tensor-memory slices of a 12-warp CTA stacked along the
-// columns, was built and measured: no gain)
-constexpr int WARPS_PER_CTA = 4;                  // one warp per tensor-memory lane quarter
-constexpr int CTAS_PER_SM = 2;
-constexpr int pow2_cols(int c) { return c == 0 ? 0 : c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
-
-struct KernelArgs {
-  const double* params;      // [n_sets][16]
-  const double* aux;         // [n_sets][n_meas][6]
-  const MeasDesc* meas;      // [n_meas]
-  const double* times;
-  const double* vals;
-  const double* uncs;
-  const double* profiles;
-  double* logll;             // [n_traj][3]
-  int* status;               // [n_traj]
-  int* nsteps;               // [n_traj][2]
-  double* curves;            // [n_sets][n_times_total] or null
-  const double* irf_mom;     // [rows][3] or null
-  double* scratch;           // per-warp slices: resampled | convolved | trimmed
-  size_t scratch_stride, off_hk, off_trim, off_r2, off_u2;
-  const double* ladder_T;
-  double* ladder_out;        // [n_traj][n_ladder]
-  int n_ladder;
-  int* counter;              // work queue head
-  const int* meas_order;     // [n_meas] measurement indices, most expensive first
-  const int* queue;          // [n_traj] explicit queue order (trpl_set_queue_order) or null
-  double* hist;              // per-warp step histories, 3 * HIST_CAP doubles each
-  int* defer_list;           // trajectories handed to the explicit path
-  int* defer_count;
-  int n_traj, n_meas, n_times_total, warps_per_cta;
-  SolverOpts opt;
-};
-
-__device__ __forceinline__ void setup_traj(const KernelArgs& a, int traj, int warp, TrajIn& in) {
-  in.hist = a.hist + (size_t)(blockIdx.x * a.warps_per_cta + warp) * (3 * HIST_CAP);
-  const int set = traj / a.n_meas;
-  const int mi = traj - set * a.n_meas;
-  const MeasDesc* md = a.meas + mi;
-  in.par = a.params + (size_t)set * TRPL_NPARAM;
-  in.md = md;
-  in.times = a.times + md->t_off;
-  in.vals = a.vals ? a.vals + md->t_off : nullptr;
-  in.uncs = a.uncs ? a.uncs + md->t_off : nullptr;
-  in.profile = a.profiles ? a.profiles + md->prof_off : nullptr;
-  const double* ax = a.aux + (size_t)traj * TRPL_NAUX;
-  in.scale_shift = ax[TRPL_A_SCALE_SHIFT];
-  in.s2T[0] = ax[TRPL_A_S2T0]; in.s2T[1] = ax[TRPL_A_S2T1]; in.s2T[2] = ax[TRPL_A_S2T2];
-  in.fl_mult = ax[TRPL_A_FLUENCE_MULT]; in.al_mult = ax[TRPL_A_ABSORB_MULT];
-  in.curve = a.curves ? a.curves + (size_t)set * a.n_times_total + md->t_off : nullptr;
-  const bool want_ll = !(a.opt.flags & OPT_NO_LIKELIHOOD);
-  const bool conv = a.irf_mom && a.scratch && md->irf_nk > 0;
-  const bool ladder = (a.opt.flags & OPT_LADDER) && a.n_ladder > 0 && a.scratch;
-  in.post_pass = want_ll && in.curve && ((a.opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
-}
-
-// tail-only addresses are formed after the loop from the (constant-bank) launch arguments
-__device__ __forceinline__ void finish_traj(const KernelArgs& a, int traj, int warp, const TrajIn& in,
-                                            const TrajMid& mid, TrajOut& out) {
-  const MeasDesc* md = in.md;
-  const bool conv = a.irf_mom && a.scratch && md->irf_nk > 0;
-  const bool ladder = (a.opt.flags & OPT_LADDER) && a.n_ladder > 0 && a.scratch;
-  TailIn tl;
-  tl.irf.nk = conv ? md->irf_nk : 0;
-  tl.irf.dt = md->irf_dt;
-  tl.irf.mom = a.irf_mom ? a.irf_mom + 3 * (size_t)md->irf_off : nullptr;
-  double* ws = a.scratch ? a.scratch + (size_t)(blockIdx.x * a.warps_per_cta + warp) * a.scratch_stride : nullptr;
-  tl.irf.ry = ws; tl.irf.hk = ws ? ws + a.off_hk : nullptr; tl.irf.trim = ws ? ws + a.off_trim : nullptr;
-  tl.r2_scratch = (ws && ladder) ? ws + a.off_r2 : nullptr;
-  tl.u2_scratch = (ws && ladder) ? ws + a.off_u2 : nullptr;
-  tl.ladder_T = a.ladder_T; tl.ladder_n = a.n_ladder;
-  tl.ladder_out = a.ladder_out ? a.ladder_out + (size_t)traj * a.n_ladder : nullptr;
-  finalize_trajectory(in, tl, a.opt, mid, out);
-  if ((threadIdx.x & 31) == 0) {
-    a.logll[3 * (size_t)traj + 0] = out.logll[0];
-    a.logll[3 * (size_t)traj + 1] = out.logll[1];
-    a.logll[3 * (size_t)traj + 2] = out.logll[2];
-    a.status[traj] = out.status;
-    a.nsteps[2 * (size_t)traj + 0] = out.n_acc;
-    a.nsteps[2 * (size_t)traj + 1] = out.n_rej;
-  }
-  __syncwarp();
-}
-
-// Tensor-memory slice of the calling warp.  One warp of the CTA allocates TM_COLS columns for the
-// CTA (tcgen05.alloc hands out whole columns, all 128 lanes); warp w then owns lanes 32*(w%4)..+31
-// of those columns.  A CTA has at most four warps, so the slices are disjoint.
-template <class SL>
-struct TmCta {
-  static constexpr int COLS = pow2_cols(4 * SL::TM_COUNT);   // columns one CTA allocates
-  static_assert(4 * SL::TM_COUNT <= 512, "tensor-memory slice exceeds 512 columns");
-};
-template <class SL>
-__device__ __forceinline__ LaneTm tmem_acquire(int warp) {
-  LaneTm tm{0u};
-  if constexpr (SL::TM_COUNT > 0) {
-    __shared__ unsigned tm_base_s;
-    if (warp == 0) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                   :: "r"((unsigned)__cvta_generic_to_shared(&tm_base_s)), "n"(TmCta<SL>::COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // broadcast from lane 0: tells ptxas the address is warp-uniform (it then lives in a uniform
-    // register instead of being re-derived from the thread index in front of every access)
-    tm.base = __shfl_sync(0xffffffffu, tm_base_s + ((unsigned)(32 * warp) << 16), 0);
-  }
-  return tm;
-}
-// every warp of the CTA is done with its slice: the allocating warp gives the columns back
-template <class SL>
-__device__ __forceinline__ void tmem_release(int warp, const LaneTm& tm) {
-  if constexpr (SL::TM_COUNT > 0) {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0)      // warp 0 owns lane quarter 0: its base is the allocation
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                   :: "r"(tm.base), "n"(TmCta<SL>::COLS) : "memory");
-  }
-}
 
 template <int NPL, int MODEL, bool FULL>
 __global__ void __launch_bounds__(32 * WARPS_PER_CTA, CTAS_PER_SM) trpl_forward_kernel(const KernelArgs a) {
@@ -455,6 +331,52 @@ int launch(trpl_handle* h, KernelArgs a) {
   return 0;
 }
 
+// Grids of 129..256 nodes: a team of two warps per trajectory, compiled in team_kernels.cu against
+// the two-warp vocabulary of simt.h (4 nodes per lane on 64 lanes).  Same queue, same arguments, same
+// per-trajectory scratch as launch<>; a CTA of four warps holds two trajectories.
+extern "C" void trpl_team_plan(int model, size_t* smem, int* tm_cols, int* teams_per_cta);
+extern "C" int trpl_team_run(int model, int full, const void* args, size_t args_size, int grid, size_t smem,
+                             void* stream, int explicit_pass);
+
+int launch_team(trpl_handle* h, KernelArgs a) {
+  size_t smem = 0;
+  int cols = 0, tpc = 1;
+  trpl_team_plan(h->model, &smem, &cols, &tpc);
+  if (smem > (size_t)h->prop.sharedMemPerBlockOptin) return fail("trajectory state does not fit in shared memory");
+  const int by_smem = (int)((size_t)h->prop.sharedMemPerMultiprocessor / (smem + 1024 + 16));
+  int per_sm = std::min(CTAS_PER_SM, by_smem);
+  if (cols > 0) per_sm = std::min(per_sm, 512 / cols);
+  if (per_sm < 1) return fail("team kernel does not fit on an SM");
+  a.warps_per_cta = tpc;                      // step logs / scratch slices: one per team
+  int grid = std::min(h->prop.multiProcessorCount * per_sm, (a.n_traj + tpc - 1) / tpc);
+  if (grid < 1) grid = 1;
+  if (getenv("TRPL_DEBUG"))
+    fprintf(stderr, "[trpl] launch two-warp teams, model=%d full=%d: %d teams/CTA, %zu B smem/CTA, %d TMEM columns/CTA, %d CTAs/SM, grid %d\n",
+            h->model, (int)h->all_full, tpc, smem, cols, per_sm, grid);
+  if (a.scratch) {
+    CU(h->d_scratch.reserve((size_t)grid * tpc * a.scratch_stride));
+    a.scratch = h->d_scratch.p;
+  }
+  CU(h->d_hist.reserve((size_t)grid * tpc * 3 * HIST_CAP));
+  a.hist = h->d_hist.p;
+  CU(cudaMemsetAsync(h->d_counter.p, 0, 4 * sizeof(int), h->stream));
+  a.defer_list = nullptr; a.defer_count = h->d_counter.p + 2;
+  if (!(a.opt.flags & OPT_NO_EXPLICIT)) {
+    CU(h->d_defer.reserve(a.n_traj));
+    a.defer_list = h->d_defer.p;
+  }
+  const int full = (h->all_full && h->max_nx == 256) ? 1 : 0;
+  CU(cudaEventRecord(h->ev0, h->stream));
+  CU((cudaError_t)trpl_team_run(h->model, full, &a, sizeof(a), grid, smem, h->stream, 0));
+  h->launches += 1;
+  if (a.defer_list) {
+    CU((cudaError_t)trpl_team_run(h->model, full, &a, sizeof(a), grid, smem, h->stream, 1));
+    h->launches += 1;
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
+  return 0;
+}
+
 // CTA-per-trajectory launch (TRPL_OPT_CTA_PER_TRAJ): 'std' model, every measurement on 128 nodes
 int launch_cta(trpl_handle* h, KernelArgs a) {
   if (h->model != TRPL_MODEL_STD || !h->all_full || h->max_nx != cta::NX)
@@ -524,20 +446,20 @@ int launch_seulex(trpl_handle* h, KernelArgs a, bool cooperative) {
 template <int MODEL>
 int launch_npl(trpl_handle* h, const KernelArgs& a) {
   const int nx = h->max_nx;
-#ifdef TRPL_DEV_NX256_ONLY      // developer builds of tuning variants: the nx = 256 instantiation only
-  if (h->all_full && nx == 256) return launch<8, MODEL, true>(h, a);
+#ifdef TRPL_DEV_NX256_ONLY      // developer builds of tuning variants: the nx = 129..256 kernels only
+  if (nx > 128 && nx <= 256) return launch_team(h, a);
   return fail("this developer build only holds the nx=256 instantiation");
 #else
-  // the padding-free instantiation exists for the headline grid (nx = 128) and nx = 256
+  // more than 128 nodes: two warps per trajectory (team_kernels.cu)
+  if (nx > 128 && nx <= 256) return launch_team(h, a);
+  // the padding-free instantiation exists for the headline grid (nx = 128)
   if (h->all_full && nx == 128) return launch<4, MODEL, true>(h, a);
 #ifdef TRPL_DEV_HEADLINE_ONLY   // developer builds of tuning variants: compile one instantiation only
   return fail("this developer build only holds the nx=128 instantiation");
 #else
-  if (h->all_full && nx == 256) return launch<8, MODEL, true>(h, a);
   if (nx <= 32) return launch<1, MODEL, false>(h, a);
   if (nx <= 64) return launch<2, MODEL, false>(h, a);
   if (nx <= 128) return launch<4, MODEL, false>(h, a);
-  if (nx <= 256) return launch<8, MODEL, false>(h, a);
   return fail("nx > 256 is not supported by this build");
 #endif
 #endif

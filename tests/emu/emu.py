@@ -9,32 +9,35 @@ from metrotrpl_b200 import _capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libtrpl_emu.so")
+SO_TEAM = os.path.join(HERE, "libtrpl_emu_team.so")      # the same source with the two-warp team vocabulary
 SRC = os.path.join(HERE, "trpl_emu.cpp")
 CSRC = os.path.join(HERE, "..", "..", "metrotrpl_b200", "csrc")
 
 
 def build(force=False):
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
-    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
-        return SO
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fopenmp", "-ffp-contract=off", "-shared",
-                           "-fPIC", "-o", SO, SRC])
+    for so, extra in ((SO, []), (SO_TEAM, ["-DTRPL_TEAM=2"])):
+        if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+            continue
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fopenmp", "-ffp-contract=off", "-shared",
+                               "-fPIC"] + extra + ["-o", so, SRC])
     return SO
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(team=False):
+    """The host lock-step build: one warp per trajectory (nx <= 128), or the two-warp team (nx 129..256)."""
+    if team not in _libs:
         build()
-        _lib = C.CDLL(SO)
+        l = C.CDLL(SO_TEAM if team else SO)
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
-        _lib.trpl_emu_loglik_batch.argtypes = [C.c_int32, C.c_int32, C.POINTER(_capi.MeasDesc), C.c_int32,
-                                               dp, dp, dp, dp, C.c_int32, dp, dp,
-                                               C.POINTER(_capi.SolverOpts), dp, ip, ip, dp, dp, dp, C.c_int32, dp]
-    return _lib
+        l.trpl_emu_loglik_batch.argtypes = [C.c_int32, C.c_int32, C.POINTER(_capi.MeasDesc), C.c_int32,
+                                            dp, dp, dp, dp, C.c_int32, dp, dp,
+                                            C.POINTER(_capi.SolverOpts), dp, ip, ip, dp, dp, dp, C.c_int32, dp]
+        _libs[team] = l
+    return _libs[team]
 
 
 def loglik_batch(prob, params, aux, opts, want_curves=True, ladder=None):
@@ -48,7 +51,10 @@ def loglik_batch(prob, params, aux, opts, want_curves=True, ladder=None):
     p = _capi._ptr
     lad_T = None if ladder is None else np.ascontiguousarray(ladder, dtype=np.float64)
     lad_out = None if ladder is None else np.empty((n_sets, prob.n_meas, lad_T.size))
-    rc = lib().trpl_emu_loglik_batch(prob.model, prob.n_meas, prob.meas, prob.n_times_total,
+    # grids of more than 128 nodes run on the two-warp team, as in the product (the extrapolation
+    # integrator's generic one-warp driver keeps its 8-nodes-per-lane host instantiation)
+    team = max(int(prob.meas[i].nx) for i in range(prob.n_meas)) > 128 and not (opts.flags & _capi.OPT_EXTRAPOLATION)
+    rc = lib(team).trpl_emu_loglik_batch(prob.model, prob.n_meas, prob.meas, prob.n_times_total,
                                      p(prob.times, C.c_double), p(prob.vals, C.c_double),
                                      p(prob.uncs, C.c_double), p(prob.profiles, C.c_double), n_sets,
                                      p(params, C.c_double), p(aux, C.c_double), C.byref(opts),

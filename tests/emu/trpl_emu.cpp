@@ -10,7 +10,9 @@
 #include "../../include/metrotrpl_b200.h"
 #include "../../metrotrpl_b200/csrc/trajectory.h"
 #include "../../metrotrpl_b200/csrc/explicit.h"
+#if TRPL_TEAM == 1
 #include "../../metrotrpl_b200/csrc/extrapolation.h"
+#endif
 
 using namespace trpl;
 
@@ -46,9 +48,12 @@ static void run_all(int n_meas, const MeasDesc* meas, int n_times_total, const d
     in.post_pass = want_ll && in.curve && ((opt.flags & OPT_FORCE_MIN_Y) || conv || ladder);
     TrajOut out;
     TrajMid mid;
+#if TRPL_TEAM == 1
     if (opt.flags & OPT_EXTRAPOLATION) {
       run_trajectory_seulex<NPL, MODEL, FULL>(in, opt, sm, out, mid);      // the one-warp driver
-    } else if (run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out, mid, !(opt.flags & OPT_NO_EXPLICIT))) {
+    } else
+#endif
+    if (run_trajectory<NPL, MODEL, FULL>(in, opt, sm, out, mid, !(opt.flags & OPT_NO_EXPLICIT))) {
       run_trajectory_explicit<NPL, MODEL, FULL>(in, opt, sm, out, mid);
       out.status |= ST_EXPLICIT;
     }
@@ -84,6 +89,13 @@ static int dispatch(int max_nx, int n_meas, const MeasDesc* meas, int n_times_to
 #define GO(N, F) run_all<N, MODEL, F>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom, ladder_T, n_ladder, ladder_out)
   bool all_full = true;
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) all_full = false;
+#if TRPL_TEAM == 2
+  // the two-warp team vocabulary (team_kernels.cu): 64 lanes x 4 nodes, the grids of 129..256 nodes
+  if (all_full && max_nx == 256) GO(4, true);
+  else if (max_nx > 128 && max_nx <= 256) GO(4, false);
+  else return 1;
+#else
+  // (8 nodes per lane: no product kernel any more, kept for the generic one-warp extrapolation driver)
   if (all_full && max_nx == 128) GO(4, true);
   else if (all_full && max_nx == 256) GO(8, true);
   else if (max_nx <= 32) GO(1, false);
@@ -91,6 +103,7 @@ static int dispatch(int max_nx, int n_meas, const MeasDesc* meas, int n_times_to
   else if (max_nx <= 128) GO(4, false);
   else if (max_nx <= 256) GO(8, false);
   else return 1;
+#endif
 #undef GO
   return 0;
 }
