@@ -67,12 +67,6 @@ TRPL_FN Blk blk_add(const Blk& x, const Blk& y) {
 }
 TRPL_FN Blk blk_neg(const Blk& x) { Blk r; r.a00 = -x.a00; r.a01 = -x.a01; r.a10 = -x.a10; r.a11 = -x.a11; return r; }
 TRPL_FN Blk blk_zero() { Blk r; r.a00 = splat(0.0); r.a01 = splat(0.0); r.a10 = splat(0.0); r.a11 = splat(0.0); return r; }
-TRPL_FN Blk blk_shfl_up(const Blk& x, int d) {
-  Blk r; r.a00 = shfl_up(x.a00, d); r.a01 = shfl_up(x.a01, d); r.a10 = shfl_up(x.a10, d); r.a11 = shfl_up(x.a11, d); return r;
-}
-TRPL_FN Blk blk_shfl_down(const Blk& x, int d) {
-  Blk r; r.a00 = shfl_down(x.a00, d); r.a01 = shfl_down(x.a01, d); r.a10 = shfl_down(x.a10, d); r.a11 = shfl_down(x.a11, d); return r;
-}
 TRPL_FN Blk blk_sel(mask m, const Blk& x, const Blk& y) {
   Blk r; r.a00 = sel(m, x.a00, y.a00); r.a01 = sel(m, x.a01, y.a01); r.a10 = sel(m, x.a10, y.a10); r.a11 = sel(m, x.a11, y.a11); return r;
 }
@@ -229,8 +223,15 @@ TRPL_FN void bt_factor(const Blk (&A)[NPL], const Blk (&B)[NPL], const Blk (&C)[
       mem_st_pairs<S::RUN2>(fm, base + S::RUN1, f2);
     }
     // reduced (interface) row of this lane
-    const Blk v0n = blk_shfl_down(v[0], 1);
-    const Blk w0n = blk_shfl_down(w[0], 1);
+    // first spikes of the next lane (one exchange of eight values)
+    Blk v0n, w0n;
+    {
+      const real mine[8] = {v[0].a00, v[0].a01, v[0].a10, v[0].a11, w[0].a00, w[0].a01, w[0].a10, w[0].a11};
+      real next[8];
+      nbr_down(mine, next);
+      v0n.a00 = next[0]; v0n.a01 = next[1]; v0n.a10 = next[2]; v0n.a11 = next[3];
+      w0n.a00 = next[4]; w0n.a01 = next[5]; w0n.a10 = next[6]; w0n.a11 = next[7];
+    }
     ra = blk_mul_neg(A[NPL - 1], v[NI - 1]);
     rb = blk_sub(blk_sub(B[NPL - 1], blk_mul(A[NPL - 1], w[NI - 1])), blk_mul(C[NPL - 1], v0n));
     rc = blk_mul_neg(C[NPL - 1], w0n);
@@ -290,7 +291,8 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch
     TRPL_UNROLL for (int j = 1; j < NI; ++j) g[j] = sub_mv(r[j], lm[j - 1], g[j - 1]);
     g[NI - 1] = blk_mv(dinv[NI - 1], g[NI - 1]);
     TRPL_UNROLL for (int j = NI - 2; j >= 0; --j) g[j] = blk_mv(dinv[j], sub_mv_lower(g[j], csup[j], g[j + 1]));
-    V2 g0n; g0n.x = shfl_down(g[0].x, 1); g0n.y = shfl_down(g[0].y, 1);
+    V2 g0n;
+    { const real mine[2] = {g[0].x, g[0].y}; real next[2]; nbr_down(mine, next); g0n.x = next[0]; g0n.y = next[1]; }
     rr = sub_mv_upper(r[NPL - 1], az, g[NI - 1]);
     rr = sub_mv_lower(rr, cz, g0n);                          // cz is zero on the last lane
   } else {
@@ -329,7 +331,8 @@ TRPL_FN void bt_solve(V2 (&r)[NPL], const FM& fm, int base, LaneMem& sm, int xch
     Blk vs[NI], ws[NI];
     mem_wait_ld(fm);
     TRPL_UNROLL for (int j = 0; j < NI; ++j) { vs[j] = get_blk(f2, 2 * j); ws[j] = get_blk(f2, 2 * NI + 2 * j); }
-    V2 zl; zl.x = shfl_up(z.x, 1); zl.y = shfl_up(z.y, 1);   // lane 0: V is zero there
+    V2 zl;                                                   // lane 0: V is zero there
+    { const real mine[2] = {z.x, z.y}; real prev[2]; nbr_up(mine, prev); zl.x = prev[0]; zl.y = prev[1]; }
     TRPL_UNROLL for (int j = 0; j < NI; ++j) r[j] = sub_mv(sub_mv(g[j], vs[j], zl), ws[j], z);
   }
 }

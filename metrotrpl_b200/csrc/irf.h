@@ -77,33 +77,67 @@ TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t
   if (warp_any(any_nan)) return false;
 
   // ---- 2. moment convolution (laplace.py:178-222) ----
+  // hk[k] = sum_{m < min(k, nk_irf)}  b(kp) I0_m + i1(kp) I1_m + i2(kp) I2_m ,   kp = k - 1 - m,
+  //   b = ry[2kp+1],  i1 = ry[2kp+2] - ry[2kp],  i2 = 2 (ry[2kp+2] - 2 ry[2kp+1] + ry[2kp]).
+  // Every lane owns OPL CONSECUTIVE outputs: the (b, i1, i2) triples of lag m+1 are those of lag m
+  // shifted by one output, so each lag costs one new 128-bit load and one new triple per lane instead
+  // of two loads and one triple per OUTPUT (the pass was a quarter of the nx = 256 kernel).  Each
+  // output still sums its lags in ascending order with the same operations: same bits as before.
+  constexpr int OPL = 4;
   real best = splat(-DBL_MAX);
   ivec best_k = isplat(0x7fffffff);
-  for (int k0 = 0; k0 <= nk; k0 += LANES) {
-    const ivec k = iadd(lane, k0);
-    const mask take = k <= nk;
-    real acc = splat(0.0);
-    const int m_hi = (k0 + LANES - 1 < f.nk) ? k0 + LANES - 1 : f.nk;      // lags needed by the largest k of this batch
-    // c carries ry[2kp+2] of the previous lag (= ry[2kp] of this one shifted): two new loads per lag
-    real c = gather(f.ry, imul(k, 2), mand(take, k >= 1), 0.0);
-    for (int m = 0; m < m_hi; ++m) {
-      const mask on = mand(take, k > m);                      // kp = k-1-m >= 0
-      const ivec kp2 = imul(iadd(k, -1 - m), 2);
-      const real a = gather(f.ry, kp2, on, 0.0);
-      const real b = gather(f.ry, iadd(kp2, 1), on, 0.0);
-      const double m0 = f.mom[3 * m], m1 = f.mom[3 * m + 1], m2 = f.mom[3 * m + 2];
-      const real i1 = c - a;
-      const real i2 = 2.0 * ((c - 2.0 * b) + a);
-      const real term = fmadd(i2, m2, fmadd(i1, m1, b * m0));
-      acc = acc + sel(on, term, 0.0);
-      c = a;
+  for (int kb = 0; kb <= nk; kb += OPL * LANES) {
+    const ivec k0 = iadd(imul(lane, OPL), kb);                // first output of this lane
+    const int k_max = kb + OPL * LANES - 1;
+    const int m_hi = (k_max < f.nk) ? k_max : f.nk;           // lags needed by the largest k of this batch
+    // window at lag 0: kp = k0 - 1 + j.  Triples of kp < 0 are zero (the lag does not exist for that
+    // output); those of kp >= nk only feed outputs beyond nk, which are never stored.  Loads reach
+    // kp = nk: ry[2 nk] closes the triple of nk - 1 (ry[2 nk + 1] may be the first word behind the
+    // resampled curve, still inside the scratch slice, and is not used).
+    real tb[OPL], t1[OPL], t2[OPL], acc[OPL];
+    real a_new;                                               // ry[2 kp] of the newest (lowest) kp
+    {
+      real a[OPL + 1], b[OPL];
+      TRPL_UNROLL for (int jj = 0; jj < OPL; ++jj) {
+        const ivec kp = iadd(k0, jj - 1);
+        gather2(f.ry, imul(kp, 2), mand(kp >= 0, kp <= nk), 0.0, a[jj], b[jj]);
+      }
+      { const ivec kp = iadd(k0, OPL - 1); a[OPL] = gather(f.ry, imul(kp, 2), mand(kp >= 1, kp <= nk), 0.0); }
+      TRPL_UNROLL for (int jj = 0; jj < OPL; ++jj) {
+        const ivec kp = iadd(k0, jj - 1);
+        const mask ok = mand(kp >= 0, kp < nk);
+        tb[jj] = sel(ok, b[jj], 0.0);
+        t1[jj] = sel(ok, a[jj + 1] - a[jj], 0.0);
+        t2[jj] = sel(ok, 2.0 * ((a[jj + 1] - 2.0 * b[jj]) + a[jj]), 0.0);
+        acc[jj] = splat(0.0);
+      }
+      a_new = a[0];
     }
-    scatter(f.hk, k, take, acc);
-    // running argmax, first occurrence
-    const mask better = mand(take, acc > best);
-    best = sel(better, acc, best);
-    best_k = seli(better, k, best_k);
-    any_nan = mor(any_nan, mand(take, is_nan(acc)));
+    TRPL_UNROLL4 for (int m = 0; m < m_hi; ++m) {
+      const double m0 = f.mom[3 * m], m1 = f.mom[3 * m + 1], m2 = f.mom[3 * m + 2];
+      // the triple that enters at the next lag: kp = k0 - 2 - m (its load is in flight during the sums)
+      const ivec kpn = iadd(k0, -2 - m);
+      const mask okn = mand(kpn >= 0, kpn < nk);
+      real an, bn;
+      gather2(f.ry, imul(kpn, 2), mand(kpn >= 0, kpn <= nk), 0.0, an, bn);
+      TRPL_UNROLL for (int jj = 0; jj < OPL; ++jj)
+        acc[jj] = acc[jj] + fmadd(t2[jj], m2, fmadd(t1[jj], m1, tb[jj] * m0));
+      TRPL_UNROLL for (int jj = OPL - 1; jj > 0; --jj) { tb[jj] = tb[jj - 1]; t1[jj] = t1[jj - 1]; t2[jj] = t2[jj - 1]; }
+      tb[0] = sel(okn, bn, 0.0);
+      t1[0] = sel(okn, a_new - an, 0.0);
+      t2[0] = sel(okn, 2.0 * ((a_new - 2.0 * bn) + an), 0.0);
+      a_new = an;
+    }
+    TRPL_UNROLL for (int jj = 0; jj < OPL; ++jj) {
+      const ivec k = iadd(k0, jj);
+      const mask take = k <= nk;
+      scatter(f.hk, k, take, acc[jj]);
+      // running argmax, first occurrence (a lane's outputs ascend; ties across lanes: smallest k below)
+      const mask better = mand(take, acc[jj] > best);
+      best = sel(better, acc[jj], best);
+      best_k = seli(better, k, best_k);
+      any_nan = mor(any_nan, mand(take, is_nan(acc[jj])));
+    }
   }
   warp_sync();
   if (warp_any(any_nan)) return false;

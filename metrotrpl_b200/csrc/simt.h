@@ -34,6 +34,7 @@
 // ------------------------------------------------------------------------------------------
 #define TRPL_FN __device__ __forceinline__
 #define TRPL_UNROLL _Pragma("unroll")
+#define TRPL_UNROLL4 _Pragma("unroll 4")
 
 namespace simt {
 typedef double real;
@@ -52,6 +53,17 @@ TRPL_FN double lane0(real x) { return __shfl_sync(FULL, x, 0); }
 TRPL_FN real shfl_up(real x, int d) { return __shfl_up_sync(FULL, x, d); }     // from lane-d (own if out of range)
 TRPL_FN real shfl_down(real x, int d) { return __shfl_down_sync(FULL, x, d); } // from lane+d (own if out of range)
 TRPL_FN real shfl_idx(real x, int src) { return __shfl_sync(FULL, x, src); }
+// batched forms (one exchange in the two-warp vocabulary): N values from the previous / next lane,
+// both directions at once, two sums at once
+template <int N> TRPL_FN void nbr_up(const real (&x)[N], real (&y)[N]) {
+  TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = __shfl_up_sync(FULL, x[i], 1);
+}
+template <int N> TRPL_FN void nbr_down(const real (&x)[N], real (&y)[N]) {
+  TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = __shfl_down_sync(FULL, x[i], 1);
+}
+template <int NU, int ND> TRPL_FN void nbr_both(const real (&xu)[NU], real (&yu)[NU], const real (&xd)[ND], real (&yd)[ND]) {
+  nbr_up<NU>(xu, yu); nbr_down<ND>(xd, yd);
+}
 #else
 // ---- two-warp team: every cross-lane primitive is  [write mailbox] -> team barrier -> [read] ----
 // One barrier per primitive, no barrier after the read: a mailbox slot may therefore be written
@@ -63,8 +75,9 @@ TRPL_FN real shfl_idx(real x, int src) { return __shfl_sync(FULL, x, src); }
 // trajectory share one.
 typedef unsigned long long lanebits;
 constexpr int TEAM_SLOTS = 64;
+constexpr int TEAM_SLOT_VALUES = 8;
 TRPL_FN double* team_box(int slot) {
-  __shared__ double box[2][TEAM_SLOTS][2];               // [team of the CTA][slot][value]
+  __shared__ double box[2][TEAM_SLOTS][TEAM_SLOT_VALUES];   // [team of the CTA][slot][value]
   return &box[(threadIdx.x >> 6) & 1][slot][0];
 }
 TRPL_FN void team_bar() { asm volatile("bar.sync %0, 64;" :: "r"(1 + (int)((threadIdx.x >> 6) & 1)) : "memory"); }
@@ -98,6 +111,38 @@ template <int S> TRPL_FN real shfl_down_s(real x, int) {
   team_bar();
   if (tl == 31u) y = b[0];
   return y;
+}
+// batched forms: up to TEAM_SLOT_VALUES values cross the warp boundary behind ONE barrier
+template <int S, int NU, int ND>
+TRPL_FN void nbr_both_s(const real (&xu)[NU], real (&yu)[NU], const real (&xd)[ND], real (&yd)[ND]) {
+  static_assert(NU + ND <= TEAM_SLOT_VALUES, "mailbox slot too small");
+  volatile double* b = team_box(S);
+  const unsigned tl = threadIdx.x & 63u;
+  TRPL_UNROLL for (int i = 0; i < NU; ++i) yu[i] = __shfl_up_sync(FULL, xu[i], 1);
+  TRPL_UNROLL for (int i = 0; i < ND; ++i) yd[i] = __shfl_down_sync(FULL, xd[i], 1);
+  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < NU; ++i) b[i] = xu[i]; }
+  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < ND; ++i) b[NU + i] = xd[i]; }
+  team_bar();
+  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < NU; ++i) yu[i] = b[i]; }
+  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < ND; ++i) yd[i] = b[NU + i]; }
+}
+template <int S, int N> TRPL_FN void nbr_up_s(const real (&x)[N], real (&y)[N]) {
+  static_assert(N <= TEAM_SLOT_VALUES, "mailbox slot too small");
+  volatile double* b = team_box(S);
+  const unsigned tl = threadIdx.x & 63u;
+  TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = __shfl_up_sync(FULL, x[i], 1);
+  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < N; ++i) b[i] = x[i]; }
+  team_bar();
+  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = b[i]; }
+}
+template <int S, int N> TRPL_FN void nbr_down_s(const real (&x)[N], real (&y)[N]) {
+  static_assert(N <= TEAM_SLOT_VALUES, "mailbox slot too small");
+  volatile double* b = team_box(S);
+  const unsigned tl = threadIdx.x & 63u;
+  TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = __shfl_down_sync(FULL, x[i], 1);
+  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < N; ++i) b[i] = x[i]; }
+  team_bar();
+  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = b[i]; }
 }
 #endif
 TRPL_FN real sel(mask m, real a, real b) { return m ? a : b; }
@@ -157,6 +202,7 @@ TRPL_FN real warp_sum(real x) {
   TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
   return x;  // bit-identical on every lane (fp add is commutative)
 }
+TRPL_FN void warp_sum2(real& a, real& b) { a = warp_sum(a); b = warp_sum(b); }
 TRPL_FN real warp_max(real x) {
   TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
   return x;
@@ -180,6 +226,13 @@ template <int S> TRPL_FN real warp_sum_s(real x) {
   team_bar();
   return b[0] + b[1];
 }
+template <int S> TRPL_FN void warp_sum2_s(real& x, real& y) {
+  volatile double* b = team_box(S);
+  TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) { x += __shfl_xor_sync(FULL, x, o); y += __shfl_xor_sync(FULL, y, o); }
+  if ((threadIdx.x & 31u) == 0u) { const unsigned w = (threadIdx.x >> 5) & 1u; b[w] = x; b[2 + w] = y; }
+  team_bar();
+  x = b[0] + b[1]; y = b[2] + b[3];
+}
 template <int S> TRPL_FN real warp_max_s(real x) {
   volatile double* b = team_box(S);
   TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
@@ -202,6 +255,11 @@ template <int S> TRPL_FN real warp_scan_incl_s(real x) {
 }
 #endif
 TRPL_FN real gather(const double* p, ivec idx, mask m, double other) { return m ? p[idx] : other; }
+// p[idx], p[idx+1] in one 128-bit load (p + idx is 16-byte aligned: idx even, p a scratch slice)
+TRPL_FN void gather2(const double* p, ivec idx, mask m, double other, real& a, real& b) {
+  if (m) { const double2 v = *reinterpret_cast<const double2*>(p + idx); a = v.x; b = v.y; }
+  else { a = other; b = other; }
+}
 TRPL_FN void scatter(double* p, ivec idx, mask m, real v) { if (m) p[idx] = v; }
 TRPL_FN ivec iadd(ivec a, int b) { return a + b; }
 TRPL_FN ivec imul(ivec a, int b) { return a * b; }
@@ -327,6 +385,7 @@ template <int N> TRPL_FN void mem_st_pairs(const LaneTm& m, int p, const real* v
 #include <stdlib.h>
 #define TRPL_FN inline
 #define TRPL_UNROLL
+#define TRPL_UNROLL4
 
 namespace simt {
 constexpr int LANES = 32 * TRPL_TEAM;
@@ -368,6 +427,11 @@ inline double lane0(const real& x) { return x.v[0]; }
 inline real shfl_up(const real& x, int d) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = (i - d >= 0) ? x.v[i - d] : x.v[i]; return r; }
 inline real shfl_down(const real& x, int d) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = (i + d < LANES) ? x.v[i + d] : x.v[i]; return r; }
 inline real shfl_idx(const real& x, int s) { return real(x.v[s]); }
+template <int N> inline void nbr_up(const real (&x)[N], real (&y)[N]) { for (int i = 0; i < N; ++i) y[i] = shfl_up(x[i], 1); }
+template <int N> inline void nbr_down(const real (&x)[N], real (&y)[N]) { for (int i = 0; i < N; ++i) y[i] = shfl_down(x[i], 1); }
+template <int NU, int ND> inline void nbr_both(const real (&xu)[NU], real (&yu)[NU], const real (&xd)[ND], real (&yd)[ND]) {
+  nbr_up<NU>(xu, yu); nbr_down<ND>(xd, yd);
+}
 inline real sel3(const mask& m, const real& a, const real& b) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
 template <class A, class B> inline real sel(const mask& m, const A& a, const B& b) { return sel3(m, real(a), real(b)); }
 inline ivec seli(const mask& m, const ivec& a, const ivec& b) { ivec r; for (int i = 0; i < LANES; ++i) r.v[i] = m.v[i] ? a.v[i] : b.v[i]; return r; }
@@ -406,6 +470,7 @@ inline real warp_max(real x) {
   return x;
 }
 inline real warp_min(const real& x) { return -warp_max(-x); }
+inline void warp_sum2(real& a, real& b) { a = warp_sum(a); b = warp_sum(b); }
 inline real warp_scan_incl(real x) {
   // (two warps: a scan inside each warp, then the first warp's total onto the second, as on the device)
   for (int o = 1; o < 32; o <<= 1) { real y = x; for (int i = 0; i < LANES; ++i) if ((i & 31) >= o) y.v[i] = x.v[i] + x.v[i - o]; x = y; }
@@ -414,6 +479,9 @@ inline real warp_scan_incl(real x) {
 }
 inline real gather(const double* p, const ivec& idx, const mask& m, double other) {
   real r; for (int i = 0; i < LANES; ++i) r.v[i] = m.v[i] ? p[idx.v[i]] : other; return r;
+}
+inline void gather2(const double* p, const ivec& idx, const mask& m, double other, real& a, real& b) {
+  for (int i = 0; i < LANES; ++i) { a.v[i] = m.v[i] ? p[idx.v[i]] : other; b.v[i] = m.v[i] ? p[idx.v[i] + 1] : other; }
 }
 inline void scatter(double* p, const ivec& idx, const mask& m, const real& v) {
   for (int i = 0; i < LANES; ++i) if (m.v[i]) p[idx.v[i]] = v.v[i];
@@ -481,6 +549,12 @@ template <int S> inline real warp_sum_s(const real& x) { team_slot_check(S); ret
 template <int S> inline real warp_max_s(const real& x) { team_slot_check(S); return warp_max(x); }
 template <int S> inline real warp_min_s(const real& x) { team_slot_check(S); return warp_min(x); }
 template <int S> inline real warp_scan_incl_s(const real& x) { team_slot_check(S); return warp_scan_incl(x); }
+template <int S> inline void warp_sum2_s(real& a, real& b) { team_slot_check(S); warp_sum2(a, b); }
+template <int S, int N> inline void nbr_up_s(const real (&x)[N], real (&y)[N]) { team_slot_check(S); nbr_up<N>(x, y); }
+template <int S, int N> inline void nbr_down_s(const real (&x)[N], real (&y)[N]) { team_slot_check(S); nbr_down<N>(x, y); }
+template <int S, int NU, int ND> inline void nbr_both_s(const real (&xu)[NU], real (&yu)[NU], const real (&xd)[ND], real (&yd)[ND]) {
+  team_slot_check(S); nbr_both<NU, ND>(xu, yu, xd, yd);
+}
 #endif
 }  // namespace simt
 #endif
@@ -498,4 +572,8 @@ template <int S> inline real warp_scan_incl_s(const real& x) { team_slot_check(S
 #define warp_max(x) warp_max_s<TRPL_TEAM_SLOT>(x)
 #define warp_min(x) warp_min_s<TRPL_TEAM_SLOT>(x)
 #define warp_scan_incl(x) warp_scan_incl_s<TRPL_TEAM_SLOT>(x)
+#define warp_sum2 warp_sum2_s<TRPL_TEAM_SLOT>
+#define nbr_up nbr_up_s<TRPL_TEAM_SLOT>
+#define nbr_down nbr_down_s<TRPL_TEAM_SLOT>
+#define nbr_both nbr_both_s<TRPL_TEAM_SLOT>
 #endif

@@ -337,8 +337,9 @@ TRPL_FN void readout(const Coef& c, const NodeMask<NPL>& m, int meas_type, const
     dacc = dacc + sel(m.real_node[j], d, 0.0);
   }
   const double scale = (meas_type == MEAS_TRPL) ? c.ks * c.dx * 1e23 : Q_COULOMB * c.dx * 1e9;
-  val = uni(warp_sum(acc)) * scale;
-  dval = uni(warp_sum(dacc)) * scale;
+  warp_sum2(acc, dacc);
+  val = uni(acc) * scale;
+  dval = uni(dacc) * scale;
 }
 
 // ---- dense output: per-lane Hermite interpolation through logged step points -----------------
