@@ -83,7 +83,10 @@ TRPL_FN bool irf_convolve_trim(const double* times, const double* curve, int n_t
   // shifted by one output, so each lag costs one new 128-bit load and one new triple per lane instead
   // of two loads and one triple per OUTPUT (the pass was a quarter of the nx = 256 kernel).  Each
   // output still sums its lags in ascending order with the same operations: same bits as before.
-  constexpr int OPL = 4;
+#ifndef TRPL_IRF_OPL
+#define TRPL_IRF_OPL 4
+#endif
+  constexpr int OPL = TRPL_IRF_OPL;
   real best = splat(-DBL_MAX);
   ivec best_k = isplat(0x7fffffff);
   for (int kb = 0; kb <= nk; kb += OPL * LANES) {

@@ -379,7 +379,7 @@ def check_edges(backend):
     _, s, ns, cur = backend(prob, _capi.pack_params(st2, idx, units), _capi.default_aux(1, 2, [1.0] * 2),
                             _capi.make_opts(RTOL=1e-8, flags=_capi.OPT_NO_LIKELIHOOD), True)
     np.testing.assert_allclose(cur[0, :11], cur[0, 11:], rtol=1e-7)
-    # every nodes-per-lane instantiation, with padding: nx = 16 (1/lane), 200 (8/lane), 'traps' at 100 (4/lane)
+    # every nodes-per-lane instantiation, with padding: nx = 16 (1/lane), 200 (two-warp team, 4/lane), 'traps' at 100 (4/lane)
     for nx, model in ((16, "std"), (200, "std"), (100, "traps")):
         names_m = names + (["kC", "Nt", "tauE"] if model == "traps" else [])
         units_m = np.concatenate([units, [1e12, 1e-21, 1.0]]) if model == "traps" else units
@@ -479,6 +479,50 @@ def check_explicit_path(backend):
         okm = ref > 1e-6 * ref[0]
         np.testing.assert_allclose(mine[okm], ref[okm], rtol=2e-6)
     return {"explicit_steps": n_auto[0, :, 0].tolist(), "rosenbrock_steps": n_ros[0, :, 0].tolist()}
+
+
+def check_team_grids(backend):
+    """Grids of 129..256 nodes run on a team of two warps per trajectory (csrc/team_kernels.cu: 64
+    lanes x 4 nodes, 6-level reduction, values crossing the warp boundary through a mailbox).  Both
+    models, padding-free (nx = 256) and padded (nx = 160, 200) grids, TRPL and TRTS, the stiff
+    Rosenbrock path and the explicit Runge-Kutta path, against the oracle's LSODA at tight tolerances."""
+    names, units, idx = _known_units()
+    t = np.linspace(0, 60, 121)
+    out = {}
+    base = dict(BASE, n0=1e8, p0=3e15, ks=4.8e-11, tauN=511, tauP=871, Cn=4.4e-29, Cp=4.4e-29)
+    stiff = dict(base, mu_n=20, mu_p=20, Sf=10, Sb=10)
+    nonstiff = dict(base, mu_n=0, mu_p=0, Sf=0, Sb=0, tauN=4, tauP=6, p0=1e17)
+    for nx, model in ((256, "std"), (160, "std"), (200, "traps"), (256, "traps")):
+        names_m = names + (["kC", "Nt", "tauE"] if model == "traps" else [])
+        units_m = np.concatenate([units, [1e12, 1e-21, 1.0]]) if model == "traps" else units
+        idx_m = {n: i for i, n in enumerate(names_m)}
+        x = (np.arange(nx) + 0.5) * (1000.0 / nx)
+        ini = np.array([2e16 * np.exp(-x / 150.0), 5e15 * np.ones(nx)])
+        rows = [dict(stiff, kC=1e-8, Nt=1e15, tauE=50.0)]
+        if model == "std":
+            rows.append(dict(nonstiff, kC=1e-8, Nt=1e15, tauE=50.0))
+        st = np.array([[r[n] for n in names_m] for r in rows], dtype=float)
+        sim = {"lengths": [1000.0, 1000.0], "nx": [nx, nx], "meas_types": ["TRPL", "TRTS"], "num_meas": 2}
+        prob = _capi.pack_problem(sim, ini, [t, t], None, None, model=model)
+        _, s, ns, cur = backend(prob, _capi.pack_params(st, idx_m, units_m, model=model),
+                                _capi.default_aux(len(rows), 2, [1.0, 1.0]),
+                                _capi.make_opts(RTOL=1e-8, flags=_capi.OPT_NO_LIKELIHOOD), True)
+        assert not np.any(s & 7), s
+        if model == "std":
+            assert not np.any(s[0] & _capi.ST_EXPLICIT) and np.all(s[1] & _capi.ST_EXPLICIT), s
+        worst = 0.0
+        for r in range(len(rows)):
+            for m, meas in enumerate(("TRPL", "TRTS")):
+                g = orc.Grid(1000.0, nx, t, 4)
+                ref = orc.simulate(ini[m], g, st[r], idx_m, meas=meas, units=units_m, model=model,
+                                   RTOL=1e-10, ATOL=1e-16)
+                mine = cur[r, m * len(t):(m + 1) * len(t)]
+                ok = np.abs(ref) > 1e-6 * np.abs(ref[0])
+                err = float(np.max(np.abs(mine[ok] / ref[ok] - 1)))
+                worst = max(worst, err)
+        assert worst < 2e-6, (nx, model, worst)           # measured: 2e-7 (both models, every grid)
+        out[f"{model}_nx{nx}"] = {"max_rel_err": worst, "steps": ns[..., 0].tolist()}
+    return out
 
 
 def check_hmax_option(backend):

@@ -2,6 +2,8 @@
 
 These tests fail loudly if the library is missing or no device is present - there is no fallback.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -94,6 +96,51 @@ def test_ragged_and_fluence_inputs(ctx):
 
 def test_traps_model_with_irf_convolution_nx256(ctx):
     print(pc.check_traps_irf(make_backend(ctx)))
+
+
+def test_two_warp_team_grids_of_129_to_256_nodes(ctx):
+    print(pc.check_team_grids(make_backend(ctx)))
+
+
+def test_two_warp_team_is_deterministic_at_full_size(ctx):
+    """configs[3] size (traps + IRF, nx = 256): 1024 parameter sets x 2 curves through the two-warp
+    team kernel.  (a) Shuffling the sets permutes the results bit for bit - whichever team, SM and
+    neighbour a trajectory gets, and however the two warps of its team interleave at the mailbox;
+    (b) a second launch reproduces the first bit for bit; (c) a sample agrees with the host lock-step
+    build of the same source (64-lane vocabulary) to integrator tolerance."""
+    from tests.emu import emu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "traps_irf.npz"))
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    nx = int(g["nx"])
+    sim = {"lengths": list(g["lengths"]), "nx": [nx] * 2, "meas_types": ["TRPL"] * 2, "num_meas": 2}
+    prob = _capi.pack_problem(sim, g["inis"], [g["t"]] * 2, list(g["vals"]), list(g["uncs"]), model="traps",
+                              ini_mode="fluence", irf_convolution=[520, 520],
+                              irf_tables={520: (g["moments"], g["t_irf"])})
+    n_sets = 1024
+    rng = np.random.default_rng(7)
+    base = g["states"][rng.integers(0, len(g["states"]), n_sets)]
+    jit = np.ones_like(base)
+    act = [idx[n] for n in names if n not in ("n0", "eps", "Tm", "m")]
+    jit[:, act] = 10 ** rng.uniform(-0.1, 0.1, size=(n_sets, len(act)))
+    params = _capi.pack_params(base * jit, idx, g["units"], model="traps")
+    aux = _capi.default_aux(n_sets, 2, [1.0] * 2)
+    opts = _capi.make_opts(RTOL=1e-7)
+    ctx.set_problem(prob)
+    ll_a, st_a, ns_a, _ = ctx.loglik_batch(params, aux, opts)
+    ll_b, st_b, ns_b, _ = ctx.loglik_batch(params, aux, opts)
+    np.testing.assert_array_equal(ll_a, ll_b)
+    np.testing.assert_array_equal(ns_a, ns_b)
+    perm = rng.permutation(n_sets)
+    ll_p, st_p, ns_p, _ = ctx.loglik_batch(params[perm], aux[perm], opts)
+    np.testing.assert_array_equal(ll_p, ll_a[perm])
+    np.testing.assert_array_equal(ns_p, ns_a[perm])
+    np.testing.assert_array_equal(st_p, st_a[perm])
+    assert np.all(np.isfinite(ll_a[..., 0])) and not np.any(st_a & 7)
+    sel = np.arange(0, n_sets, 128)
+    ll_e, st_e, ns_e, _ = emu.loglik_batch(prob, params[sel], aux[sel], opts, True)
+    np.testing.assert_allclose(ll_a[sel], ll_e, rtol=1e-6)
+    assert np.abs(ns_a[sel][..., 0] - ns_e[..., 0]).max() <= 5
 
 
 def test_explicit_rk_path_for_nonstiff_trajectories(ctx):

@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 
-def main(rep, cubin, kernel_pat, top=40, depth_inner=False):
+def main(rep, cubin, kernel_pat, top=40, depth_inner=False, within=None):
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -44,7 +44,15 @@ def main(rep, cubin, kernel_pat, top=40, depth_inner=False):
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
             fresh = True
             outer = [c for c in chain if c[2] is not None and c[2].endswith(".cu")]
-            if depth_inner:
+            if within is not None:
+                # lines one frame below `within` (file:line of an outer frame): where that call spends its samples
+                names = [f"{c[0]}:{c[1]}" for c in chain]
+                if within in names:
+                    k = names.index(within)
+                    tags.append((chain[k - 1][0], chain[k - 1][1]) if k > 0 else (chain[0][0], chain[0][1]))
+                else:
+                    tags.append(("(elsewhere)", 0))
+            elif depth_inner:
                 tags.append((chain[0][0], chain[0][1]) if chain else ("?", 0))
             else:
                 tags.append((outer[-1][0], outer[-1][1]) if outer else ((chain[-1][0], chain[-1][1]) if chain else ("?", 0)))
@@ -78,4 +86,5 @@ def main(rep, cubin, kernel_pat, top=40, depth_inner=False):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40, "--inner" in sys.argv)
+    main(sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 40, "--inner" in sys.argv,
+         next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--within=")), None))
