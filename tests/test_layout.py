@@ -22,13 +22,15 @@ int main() { show<1,0>(); show<2,0>(); show<4,0>(); show<8,0>(); show<1,1>(); sh
 '''
 
 
-def layouts():
+def layouts(team=False):
+    """Layout rows of the one-warp instantiations, or (team) of the same source compiled with the
+    two-warp vocabulary (csrc/team_kernels.cu: only 4 nodes per lane is instantiated there)."""
     tmp = tempfile.mkdtemp()
     src = os.path.join(tmp, "slots.cpp")
     with open(src, "w") as f:
         f.write(PROGRAM % {"root": ROOT})
     exe = os.path.join(tmp, "slots")
-    subprocess.check_call(["g++", "-std=c++17", "-o", exe, src])
+    subprocess.check_call(["g++", "-std=c++17"] + (["-DTRPL_TEAM=2"] if team else []) + ["-o", exe, src])
     rows = []
     for line in subprocess.check_output([exe], text=True).strip().splitlines():
         v = [int(x) for x in line.split()]
@@ -65,3 +67,20 @@ def test_headline_instantiation_layout():
     assert r["pm_tm"] == 24 and r["pm_sm"] == 0 and r["k_tm_stages"] == 2
     assert r["tm_count"] == 64 and r["tm_cols"] == 256
     assert 8 * r["sm_bytes"] <= 227 * 1024          # eight trajectories per SM
+
+
+def test_two_warp_team_layout():
+    """nx = 129..256 (csrc/team_kernels.cu): each of the two warps holds 4 nodes per lane, so a warp's
+    tensor-memory slice is the headline kernel's 64 pairs (two CTAs = four trajectories per SM); the
+    reduced system has 64 rows, hence 6 PCR levels of multipliers (26 pairs + padding); a TEAM's
+    shared-memory slice is 64 lanes wide and four of them, plus the 8 KB mailbox, fit an SM."""
+    for model in (0, 1):
+        r = [x for x in layouts(team=True) if x["npl"] == 4 and x["model"] == model][0]
+        assert r["fac_in_tm"] == 1
+        assert r["tm_count"] <= 64 and r["tm_cols"] == 256            # two CTAs per SM
+        assert r["pm_tm"] + r["pm_sm"] in (26, 28) and r["pm_tm"] % 4 == 0
+        assert r["sm_bytes"] == r["sm_pairs"] * 1024                    # 64 lanes x 16 B per pair
+        assert r["kcap"] >= 7 * r["kstride"]
+        # two CTAs per SM, two teams per CTA, 8 KB of static mailbox + 1 KB reserved per CTA
+        assert 2 * (2 * r["sm_bytes"] + 8208 + 1024) <= 228 * 1024
+
