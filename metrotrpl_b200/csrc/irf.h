@@ -29,14 +29,29 @@ struct IrfDesc {
 
 // np.interp(x, xp, fp) for one x per lane, xp ascending, xp[0] <= x <= xp[n-1]
 TRPL_FN real interp_lanes(const double* xp, const double* fp, int n, const real& x, const mask& take) {
-  ivec lo = isplat(0), hi = isplat(n - 1);
-  // invariant xp[lo] <= x; find the largest such lo (uniform trip count)
-  for (int span = n; span > 1; span = (span + 1) >> 1) {
-    const ivec mid = ishr1(iaddv(iaddv(lo, hi), isplat(1)));
-    const real xm = gather(xp, mid, take, 0.0);
-    const mask le = xm <= x;
-    lo = seli(le, mid, lo);
-    hi = seli(le, hi, iadd(mid, -1));
+  ivec lo = isplat(0);
+  // Measurement times are usually equally spaced: guess the interval from the mean spacing and keep
+  // the guess if it brackets x (xp[g] <= x < xp[g+1], or g is the last interval); that IS the
+  // interval the search below would return.  Any miss nearby: everyone searches.
+  bool searched = n < 3;
+  if (!searched) {
+    const double inv = (double)(n - 1) / (xp[n - 1] - xp[0]);
+    const ivec g = iclamp(to_int_floor((x - xp[0]) * inv), 0, n - 2);
+    const real xg = gather(xp, g, take, 0.0), xg1 = gather(xp, iadd(g, 1), take, 1.0);
+    const mask hit = mand(xg <= x, mor(x < xg1, g == n - 2));
+    if (local_any(mand(take, mnot(hit)))) searched = true; else lo = g;
+  }
+  if (searched) {
+    ivec hi = isplat(n - 1);
+    lo = isplat(0);
+    // invariant xp[lo] <= x; find the largest such lo (uniform trip count)
+    for (int span = n; span > 1; span = (span + 1) >> 1) {
+      const ivec mid = ishr1(iaddv(iaddv(lo, hi), isplat(1)));
+      const real xm = gather(xp, mid, take, 0.0);
+      const mask le = xm <= x;
+      lo = seli(le, mid, lo);
+      hi = seli(le, hi, iadd(mid, -1));
+    }
   }
   lo = iclamp(lo, 0, n - 2 > 0 ? n - 2 : 0);
   const ivec lo1 = iadd(lo, n > 1 ? 1 : 0);

@@ -165,6 +165,9 @@ template <int S> TRPL_FN lanebits warp_ballot_s(mask m) {
 template <int S> TRPL_FN bool warp_any_s(mask m) { return warp_ballot_s<S>(m) != 0ull; }
 #endif
 TRPL_FN mask lane_lt(ivec l, int k) { return l < k; }
+// "does any lane near me see m": evaluated per hardware warp, no team barrier.  Only for choosing
+// between two code paths that give the same result and contain no cross-lane primitive.
+TRPL_FN bool local_any(mask m) { return __any_sync(FULL, m) != 0; }
 TRPL_FN real fmadd(real a, real b, real c) { return fma(a, b, c); }
 // Reciprocal: hardware seed (MUFU.RCP64H, ~2^-23) + two Newton steps, no special-case slow path.
 // Every argument on this path is a finite, normal, non-zero number (densities, determinants of
@@ -442,6 +445,7 @@ inline mask mconst(bool b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = b;
 inline bool warp_any(const mask& m) { for (int i = 0; i < LANES; ++i) if (m.v[i]) return true; return false; }
 inline lanebits warp_ballot(const mask& m) { lanebits b = 0; for (int i = 0; i < LANES; ++i) if (m.v[i]) b |= (1ull << i); return b; }
 inline mask lane_lt(const ivec& l, int k) { return l < k; }
+inline bool local_any(const mask& m) { for (int i = 0; i < LANES; ++i) if (m.v[i]) return true; return false; }
 inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
 template <class A, class B, class C> inline real fmadd(const A& a, const B& b, const C& c) { return fmadd3(real(a), real(b), real(c)); }
 inline real vdiv(const real& a, const real& b) { return a / b; }

@@ -448,6 +448,42 @@ def check_traps_irf(backend, curve_tol=CURVE_TOL_CLEAN):
     return rep
 
 
+def check_irf_uneven_times(backend):
+    """The IRF pass on measurement times that are NOT equally spaced (denser early, and a jittered
+    grid): resampling and trimming locate their interval by a guess from the mean spacing and fall
+    back to a search where the guess misses.  Our likelihood against the oracle's restatement of
+    laplace.py applied to our own curves: exact to rounding, as on the even grid."""
+    g = np.load(os.path.join(GOLDEN, "traps_irf.npz"))
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    t0 = g["t"]
+    nx = int(g["nx"])
+    tables = {520: (g["moments"], g["t_irf"])}
+    sim = {"lengths": list(g["lengths"]), "nx": [nx] * 2, "meas_types": ["TRPL"] * 2, "num_meas": 2}
+    rng = np.random.default_rng(3)
+    n = len(t0)
+    grids = {"power": t0[-1] * (np.arange(n) / (n - 1)) ** 1.4,
+             "jitter": np.concatenate([[0.0], np.sort(t0[1:-1] + rng.uniform(-0.1, 0.1, n - 2)), [t0[-1]]])}
+    rep = {}
+    params = _capi.pack_params(g["states"][:2], idx, g["units"], model="traps")
+    aux = _capi.default_aux(2, 2, [1.0] * 2)
+    for name, t in grids.items():
+        vals = [np.interp(t, t0, g["vals"][m]) for m in range(2)]
+        uncs = [np.interp(t, t0, g["uncs"][m]) for m in range(2)]
+        prob = _capi.pack_problem(sim, g["inis"], [t] * 2, vals, uncs, model="traps", ini_mode="fluence",
+                                  irf_convolution=[520, 520], irf_tables=tables)
+        ll, st, ns, cur = backend(prob, params, aux, _capi.make_opts(RTOL=1e-7), True)
+        cur = cur.reshape(2, 2, n)
+        worst = 0.0
+        for s_ in range(2):
+            chain = sum(orc.curve_loglik(cur[s_, m], t, t, vals[m], uncs[m], 1.0, irf_table=tables[520])
+                        for m in range(2))
+            worst = max(worst, abs(ll[s_, :, 0].sum() / chain - 1))
+        assert np.all(st == 0) and worst <= 1e-12, (name, worst, st)
+        rep[name] = worst
+    return rep
+
+
 def check_explicit_path(backend):
     """Non-stiff trajectories (no transport: the mobility-free cases of the reference's unit tests)
     are classified at t = 0 and integrated by the embedded explicit Runge-Kutta pair; the result must

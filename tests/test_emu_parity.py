@@ -43,6 +43,10 @@ def test_traps_model_with_irf_convolution_nx256():
     print(pc.check_traps_irf(backend))
 
 
+def test_irf_pass_on_uneven_measurement_times():
+    print(pc.check_irf_uneven_times(backend))
+
+
 def test_two_warp_team_grids_of_129_to_256_nodes():
     print(pc.check_team_grids(backend))
 
