@@ -183,7 +183,9 @@ struct Slots {
 #else
   static constexpr int TM_WANT = 64;
 #endif
-  // one CTA per SM (128 pairs) for the grids whose factor blocks alone exceed the two-CTA budget
+  // one CTA per SM (128 pairs) for the grids whose factor blocks alone exceed the two-CTA budget (8
+  // nodes per lane: no product kernel since the two-warp teams of team_kernels.cu, host lock-step
+  // instantiation of the generic extrapolation driver only)
   static constexpr int TM_BUDGET = (TM_WANT == 64 && FACP > 64) ? 128 : TM_WANT;
   // priority: factor blocks, then multipliers (whole levels; the rest stays in shared memory),
   // then stage increments, then the trap coefficients
