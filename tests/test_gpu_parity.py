@@ -147,6 +147,45 @@ def test_two_warp_team_is_deterministic_at_full_size(ctx):
     assert np.abs(ns_a[sel][..., 0] - ns_e[..., 0]).max() <= 5
 
 
+def test_two_warp_team_ladder_queue_order_and_min_y_floor(ctx):
+    """The options of the one-warp path through the team kernel (traps + IRF, nx = 256): the tempering
+    ladder equals the three temperature slots of a plain call, the per-chain ladder rows are their sums
+    over the curves, an explicit queue order changes nothing, and force_min_y is the host lock-step
+    build's to rounding."""
+    from tests.emu import emu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "traps_irf.npz"))
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    nx = int(g["nx"])
+    sim = {"lengths": list(g["lengths"]), "nx": [nx] * 2, "meas_types": ["TRPL"] * 2, "num_meas": 2}
+    prob = _capi.pack_problem(sim, g["inis"], [g["t"]] * 2, list(g["vals"]), list(g["uncs"]), model="traps",
+                              ini_mode="fluence", irf_convolution=[520, 520],
+                              irf_tables={520: (g["moments"], g["t_irf"])})
+    params = _capi.pack_params(g["states"], idx, g["units"], model="traps")
+    n = params.shape[0]
+    ctx.set_problem(prob)
+    opts = _capi.make_opts(RTOL=1e-7)
+    aux = _capi.default_aux(n, 2, [1.0] * 2, temps=(1.0, 2.0, 8.0))
+    ll, st, ns, cur = ctx.loglik_batch(params, aux, opts, want_curves=True)
+    ctx.set_ladder(np.array([1.0, 2.0, 8.0, 64.0]))
+    aux1 = _capi.default_aux(n, 2, [1.0] * 2, temps=(1.0, 1.0, 1.0))
+    ctx.loglik_batch(params, aux1, _capi.make_opts(RTOL=1e-7, flags=_capi.OPT_LADDER), want_curves=False)
+    lad = ctx.download_ladder(n)
+    np.testing.assert_allclose(lad[:, :, :3], ll, rtol=1e-12)
+    assert np.all(lad[:, :, 3] > lad[:, :, 2])
+    rows, _ = ctx.download_ladder_sums(n)
+    np.testing.assert_allclose(rows, lad.sum(axis=1), rtol=1e-14)
+    ctx.set_queue_order(np.random.default_rng(0).permutation(2 * n))
+    ll_p, st_p, ns_p, cur_p = ctx.loglik_batch(params, aux, opts, want_curves=True)
+    ctx.set_queue_order(None)
+    np.testing.assert_array_equal(ll_p, ll)
+    np.testing.assert_array_equal(cur_p, cur)
+    o_f = _capi.make_opts(RTOL=1e-7, flags=_capi.OPT_FORCE_MIN_Y)
+    ll_f, _, _, _ = ctx.loglik_batch(params, aux, o_f, want_curves=True)
+    ll_e, _, _, _ = emu.loglik_batch(prob, params, aux, o_f, True)
+    np.testing.assert_allclose(ll_f, ll_e, rtol=1e-6)
+
+
 def test_explicit_rk_path_for_nonstiff_trajectories(ctx):
     print(pc.check_explicit_path(make_backend(ctx)))
 
