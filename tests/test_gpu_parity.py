@@ -479,3 +479,27 @@ def test_step_log_flush_with_more_than_1024_steps(ctx, flags):
     np.testing.assert_allclose(np.where(in_range, capped[3], 1.0), np.where(in_range, T, 1.0), rtol=3e-5)
     ok = free[0][:, :, 0].sum(axis=1) > pc.LOGLL_FLOOR
     np.testing.assert_allclose(capped[0][ok], free[0][ok], rtol=2e-6)
+
+
+def test_step_log_flush_in_the_two_warp_team_kernel(ctx):
+    """The same flush at nx = 256 (traps + IRF): a 0.04 ns step cap forces ~2500 steps per curve, the
+    step log is flushed twice mid-run by the team's 64 lanes.  Same curves and likelihoods as the
+    uncapped run."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "traps_irf.npz"))
+    names = [str(n) for n in g["names"]]
+    idx = {n: i for i, n in enumerate(names)}
+    nx = int(g["nx"])
+    sim = {"lengths": list(g["lengths"]), "nx": [nx] * 2, "meas_types": ["TRPL"] * 2, "num_meas": 2}
+    prob = _capi.pack_problem(sim, g["inis"], [g["t"]] * 2, list(g["vals"]), list(g["uncs"]), model="traps",
+                              ini_mode="fluence", irf_convolution=[520, 520],
+                              irf_tables={520: (g["moments"], g["t_irf"])})
+    params = _capi.pack_params(g["states"][:2], idx, g["units"], model="traps")
+    aux = _capi.default_aux(2, 2, [1.0] * 2)
+    ctx.set_problem(prob)
+    free = ctx.loglik_batch(params, aux, _capi.make_opts(RTOL=1e-7), want_curves=True)
+    capped = ctx.loglik_batch(params, aux, _capi.make_opts(RTOL=1e-7, hmax=0.04, honor_hmax=True), want_curves=True)
+    assert capped[2][..., 0].min() > 2100 and free[2][..., 0].max() < 1024
+    np.testing.assert_allclose(capped[3], free[3], rtol=3e-5)
+    np.testing.assert_allclose(capped[0], free[0], rtol=2e-6)
+    assert not np.any(capped[1] & 7)
+
