@@ -356,13 +356,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: 4096 random parameter sets x 6 TRPL curves "
-                               "(staub_MAPI threepower_twothick), nx=128, std model, per GPU",
-                   "sets_per_gpu": args.sets, "curves_per_set": 6, "times_per_curve": int(len(t)),
-                   "rtol": args.rtol, "hmax": "not imposed: steps are error-controlled (the reference arm runs "
-                                              "LSODA with its own max_step = 4 ns)",
-                   "l2": "flushed between steps (256 MiB memset); inputs are 0.5 MB and L2-resident by design",
-                   "parallelism": f"independent parameter-set shards x{world}, no data-path collective"},
+        "config": workload_config(args, world, len(t)),
         "e2e": {"value": e2e_value, "unit": "sims/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(gpu_launches),
@@ -383,6 +377,17 @@ def run_ours(args):
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def workload_config(args, world, n_t):
+    """`config` of the JSON line: the workload the metric is quoted on.  Both arms print the same dict."""
+    return {"workload": "configs[1]: 4096 random parameter sets x 6 TRPL curves "
+                        "(staub_MAPI threepower_twothick), nx=128, std model, per GPU",
+            "sets_per_gpu": args.sets, "curves_per_set": 6, "times_per_curve": int(n_t),
+            "rtol": args.rtol, "hmax": "GPU arm: not imposed, steps are error-controlled; reference arm: LSODA "
+                                       "with the reference's own max_step = 4 ns (sim_utils.py:17)",
+            "l2": "GPU arm: flushed between steps (256 MiB memset); inputs are 0.5 MB and L2-resident by design",
+            "parallelism": f"independent parameter-set shards x{world}, no data-path collective"}
 
 
 CPU_DESCRIPTION = {
@@ -560,13 +565,15 @@ def run_reference(args):
            "unit": "sims/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "configs[1] sample: random parameter sets x 6 TRPL curves "
-                                  "(staub_MAPI threepower_twothick), nx=128, std model",
-                      "sets_per_step": per_step, "curves_per_set": 6, "times_per_curve": int(len(t)),
-                      "rtol": 1e-7, "atol": 1e-10, "hmax": "4 ns (the reference's LSODA max_step, sim_utils.py:17)",
-                      "parallelism": f"{cores} worker processes, work queue of single parameter sets"},
+           # the GPU arm's config, key for key (the workload both arms are quoted on); what this run
+           # did with it - a bounded sample per step on the host cores - is under `reference_run`
+           "config": workload_config(args, int(os.environ.get("WORLD_SIZE", "1")), len(t)),
+           "reference_run": {"sets_per_step": per_step, "rtol": 1e-7, "atol": 1e-10,
+                             "hmax": "4 ns (the reference's LSODA max_step, sim_utils.py:17)",
+                             "parallelism": f"{cores} worker processes, work queue of single parameter sets"},
            "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": cpu_kind(),
-                            "sample": f"{per_step} parameter sets x 6 curves per step, " + CPU_DESCRIPTION[cpu_kind()]},
+                            "sample": f"{per_step} of the workload's parameter sets x 6 curves per step (the first "
+                                      f"ones of the same seeded list), " + CPU_DESCRIPTION[cpu_kind()]},
            "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
