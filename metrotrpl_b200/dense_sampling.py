@@ -17,6 +17,17 @@ from .utils import search_c_grps
 
 DEFAULT_BLOCK = 16384     # parameter sets per launch: the tail of a launch is amortised (5% over 4096)
 
+_SECOND_CTX = {}          # device -> the second context of the block pipeline (kept for the process)
+
+
+def _second_context(device):
+    """The pipeline's second context (stream + device buffers), created once per device: creating
+    and destroying it on every call cost up to 0.4 s (cudaFree of its buffers) per simulate()."""
+    from . import _capi
+    if device not in _SECOND_CTX:
+        _SECOND_CTX[device] = _capi.Context(device)
+    return _SECOND_CTX[device]
+
 
 def random_grid(min_X, max_X, do_log, num_samples):
     """Uniform (or log-uniform) draws inside the box, column by column (dense_sampling.py:17-35)."""
@@ -78,7 +89,7 @@ def simulate(e_data, P, X, param_info, sim_params, init_params, sim_flags, logge
         from .forward_solver import get_context
         from .trial_move_evaluation import PathCache
         dev = get_context(comm.local_rank).device
-        caches = [PathCache(sf, device=dev), PathCache(sf, ctx=_capi.Context(dev))]
+        caches = [PathCache(sf, device=dev), PathCache(sf, ctx=_second_context(dev))]
         pending = [None, None]
 
         def collect(k):
@@ -88,24 +99,21 @@ def simulate(e_data, P, X, param_info, sim_params, init_params, sim_flags, logge
             local[b0 - lo:b1 - lo] = np.where(np.isnan(ll), -np.inf, ll)
             pending[k] = None
 
-        try:
-            for i, (b0, b1) in enumerate(blocks):
-                k = i % 2
-                if pending[k] is not None:
-                    collect(k)
-                if logger is not None:
-                    logger.info(f"Rank {comm.rank}: samples {b0}..{b1} of {n}")
-                c = caches[k]
-                params, aux = c.pack(X[b0:b1], sigmas, np.ones((b1 - b0, 3)))
-                c.ctx.set_problem_if_needed(c.prob)
-                c.ctx.upload(params, aux)
-                c.ctx.run_resident(c.opts())
-                pending[k] = (b0, b1)
-            for k in ((len(blocks)) % 2, (len(blocks) + 1) % 2):       # oldest first
-                if pending[k] is not None:
-                    collect(k)
-        finally:
-            caches[1].ctx.close()                                      # the private second context
+        for i, (b0, b1) in enumerate(blocks):
+            k = i % 2
+            if pending[k] is not None:
+                collect(k)
+            if logger is not None:
+                logger.info(f"Rank {comm.rank}: samples {b0}..{b1} of {n}")
+            c = caches[k]
+            params, aux = c.pack(X[b0:b1], sigmas, np.ones((b1 - b0, 3)))
+            c.ctx.set_problem_if_needed(c.prob)
+            c.ctx.upload(params, aux)
+            c.ctx.run_resident(c.opts())
+            pending[k] = (b0, b1)
+        for k in ((len(blocks)) % 2, (len(blocks) + 1) % 2):       # oldest first
+            if pending[k] is not None:
+                collect(k)
     else:
         for b0, b1 in blocks:
             if logger is not None:
