@@ -69,7 +69,7 @@ typedef struct trpl_meas_desc {
   double thickness;   /* nm */
   double ini_a;       /* fluence mode: fluence [cm^-2] */
   double ini_b;       /* fluence mode: absorption coefficient [cm^-1] */
-  int32_t nx;         /* space nodes, 2..256 */
+  int32_t nx;         /* space nodes, 2..512 */
   int32_t meas_type;  /* trpl_meas_type */
   int32_t ini_mode;   /* trpl_ini_mode */
   int32_t ini_dir;    /* fluence mode: <0 reverses the profile */

@@ -15,17 +15,18 @@
 #include <stdint.h>
 
 // TRPL_TEAM: warps that integrate one trajectory together.  1 (default): the one-warp vocabulary
-// described above.  2: a TEAM of two warps is the "wide warp" - 64 lanes, lane_id() 0..63 - and
-// every cross-lane primitive spans both warps: shuffles between neighbours hand the one value that
-// crosses the warp boundary through a shared-memory mailbox, reductions combine the two warps'
-// partials there, warp_sync() is a named barrier of the team's 64 threads.  The integrator source
-// is the same; team_kernels.cu compiles it a second time with this vocabulary for the grids of more
-// than 128 nodes (4 nodes per lane instead of 8: the state fits the register file again).
+// described above.  2 or 4: a TEAM of that many warps is the "wide warp" - 64 or 128 lanes, lane_id()
+// 0..LANES-1 - and every cross-lane primitive spans all its warps: shuffles between neighbours hand
+// the one value that crosses each warp boundary through a shared-memory mailbox, reductions combine
+// the warps' partials there in a fixed order, warp_sync() is a named barrier of the team's threads.
+// The integrator source is the same; team_kernels.cu / team4_kernels.cu compile it again with this
+// vocabulary for the grids of 129..256 / 257..512 nodes (4 nodes per lane: the state fits the
+// register file, where one warp with 8 or 16 nodes per lane spills).
 #ifndef TRPL_TEAM
 #define TRPL_TEAM 1
 #endif
-#if TRPL_TEAM != 1 && TRPL_TEAM != 2
-#error "TRPL_TEAM must be 1 or 2"
+#if TRPL_TEAM != 1 && TRPL_TEAM != 2 && TRPL_TEAM != 4
+#error "TRPL_TEAM must be 1, 2 or 4"
 #endif
 
 #if defined(__CUDACC__) && !defined(TRPL_HOST_EMU)
@@ -42,7 +43,7 @@ typedef bool mask;
 typedef int ivec;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int LANES = 32 * TRPL_TEAM;            // lanes of the (wide) warp that owns a trajectory
-constexpr int LOG2_LANES = TRPL_TEAM == 2 ? 6 : 5;
+constexpr int LOG2_LANES = TRPL_TEAM == 4 ? 7 : TRPL_TEAM == 2 ? 6 : 5;
 
 TRPL_FN ivec lane_id() { return (int)(threadIdx.x & (unsigned)(LANES - 1)); }
 TRPL_FN real splat(double x) { return x; }
@@ -65,84 +66,87 @@ template <int NU, int ND> TRPL_FN void nbr_both(const real (&xu)[NU], real (&yu)
   nbr_up<NU>(xu, yu); nbr_down<ND>(xd, yd);
 }
 #else
-// ---- two-warp team: every cross-lane primitive is  [write mailbox] -> team barrier -> [read] ----
+// ---- team of W = TRPL_TEAM warps: every cross-lane primitive is  [write mailbox] -> team barrier -> [read] ----
 // One barrier per primitive, no barrier after the read: a mailbox slot may therefore be written
 // again only after ANOTHER team primitive (whose barrier every reader has reached) has run in
 // between.  Every CALL SITE has a slot of its own (the macros at the end of this file hand out
-// __COUNTER__; team_kernels.cu asserts that there are at most TEAM_SLOTS sites), so only a site
+// __COUNTER__; the kernel units assert that there are at most TEAM_SLOTS sites), so only a site
 // that runs twice in a row with no other team primitive in between could collide; the host
 // lock-step build runs the same slot numbers and aborts if two consecutive primitives of a
-// trajectory share one.
+// trajectory share one.  A CTA is always four warps (one per tensor-memory lane quarter): two teams
+// of two warps, or one team of four.
+#if TRPL_TEAM == 4
+typedef unsigned __int128 lanebits;
+#else
 typedef unsigned long long lanebits;
+#endif
+constexpr int TEAM_WARPS = TRPL_TEAM;
+constexpr int TEAMS_PER_CTA = 4 / TRPL_TEAM;
 constexpr int TEAM_SLOTS = 64;
-constexpr int TEAM_SLOT_VALUES = 8;
+constexpr int TEAM_SLOT_VALUES = 8;                                        // values per warp boundary and slot
+constexpr int TEAM_SLOT_DOUBLES = TEAM_SLOT_VALUES * (TEAM_WARPS - 1);     // (reductions use 2 per warp: <= 8)
+TRPL_FN unsigned team_index() { return (threadIdx.x / (unsigned)LANES) & (unsigned)(TEAMS_PER_CTA - 1); }
+TRPL_FN unsigned team_warp() { return (threadIdx.x >> 5) & (unsigned)(TEAM_WARPS - 1); }   // warp within its team
 TRPL_FN double* team_box(int slot) {
-  __shared__ double box[2][TEAM_SLOTS][TEAM_SLOT_VALUES];   // [team of the CTA][slot][value]
-  return &box[(threadIdx.x >> 6) & 1][slot][0];
+  __shared__ double box[TEAMS_PER_CTA][TEAM_SLOTS][TEAM_SLOT_DOUBLES];
+  return &box[team_index()][slot][0];
 }
-TRPL_FN void team_bar() { asm volatile("bar.sync %0, 64;" :: "r"(1 + (int)((threadIdx.x >> 6) & 1)) : "memory"); }
+TRPL_FN void team_bar() { asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)team_index()), "n"(LANES) : "memory"); }
 template <int S> TRPL_FN double lane0_s(real x) {
   volatile double* b = team_box(S);
-  if ((threadIdx.x & 63u) == 0u) b[0] = x;
+  if ((threadIdx.x & (unsigned)(LANES - 1)) == 0u) b[0] = x;
   team_bar();
   return b[0];
 }
 template <int S> TRPL_FN real shfl_idx_s(real x, int src) {
   volatile double* b = team_box(S);
-  if ((int)(threadIdx.x & 63u) == src) b[0] = x;
+  if ((int)(threadIdx.x & (unsigned)(LANES - 1)) == src) b[0] = x;
   team_bar();
   return b[0];
 }
-// neighbour shuffles: distance 1 only (all the integrator uses); lane 31 -> 32 and back through the mailbox
-template <int S> TRPL_FN real shfl_up_s(real x, int) {
-  volatile double* b = team_box(S);
-  real y = __shfl_up_sync(FULL, x, 1);
-  const unsigned tl = threadIdx.x & 63u;
-  if (tl == 31u) b[0] = x;
-  team_bar();
-  if (tl == 32u) y = b[0];
-  return y;
-}
-template <int S> TRPL_FN real shfl_down_s(real x, int) {
-  volatile double* b = team_box(S);
-  real y = __shfl_down_sync(FULL, x, 1);
-  const unsigned tl = threadIdx.x & 63u;
-  if (tl == 32u) b[0] = x;
-  team_bar();
-  if (tl == 31u) y = b[0];
-  return y;
-}
-// batched forms: up to TEAM_SLOT_VALUES values cross the warp boundary behind ONE barrier
+// Neighbour exchanges (distance 1, all the integrator uses): the hardware shuffle inside each warp;
+// the value that crosses a warp boundary goes from lane 31 of warp w to lane 0 of warp w+1 (or back)
+// through that boundary's part of the slot.  Up to TEAM_SLOT_VALUES values behind ONE barrier.
 template <int S, int NU, int ND>
 TRPL_FN void nbr_both_s(const real (&xu)[NU], real (&yu)[NU], const real (&xd)[ND], real (&yd)[ND]) {
   static_assert(NU + ND <= TEAM_SLOT_VALUES, "mailbox slot too small");
   volatile double* b = team_box(S);
-  const unsigned tl = threadIdx.x & 63u;
+  const unsigned wl = threadIdx.x & 31u, w = team_warp();
   TRPL_UNROLL for (int i = 0; i < NU; ++i) yu[i] = __shfl_up_sync(FULL, xu[i], 1);
   TRPL_UNROLL for (int i = 0; i < ND; ++i) yd[i] = __shfl_down_sync(FULL, xd[i], 1);
-  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < NU; ++i) b[i] = xu[i]; }
-  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < ND; ++i) b[NU + i] = xd[i]; }
+  if (wl == 31u && w + 1u < (unsigned)TEAM_WARPS) { TRPL_UNROLL for (int i = 0; i < NU; ++i) b[w * TEAM_SLOT_VALUES + i] = xu[i]; }
+  if (wl == 0u && w > 0u) { TRPL_UNROLL for (int i = 0; i < ND; ++i) b[(w - 1u) * TEAM_SLOT_VALUES + NU + i] = xd[i]; }
   team_bar();
-  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < NU; ++i) yu[i] = b[i]; }
-  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < ND; ++i) yd[i] = b[NU + i]; }
+  if (wl == 0u && w > 0u) { TRPL_UNROLL for (int i = 0; i < NU; ++i) yu[i] = b[(w - 1u) * TEAM_SLOT_VALUES + i]; }
+  if (wl == 31u && w + 1u < (unsigned)TEAM_WARPS) { TRPL_UNROLL for (int i = 0; i < ND; ++i) yd[i] = b[w * TEAM_SLOT_VALUES + NU + i]; }
 }
 template <int S, int N> TRPL_FN void nbr_up_s(const real (&x)[N], real (&y)[N]) {
   static_assert(N <= TEAM_SLOT_VALUES, "mailbox slot too small");
   volatile double* b = team_box(S);
-  const unsigned tl = threadIdx.x & 63u;
+  const unsigned wl = threadIdx.x & 31u, w = team_warp();
   TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = __shfl_up_sync(FULL, x[i], 1);
-  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < N; ++i) b[i] = x[i]; }
+  if (wl == 31u && w + 1u < (unsigned)TEAM_WARPS) { TRPL_UNROLL for (int i = 0; i < N; ++i) b[w * TEAM_SLOT_VALUES + i] = x[i]; }
   team_bar();
-  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = b[i]; }
+  if (wl == 0u && w > 0u) { TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = b[(w - 1u) * TEAM_SLOT_VALUES + i]; }
 }
 template <int S, int N> TRPL_FN void nbr_down_s(const real (&x)[N], real (&y)[N]) {
   static_assert(N <= TEAM_SLOT_VALUES, "mailbox slot too small");
   volatile double* b = team_box(S);
-  const unsigned tl = threadIdx.x & 63u;
+  const unsigned wl = threadIdx.x & 31u, w = team_warp();
   TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = __shfl_down_sync(FULL, x[i], 1);
-  if (tl == 32u) { TRPL_UNROLL for (int i = 0; i < N; ++i) b[i] = x[i]; }
+  if (wl == 0u && w > 0u) { TRPL_UNROLL for (int i = 0; i < N; ++i) b[(w - 1u) * TEAM_SLOT_VALUES + i] = x[i]; }
   team_bar();
-  if (tl == 31u) { TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = b[i]; }
+  if (wl == 31u && w + 1u < (unsigned)TEAM_WARPS) { TRPL_UNROLL for (int i = 0; i < N; ++i) y[i] = b[w * TEAM_SLOT_VALUES + i]; }
+}
+template <int S> TRPL_FN real shfl_up_s(real x, int) {
+  const real in[1] = {x}; real out[1];
+  nbr_up_s<S, 1>(in, out);
+  return out[0];
+}
+template <int S> TRPL_FN real shfl_down_s(real x, int) {
+  const real in[1] = {x}; real out[1];
+  nbr_down_s<S, 1>(in, out);
+  return out[0];
 }
 #endif
 TRPL_FN real sel(mask m, real a, real b) { return m ? a : b; }
@@ -158,11 +162,13 @@ TRPL_FN lanebits warp_ballot(mask m) { return __ballot_sync(FULL, m); }
 template <int S> TRPL_FN lanebits warp_ballot_s(mask m) {
   volatile double* b = team_box(S);
   const unsigned mine = __ballot_sync(FULL, m);
-  if ((threadIdx.x & 31u) == 0u) b[(threadIdx.x >> 5) & 1u] = (double)mine;      // exact: < 2^32
+  if ((threadIdx.x & 31u) == 0u) b[team_warp()] = (double)mine;      // exact: < 2^32
   team_bar();
-  return (lanebits)(unsigned)b[0] | ((lanebits)(unsigned)b[1] << 32);
+  lanebits r = 0;
+  TRPL_UNROLL for (int w = 0; w < TEAM_WARPS; ++w) r |= (lanebits)(unsigned)b[w] << (32 * w);
+  return r;
 }
-template <int S> TRPL_FN bool warp_any_s(mask m) { return warp_ballot_s<S>(m) != 0ull; }
+template <int S> TRPL_FN bool warp_any_s(mask m) { return warp_ballot_s<S>(m) != 0u; }
 #endif
 TRPL_FN mask lane_lt(ivec l, int k) { return l < k; }
 // "does any lane near me see m": evaluated per hardware warp, no team barrier.  Only for choosing
@@ -220,28 +226,33 @@ TRPL_FN real warp_scan_incl(real x) {
   return x;
 }
 #else
-// reductions: each warp reduces with shuffles, the two partials meet in the mailbox and both warps
-// add them in the same order (identical bits on all 64 lanes: control flow stays team-uniform)
+// reductions: each warp reduces with shuffles, the partials meet in the mailbox and every warp
+// combines them in the same order (identical bits on all lanes: control flow stays team-uniform)
+TRPL_FN double team_combine_sum(volatile double* b) {
+  if constexpr (TEAM_WARPS == 2) return b[0] + b[1]; else return (b[0] + b[1]) + (b[2] + b[3]);
+}
 template <int S> TRPL_FN real warp_sum_s(real x) {
   volatile double* b = team_box(S);
   TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-  if ((threadIdx.x & 31u) == 0u) b[(threadIdx.x >> 5) & 1u] = x;
+  if ((threadIdx.x & 31u) == 0u) b[team_warp()] = x;
   team_bar();
-  return b[0] + b[1];
+  return team_combine_sum(b);
 }
 template <int S> TRPL_FN void warp_sum2_s(real& x, real& y) {
   volatile double* b = team_box(S);
   TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) { x += __shfl_xor_sync(FULL, x, o); y += __shfl_xor_sync(FULL, y, o); }
-  if ((threadIdx.x & 31u) == 0u) { const unsigned w = (threadIdx.x >> 5) & 1u; b[w] = x; b[2 + w] = y; }
+  if ((threadIdx.x & 31u) == 0u) { const unsigned w = team_warp(); b[w] = x; b[TEAM_WARPS + w] = y; }
   team_bar();
-  x = b[0] + b[1]; y = b[2] + b[3];
+  x = team_combine_sum(b); y = team_combine_sum(b + TEAM_WARPS);
 }
 template <int S> TRPL_FN real warp_max_s(real x) {
   volatile double* b = team_box(S);
   TRPL_UNROLL for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(FULL, x, o));
-  if ((threadIdx.x & 31u) == 0u) b[(threadIdx.x >> 5) & 1u] = x;
+  if ((threadIdx.x & 31u) == 0u) b[team_warp()] = x;
   team_bar();
-  return fmax(b[0], b[1]);
+  real r = fmax(b[0], b[1]);
+  if constexpr (TEAM_WARPS == 4) r = fmax(r, fmax(b[2], b[3]));
+  return r;
 }
 template <int S> TRPL_FN real warp_min_s(real x) { return -warp_max_s<S>(-x); }
 template <int S> TRPL_FN real warp_scan_incl_s(real x) {
@@ -251,9 +262,13 @@ template <int S> TRPL_FN real warp_scan_incl_s(real x) {
     real y = __shfl_up_sync(FULL, x, o);
     if (l >= o) x += y;
   }
-  if ((threadIdx.x & 63u) == 31u) b[0] = x;               // total of the first warp
+  const unsigned w = team_warp();
+  if (l == 31) b[w] = x;                                   // total of this warp
   team_bar();
-  if (threadIdx.x & 32u) x += b[0];
+  // totals of the warps before this one, added up in warp order
+  real off = 0.0;
+  TRPL_UNROLL for (int k = 0; k + 1 < TEAM_WARPS; ++k) if ((unsigned)k < w) off = (k == 0) ? (real)b[0] : off + b[k];
+  if (w > 0u) x += off;
   return x;
 }
 #endif
@@ -392,8 +407,12 @@ template <int N> TRPL_FN void mem_st_pairs(const LaneTm& m, int p, const real* v
 
 namespace simt {
 constexpr int LANES = 32 * TRPL_TEAM;
-constexpr int LOG2_LANES = TRPL_TEAM == 2 ? 6 : 5;
+constexpr int LOG2_LANES = TRPL_TEAM == 4 ? 7 : TRPL_TEAM == 2 ? 6 : 5;
+#if TRPL_TEAM == 4
+typedef unsigned __int128 lanebits;
+#else
 typedef unsigned long long lanebits;
+#endif
 struct real {
   double v[LANES];
   real() {}
@@ -443,7 +462,7 @@ inline mask mor(const mask& a, const mask& b) { mask r; for (int i = 0; i < LANE
 inline mask mnot(const mask& a) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = !a.v[i]; return r; }
 inline mask mconst(bool b) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = b; return r; }
 inline bool warp_any(const mask& m) { for (int i = 0; i < LANES; ++i) if (m.v[i]) return true; return false; }
-inline lanebits warp_ballot(const mask& m) { lanebits b = 0; for (int i = 0; i < LANES; ++i) if (m.v[i]) b |= (1ull << i); return b; }
+inline lanebits warp_ballot(const mask& m) { lanebits b = 0; for (int i = 0; i < LANES; ++i) if (m.v[i]) b |= ((lanebits)1 << i); return b; }
 inline mask lane_lt(const ivec& l, int k) { return l < k; }
 inline bool local_any(const mask& m) { for (int i = 0; i < LANES; ++i) if (m.v[i]) return true; return false; }
 inline real fmadd3(const real& a, const real& b, const real& c) { real r; for (int i = 0; i < LANES; ++i) r.v[i] = fma(a.v[i], b.v[i], c.v[i]); return r; }
@@ -463,8 +482,11 @@ template <class A, class B> inline real vmin(const A& a, const B& b) { return vm
 inline mask is_nan(const real& x) { mask r; for (int i = 0; i < LANES; ++i) r.v[i] = (x.v[i] != x.v[i]); return r; }
 inline real warp_sum(real x) {
   for (int o = 16; o > 0; o >>= 1) { real y; for (int i = 0; i < LANES; ++i) y.v[i] = x.v[i] + x.v[i ^ o]; x = y; }
+  // several warps: the device build's order - each warp's partial, then (p0 + p1) [+ (p2 + p3)]
 #if TRPL_TEAM == 2
-  return real(x.v[0] + x.v[32]);       // the device build's order: first warp's partial + second warp's
+  return real(x.v[0] + x.v[32]);
+#elif TRPL_TEAM == 4
+  return real((x.v[0] + x.v[32]) + (x.v[64] + x.v[96]));
 #else
   return x;
 #endif
@@ -478,7 +500,15 @@ inline void warp_sum2(real& a, real& b) { a = warp_sum(a); b = warp_sum(b); }
 inline real warp_scan_incl(real x) {
   // (two warps: a scan inside each warp, then the first warp's total onto the second, as on the device)
   for (int o = 1; o < 32; o <<= 1) { real y = x; for (int i = 0; i < LANES; ++i) if ((i & 31) >= o) y.v[i] = x.v[i] + x.v[i - o]; x = y; }
-  if (LANES > 32) { const double tot = x.v[31]; for (int i = 32; i < LANES; ++i) x.v[i] += tot; }
+  if (LANES > 32) {
+    double tot[LANES / 32];
+    for (int w = 0; w < LANES / 32; ++w) tot[w] = x.v[32 * w + 31];
+    for (int w = 1; w < LANES / 32; ++w) {
+      double off = tot[0];
+      for (int k = 1; k < w; ++k) off = off + tot[k];
+      for (int i = 32 * w; i < 32 * w + 32; ++i) x.v[i] += off;
+    }
+  }
   return x;
 }
 inline real gather(const double* p, const ivec& idx, const mask& m, double other) {
@@ -517,7 +547,7 @@ struct LaneMem {
   double uld(int p, int i) const { return slots.at(2 * p + (i & 1)).v[i >> 1]; }
   void ust(int p, int i, double v) { slots.at(2 * p + (i & 1)).v[i >> 1] = v; }
 };
-#if TRPL_TEAM == 2
+#if TRPL_TEAM >= 2
 inline void team_other_sync();
 inline void warp_sync() { team_other_sync(); }
 #else
@@ -534,7 +564,7 @@ template <class M> inline void mem_wait_ld(const M&) {}
 template <class M> inline void mem_wait_st(const M&) {}
 template <int N, class M> inline void mem_ld_pairs(const M& m, int p, real* v) { for (int i = 0; i < N; ++i) m.ld2(p + i, v[2 * i], v[2 * i + 1]); }
 template <int N, class M> inline void mem_st_pairs(M& m, int p, const real* v) { for (int i = 0; i < N; ++i) m.st2(p + i, v[2 * i], v[2 * i + 1]); }
-#if TRPL_TEAM == 2
+#if TRPL_TEAM >= 2
 // The device build's mailbox discipline, checked: two consecutive team primitives of a trajectory
 // must not use the same mailbox slot (see the device half).  Slot numbers come from the same macros.
 inline int& team_last_slot() { static thread_local int last = -1; return last; }
@@ -563,7 +593,7 @@ template <int S, int NU, int ND> inline void nbr_both_s(const real (&xu)[NU], re
 }  // namespace simt
 #endif
 
-#if TRPL_TEAM == 2
+#if TRPL_TEAM >= 2
 // One mailbox slot per call site (see the device half of the team vocabulary).
 #define TRPL_TEAM_SLOT (__COUNTER__ & 63)
 #define lane0(x) lane0_s<TRPL_TEAM_SLOT>(x)

@@ -331,17 +331,23 @@ int launch(trpl_handle* h, KernelArgs a) {
   return 0;
 }
 
-// Grids of 129..256 nodes: a team of two warps per trajectory, compiled in team_kernels.cu against
-// the two-warp vocabulary of simt.h (4 nodes per lane on 64 lanes).  Same queue, same arguments, same
-// per-trajectory scratch as launch<>; a CTA of four warps holds two trajectories.
+// Grids of 129..256 / 257..512 nodes: a team of two / four warps per trajectory, compiled in
+// team_kernels.cu / team4_kernels.cu against the team vocabularies of simt.h (4 nodes per lane on 64 /
+// 128 lanes).  Same queue, same arguments, same per-trajectory scratch as launch<>; a CTA of four
+// warps holds two trajectories, or one.
 extern "C" void trpl_team_plan(int model, size_t* smem, int* tm_cols, int* teams_per_cta);
 extern "C" int trpl_team_run(int model, int full, const void* args, size_t args_size, int grid, size_t smem,
                              void* stream, int explicit_pass);
+extern "C" void trpl_team4_plan(int model, size_t* smem, int* tm_cols, int* teams_per_cta);
+extern "C" int trpl_team4_run(int model, int full, const void* args, size_t args_size, int grid, size_t smem,
+                              void* stream, int explicit_pass);
 
-int launch_team(trpl_handle* h, KernelArgs a) {
+int launch_team(trpl_handle* h, KernelArgs a, int team_warps) {
   size_t smem = 0;
   int cols = 0, tpc = 1;
-  trpl_team_plan(h->model, &smem, &cols, &tpc);
+  const auto plan = team_warps == 4 ? trpl_team4_plan : trpl_team_plan;
+  const auto run = team_warps == 4 ? trpl_team4_run : trpl_team_run;
+  plan(h->model, &smem, &cols, &tpc);
   if (smem > (size_t)h->prop.sharedMemPerBlockOptin) return fail("trajectory state does not fit in shared memory");
   const int by_smem = (int)((size_t)h->prop.sharedMemPerMultiprocessor / (smem + 1024 + 16));
   int per_sm = std::min(CTAS_PER_SM, by_smem);
@@ -351,8 +357,8 @@ int launch_team(trpl_handle* h, KernelArgs a) {
   int grid = std::min(h->prop.multiProcessorCount * per_sm, (a.n_traj + tpc - 1) / tpc);
   if (grid < 1) grid = 1;
   if (getenv("TRPL_DEBUG"))
-    fprintf(stderr, "[trpl] launch two-warp teams, model=%d full=%d: %d teams/CTA, %zu B smem/CTA, %d TMEM columns/CTA, %d CTAs/SM, grid %d\n",
-            h->model, (int)h->all_full, tpc, smem, cols, per_sm, grid);
+    fprintf(stderr, "[trpl] launch %d-warp teams, model=%d full=%d: %d teams/CTA, %zu B smem/CTA, %d TMEM columns/CTA, %d CTAs/SM, grid %d\n",
+            team_warps, h->model, (int)h->all_full, tpc, smem, cols, per_sm, grid);
   if (a.scratch) {
     CU(h->d_scratch.reserve((size_t)grid * tpc * a.scratch_stride));
     a.scratch = h->d_scratch.p;
@@ -365,12 +371,12 @@ int launch_team(trpl_handle* h, KernelArgs a) {
     CU(h->d_defer.reserve(a.n_traj));
     a.defer_list = h->d_defer.p;
   }
-  const int full = (h->all_full && h->max_nx == 256) ? 1 : 0;
+  const int full = (h->all_full && h->max_nx == 128 * team_warps) ? 1 : 0;
   CU(cudaEventRecord(h->ev0, h->stream));
-  CU((cudaError_t)trpl_team_run(h->model, full, &a, sizeof(a), grid, smem, h->stream, 0));
+  CU((cudaError_t)run(h->model, full, &a, sizeof(a), grid, smem, h->stream, 0));
   h->launches += 1;
   if (a.defer_list) {
-    CU((cudaError_t)trpl_team_run(h->model, full, &a, sizeof(a), grid, smem, h->stream, 1));
+    CU((cudaError_t)run(h->model, full, &a, sizeof(a), grid, smem, h->stream, 1));
     h->launches += 1;
   }
   CU(cudaEventRecord(h->ev1, h->stream));
@@ -446,12 +452,12 @@ int launch_seulex(trpl_handle* h, KernelArgs a, bool cooperative) {
 template <int MODEL>
 int launch_npl(trpl_handle* h, const KernelArgs& a) {
   const int nx = h->max_nx;
-#ifdef TRPL_DEV_NX256_ONLY      // developer builds of tuning variants: the nx = 129..256 kernels only
-  if (nx > 128 && nx <= 256) return launch_team(h, a);
-  return fail("this developer build only holds the nx=256 instantiation");
+#ifdef TRPL_DEV_NX256_ONLY      // developer builds of tuning variants: the nx = 129..512 kernels only
+  if (nx > 128 && nx <= 512) return launch_team(h, a, nx <= 256 ? 2 : 4);
+  return fail("this developer build only holds the team instantiations (nx > 128)");
 #else
-  // more than 128 nodes: two warps per trajectory (team_kernels.cu)
-  if (nx > 128 && nx <= 256) return launch_team(h, a);
+  // more than 128 nodes: two or four warps per trajectory (team_kernels.cu, team4_kernels.cu)
+  if (nx > 128 && nx <= 512) return launch_team(h, a, nx <= 256 ? 2 : 4);
   // the padding-free instantiation exists for the headline grid (nx = 128)
   if (h->all_full && nx == 128) return launch<4, MODEL, true>(h, a);
 #ifdef TRPL_DEV_HEADLINE_ONLY   // developer builds of tuning variants: compile one instantiation only
@@ -460,7 +466,7 @@ int launch_npl(trpl_handle* h, const KernelArgs& a) {
   if (nx <= 32) return launch<1, MODEL, false>(h, a);
   if (nx <= 64) return launch<2, MODEL, false>(h, a);
   if (nx <= 128) return launch<4, MODEL, false>(h, a);
-  return fail("nx > 256 is not supported by this build");
+  return fail("nx > 512 is not supported by this build");
 #endif
 #endif
 }
@@ -530,7 +536,7 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
   int max_nx = 0;
   for (int i = 0; i < n_meas; ++i) {
     const trpl_meas_desc& m = meas[i];
-    if (m.nx < 2 || m.nx > 256) return fail("nx must be in 2..256");
+    if (m.nx < 2 || m.nx > 512) return fail("nx must be in 2..512");
     if (m.n_t < 1 || m.t_off < 0 || m.t_off + m.n_t > n_times_total) return fail("bad time slice");
     if (times[m.t_off] != 0.0) return fail("Grid error - times must start at t=0");   // sim_utils.py:271-272
     for (int k = 1; k < m.n_t; ++k)
@@ -549,9 +555,10 @@ int trpl_set_problem(trpl_handle* h, int32_t model, int32_t n_meas, const trpl_m
   }
   // all measurements of one launch share the nodes-per-lane template: nx must fit 32*NPL and
   // exceed NPL so that the two contacts sit on different lanes
-  const int npl = max_nx <= 32 ? 1 : max_nx <= 64 ? 2 : max_nx <= 128 ? 4 : 8;
+  // (more than 128 nodes: still 4 per lane, on the 64 or 128 lanes of a team)
+  const int npl = max_nx <= 32 ? 1 : max_nx <= 64 ? 2 : 4;
   for (int i = 0; i < n_meas; ++i)
-    if (meas[i].nx <= npl) return fail("mixed nx: smallest nx must exceed max_nx/32 rounded up to a power of two");
+    if (meas[i].nx <= npl) return fail("mixed nx: smallest nx must exceed the nodes per lane of the largest grid (1, 2 or 4)");
   CU(cudaSetDevice(h->device));
   CU(h->d_meas.reserve(n_meas));
   CU(h->d_times.reserve(n_times_total));

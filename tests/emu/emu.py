@@ -10,13 +10,14 @@ from metrotrpl_b200 import _capi
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libtrpl_emu.so")
 SO_TEAM = os.path.join(HERE, "libtrpl_emu_team.so")      # the same source with the two-warp team vocabulary
+SO_TEAM4 = os.path.join(HERE, "libtrpl_emu_team4.so")    # ... and with the four-warp one
 SRC = os.path.join(HERE, "trpl_emu.cpp")
 CSRC = os.path.join(HERE, "..", "..", "metrotrpl_b200", "csrc")
 
 
 def build(force=False):
     deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".h")]
-    for so, extra in ((SO, []), (SO_TEAM, ["-DTRPL_TEAM=2"])):
+    for so, extra in ((SO, []), (SO_TEAM, ["-DTRPL_TEAM=2"]), (SO_TEAM4, ["-DTRPL_TEAM=4"])):
         if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
             continue
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fopenmp", "-ffp-contract=off", "-shared",
@@ -27,11 +28,13 @@ def build(force=False):
 _libs = {}
 
 
-def lib(team=False):
-    """The host lock-step build: one warp per trajectory (nx <= 128), or the two-warp team (nx 129..256)."""
+def lib(team=0):
+    """The host lock-step build: one warp per trajectory (nx <= 128), the two-warp team (team=2, nx
+    129..256) or the four-warp team (team=4, nx 257..512)."""
+    team = int(team)
     if team not in _libs:
         build()
-        l = C.CDLL(SO_TEAM if team else SO)
+        l = C.CDLL({0: SO, 2: SO_TEAM, 4: SO_TEAM4}[team])
         dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
         l.trpl_emu_loglik_batch.argtypes = [C.c_int32, C.c_int32, C.POINTER(_capi.MeasDesc), C.c_int32,
                                             dp, dp, dp, dp, C.c_int32, dp, dp,
@@ -53,7 +56,8 @@ def loglik_batch(prob, params, aux, opts, want_curves=True, ladder=None):
     lad_out = None if ladder is None else np.empty((n_sets, prob.n_meas, lad_T.size))
     # grids of more than 128 nodes run on the two-warp team, as in the product (the extrapolation
     # integrator's generic one-warp driver keeps its 8-nodes-per-lane host instantiation)
-    team = max(int(prob.meas[i].nx) for i in range(prob.n_meas)) > 128 and not (opts.flags & _capi.OPT_EXTRAPOLATION)
+    max_nx = max(int(prob.meas[i].nx) for i in range(prob.n_meas))
+    team = 0 if (max_nx <= 128 or (opts.flags & _capi.OPT_EXTRAPOLATION)) else (2 if max_nx <= 256 else 4)
     rc = lib(team).trpl_emu_loglik_batch(prob.model, prob.n_meas, prob.meas, prob.n_times_total,
                                      p(prob.times, C.c_double), p(prob.vals, C.c_double),
                                      p(prob.uncs, C.c_double), p(prob.profiles, C.c_double), n_sets,

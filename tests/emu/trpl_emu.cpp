@@ -89,10 +89,12 @@ static int dispatch(int max_nx, int n_meas, const MeasDesc* meas, int n_times_to
 #define GO(N, F) run_all<N, MODEL, F>(n_meas, meas, n_times_total, times, vals, uncs, profiles, n_sets, params, aux, opt, logll, status, nsteps, curves, irf_mom, ladder_T, n_ladder, ladder_out)
   bool all_full = true;
   for (int i = 0; i < n_meas; ++i) if (meas[i].nx != max_nx) all_full = false;
-#if TRPL_TEAM == 2
-  // the two-warp team vocabulary (team_kernels.cu): 64 lanes x 4 nodes, the grids of 129..256 nodes
-  if (all_full && max_nx == 256) GO(4, true);
-  else if (max_nx > 128 && max_nx <= 256) GO(4, false);
+#if TRPL_TEAM >= 2
+  // the team vocabularies (team_kernels.cu / team4_kernels.cu): 64 or 128 lanes x 4 nodes, the grids
+  // of 129..256 / 257..512 nodes
+  constexpr int TOP = 128 * TRPL_TEAM;
+  if (all_full && max_nx == TOP) GO(4, true);
+  else if (max_nx > TOP / 2 && max_nx <= TOP) GO(4, false);
   else return 1;
 #else
   // (8 nodes per lane: no product kernel any more, kept for the generic one-warp extrapolation driver)

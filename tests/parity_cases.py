@@ -519,8 +519,9 @@ def check_explicit_path(backend):
 
 def check_team_grids(backend):
     """Grids of 129..256 nodes run on a team of two warps per trajectory (csrc/team_kernels.cu: 64
-    lanes x 4 nodes, 6-level reduction, values crossing the warp boundary through a mailbox).  Both
-    models, padding-free (nx = 256) and padded (nx = 160, 200) grids, TRPL and TRTS, the stiff
+    lanes x 4 nodes, 6-level reduction, values crossing the warp boundary through a mailbox), grids of
+    257..512 nodes on a team of four (team4_kernels.cu: 128 lanes, 7 levels, three boundaries).  Both
+    models, padding-free (nx = 256, 512) and padded (nx = 160, 200, 400) grids, TRPL and TRTS, the stiff
     Rosenbrock path and the explicit Runge-Kutta path, against the oracle's LSODA at tight tolerances."""
     names, units, idx = _known_units()
     t = np.linspace(0, 60, 121)
@@ -528,7 +529,7 @@ def check_team_grids(backend):
     base = dict(BASE, n0=1e8, p0=3e15, ks=4.8e-11, tauN=511, tauP=871, Cn=4.4e-29, Cp=4.4e-29)
     stiff = dict(base, mu_n=20, mu_p=20, Sf=10, Sb=10)
     nonstiff = dict(base, mu_n=0, mu_p=0, Sf=0, Sb=0, tauN=4, tauP=6, p0=1e17)
-    for nx, model in ((256, "std"), (160, "std"), (200, "traps"), (256, "traps")):
+    for nx, model in ((256, "std"), (160, "std"), (200, "traps"), (256, "traps"), (400, "std"), (512, "traps")):
         names_m = names + (["kC", "Nt", "tauE"] if model == "traps" else [])
         units_m = np.concatenate([units, [1e12, 1e-21, 1.0]]) if model == "traps" else units
         idx_m = {n: i for i, n in enumerate(names_m)}

@@ -30,7 +30,7 @@ def layouts(team=False):
     with open(src, "w") as f:
         f.write(PROGRAM % {"root": ROOT})
     exe = os.path.join(tmp, "slots")
-    subprocess.check_call(["g++", "-std=c++17"] + (["-DTRPL_TEAM=2"] if team else []) + ["-o", exe, src])
+    subprocess.check_call(["g++", "-std=c++17"] + ([f"-DTRPL_TEAM={int(team)}"] if team else []) + ["-o", exe, src])
     rows = []
     for line in subprocess.check_output([exe], text=True).strip().splitlines():
         v = [int(x) for x in line.split()]
@@ -75,7 +75,7 @@ def test_two_warp_team_layout():
     reduced system has 64 rows, hence 6 PCR levels of multipliers (26 pairs + padding); a TEAM's
     shared-memory slice is 64 lanes wide and four of them, plus the 8 KB mailbox, fit an SM."""
     for model in (0, 1):
-        r = [x for x in layouts(team=True) if x["npl"] == 4 and x["model"] == model][0]
+        r = [x for x in layouts(team=2) if x["npl"] == 4 and x["model"] == model][0]
         assert r["fac_in_tm"] == 1
         assert r["tm_count"] <= 64 and r["tm_cols"] == 256            # two CTAs per SM
         assert r["pm_tm"] + r["pm_sm"] in (26, 28) and r["pm_tm"] % 4 == 0
@@ -83,4 +83,17 @@ def test_two_warp_team_layout():
         assert r["kcap"] >= 7 * r["kstride"]
         # two CTAs per SM, two teams per CTA, 8 KB of static mailbox + 1 KB reserved per CTA
         assert 2 * (2 * r["sm_bytes"] + 8208 + 1024) <= 228 * 1024
+
+
+def test_four_warp_team_layout():
+    """nx = 257..512 (csrc/team4_kernels.cu): 128 lanes, 7 PCR levels (30 pairs of multipliers + padding),
+    one trajectory per CTA; two CTAs with their 12 KB mailboxes fit an SM."""
+    for model in (0, 1):
+        r = [x for x in layouts(team=4) if x["npl"] == 4 and x["model"] == model][0]
+        assert r["fac_in_tm"] == 1
+        assert r["tm_count"] <= 64 and r["tm_cols"] == 256
+        assert r["pm_tm"] + r["pm_sm"] in (30, 32) and r["pm_tm"] % 4 == 0
+        assert r["sm_bytes"] == r["sm_pairs"] * 2048                    # 128 lanes x 16 B per pair
+        assert r["kcap"] >= 7 * r["kstride"]
+        assert 2 * (r["sm_bytes"] + 12304 + 1024) <= 228 * 1024
 

@@ -1,4 +1,4 @@
-"""Developer helper (GPU box): race hunt for the two-warp team kernels.  The configs[3] batch (traps + IRF,
+"""Developer helper (GPU box): race hunt for the two- and four-warp team kernels.  The configs[3] batch (traps + IRF,
 nx = 256) and a padded 'std' grid (nx = 200) are launched repeatedly under random permutations of the
 parameter sets and random explicit queue orders; every launch must reproduce the first one bit for bit."""
 import os
@@ -35,6 +35,13 @@ ini2 = [2e16 * np.exp(-x / 100.0), 2e17 * np.exp(-x / 100.0), 5e15 * np.ones(200
 prob2 = _capi.pack_problem(sim2, ini2, [t] * 3, [np.full(len(t), 20.0)] * 3, [np.full(len(t), 0.05)] * 3)
 cases.append(("std nx=200 (padded)", prob2, _capi.pack_params(bench.draw_states(n_sets, seed=5), bench.IDX, bench.UNITS),
               _capi.default_aux(n_sets, 3, [1.0] * 3)))
+x4 = (np.arange(400) + 0.5) * (311.0 / 400)
+sim4 = {"lengths": [311.0] * 2, "nx": [400] * 2, "meas_types": ["TRPL", "TRTS"], "num_meas": 2}
+ini4 = [2e16 * np.exp(-x4 / 100.0), 2e17 * np.exp(-x4 / 100.0)]
+prob4 = _capi.pack_problem(sim4, ini4, [t] * 2, [np.full(len(t), 20.0)] * 2, [np.full(len(t), 0.05)] * 2)
+cases.append(("std nx=400 (padded, four-warp team)", prob4,
+              _capi.pack_params(bench.draw_states(n_sets, seed=6), bench.IDX, bench.UNITS),
+              _capi.default_aux(n_sets, 2, [1.0] * 2)))
 opts = _capi.make_opts(RTOL=1e-7)
 for label, pb, params, aux in cases:
     ctx.set_problem(pb)
