@@ -47,7 +47,7 @@ def test_irf_pass_on_uneven_measurement_times():
     print(pc.check_irf_uneven_times(backend))
 
 
-def test_two_warp_team_grids_of_129_to_256_nodes():
+def test_team_grids_of_129_to_512_nodes():
     print(pc.check_team_grids(backend))
 
 

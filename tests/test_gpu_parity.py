@@ -102,7 +102,7 @@ def test_irf_pass_on_uneven_measurement_times(ctx):
     print(pc.check_irf_uneven_times(make_backend(ctx)))
 
 
-def test_two_warp_team_grids_of_129_to_256_nodes(ctx):
+def test_team_grids_of_129_to_512_nodes(ctx):
     print(pc.check_team_grids(make_backend(ctx)))
 
 
